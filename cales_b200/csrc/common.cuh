@@ -1,0 +1,91 @@
+// Shared internals of libcales_b200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cales_b200.h"
+
+// ---- indexing of haloed Fortran arrays (0:n1+1,0:n2+1,0:n3+1) -----------------------------------
+struct Dims {
+  int n1, n2, n3;  // interior extents
+  long s1, s2;     // strides of j and k in elements: s1 = n1+2, s2 = (n1+2)*(n2+2)
+  __host__ __device__ Dims() {}
+  __host__ __device__ Dims(const int n[3]) : n1(n[0]), n2(n[1]), n3(n[2]), s1(n[0] + 2), s2((long)(n[0] + 2) * (n[1] + 2)) {}
+  __host__ __device__ long idx(int i, int j, int k) const { return i + s1 * j + s2 * (long)k; }
+  __host__ long size() const { return s2 * (n3 + 2); }
+};
+
+struct Plan {  // what fftini returns (src/fft.f90:23-143)
+  bool used = false;
+  int ng[3];
+  char bc[2][2];     // [dir][ib]
+  char c_or_f[2];
+  double normfft;
+};
+
+struct FftTables {   // twiddle tables per transform length, device resident
+  double2* w = nullptr;   // exp(-2 pi i k / n),      k = 0..n-1
+  double2* h = nullptr;   // exp(-  pi i k / (2 n)),  k = 0..n-1   (Makhoul DCT twiddles)
+};
+
+struct cales_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int diffusion = CALES_DIFF_EXPLICIT;
+  // decomposition (initmpi)
+  int ng[3], dims[2], ipencil, rank, nranks, coord[2];
+  char cbcpre[6];
+  int lo[3], hi[3], n[3];
+  int xst[3], xen[3], xsz[3], yst[3], yen[3], ysz[3], zst[3], zen[3], zsz[3];
+  int nb[6], is_bound[6];
+  // comms (comm.cu)
+  void* nccl = nullptr;                 // ncclComm_t
+  cudaStream_t comm_stream = nullptr;
+  // scratch owned by the callee (the reference's `save`d allocatables and module buffers)
+  std::map<std::string, std::pair<void*, size_t>> scratch;
+  double* red = nullptr;                // device reduction slots
+  double* red_host = nullptr;           // pinned mirror
+  double* fdev = nullptr;               // bulk forcing f(3), device resident
+  int rk_swap = 0;                      // which of the two RHS sets is "old" (rk.f90:98-100)
+  bool rk_first = true;
+  bool sgs_first = true;
+  std::vector<Plan> plans;
+  std::map<int, FftTables> tables;
+  long launches = 0;                    // kernels launched by this library (bench.py gpu_launches)
+  char err[512] = {0};
+};
+
+extern char g_cales_err[512];
+
+int cales_fail(cales_ctx* ctx, int code, const char* fmt, ...);
+void* cales_scratch(cales_ctx* ctx, const char* name, size_t bytes, bool zero_on_create = false);
+
+#define CUDA_TRY(ctx, call)                                                                        \
+  do {                                                                                              \
+    cudaError_t e_ = (call);                                                                        \
+    if (e_ != cudaSuccess) return cales_fail(ctx, CALES_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, \
+                                             cudaGetErrorString(e_));                               \
+  } while (0)
+
+#define KERNEL_CHECK(ctx) do { (ctx)->launches++; CUDA_TRY(ctx, cudaGetLastError()); } while (0)
+#define CHECK_CTX(ctx) do { if (!(ctx)) return CALES_ERR_INVALID; } while (0)
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+
+// tables indexed ib + 2*idir
+__host__ __device__ inline int tb(int ib, int idir) { return ib + 2 * idir; }
+
+// internal device-level entry points shared between translation units (no host sync)
+int k_halo_exchange(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields);
+int k_boundp(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_bound* bcp, const int nb[6],
+             const int is_bound[6], const double dl[3], const double* dzc, double* p);
+int k_boundp_multi(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_bound* bcp, const int nb[6],
+                   const int is_bound[6], const double dl[3], const double* dzc, double* const* ps, int np);
+int k_allreduce_sum(cales_ctx* ctx, double* dev, int count);
+int k_allreduce_minmax(cales_ctx* ctx, double* dev, int count, int is_max);
+FftTables* k_tables(cales_ctx* ctx, int n);

@@ -1,0 +1,311 @@
+// Batched 1-D real transforms of the Poisson/Helmholtz solver, hand-written (no cuFFT).
+// Replaces the FFTW r2r plans of the reference CPU path (src/fft.f90:23-143,176-190) and the cuFFT
+// + `signal_processing` re-ordering passes of its GPU path (src/fft.f90:247-661):
+//   PP  R2HC / HC2R             (halfcomplex order r0..r_{n/2}, i_{(n+1)/2-1}..i_1, as FFTW)
+//   NN  REDFT10 / REDFT01       (DCT-II / DCT-III, Makhoul's N-point algorithm)
+//   DD  RODFT10 / RODFT01       (DST-II / DST-III via sign flip + index reversal of the DCT)
+// all unnormalised with FFTW's factor-2 convention (find_fft, src/fft.f90:192-245).
+// One CTA stages NL lines in shared memory, packs each real line of n points into n/2 complex
+// points, runs a Stockham autosort FFT (radix 4/2/3/5/generic) between two shared buffers and
+// applies the even/odd split, the DCT twiddles, the index permutations and the final scale while
+// loading/storing, so a transform pass reads and writes every element exactly once (16 B/cell).
+// x-lines are contiguous; y-lines are handled as [NL consecutive x] x [all y] tiles so global access
+// stays coalesced without any transpose pass.
+#include <cmath>
+
+#include "common.cuh"
+
+enum { K_PP = 0, K_NN = 1, K_DD = 2 };
+
+struct FftArgs {
+  const double* in; double* out;
+  long ies, il1, il2;      // input strides: element, line index 1, line index 2
+  long oes, ol1, ol2;      // output strides
+  int n, nl1, nl2;         // transform length, number of lines along l1 / l2
+  int kind, backward;
+  double scale;
+  const double2* wm;       // exp(-2 pi i t/m), t<m   (m = n/2)
+  const double2* wn;       // exp(-2 pi i t/n), t<n
+  const double2* h4;       // exp(-pi i t/(2n)), t<=n
+  int nfac; int fac[24];   // radices of m
+};
+
+__device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cconj(double2 a) { return make_double2(a.x, -a.y); }
+// multiply by -i (forward) or +i (inverse)
+__device__ __forceinline__ double2 cmuli(double2 a, bool inv) { return inv ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }
+__device__ __forceinline__ double2 twid(const double2* __restrict__ w, int t, bool inv) {
+  double2 v = __ldg(w + t);
+  if (inv) v.y = -v.y;
+  return v;
+}
+
+// one Stockham stage of radix R over NL lines: src -> dst (both [NL][LS] complex)
+template <int R>
+__device__ __forceinline__ void stage(const double2* __restrict__ src, double2* __restrict__ dst, int NL, int LS, int m, int Ns,
+                                      const double2* __restrict__ wm, bool inv) {
+  const int nb = m / R;
+  const int tstep = m / (Ns * R);
+  for (int idx = threadIdx.x; idx < NL * nb; idx += blockDim.x) {
+    const int l = idx / nb, j = idx - l * nb;
+    const int k = j % Ns;
+    const double2* s = src + l * LS;
+    double2* d = dst + l * LS + (j - k) * R + k;
+    if (R == 2) {
+      double2 a = s[j], b = s[j + nb];
+      if (Ns > 1) b = cmul(b, twid(wm, k * tstep, inv));
+      d[0] = cadd(a, b); d[Ns] = csub(a, b);
+    } else if (R == 4) {
+      double2 a = s[j], b = s[j + nb], c = s[j + 2 * nb], e = s[j + 3 * nb];
+      if (Ns > 1) {
+        b = cmul(b, twid(wm, k * tstep, inv));
+        c = cmul(c, twid(wm, 2 * k * tstep, inv));
+        e = cmul(e, twid(wm, 3 * k * tstep, inv));
+      }
+      const double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, e), t3 = cmuli(csub(b, e), inv);
+      d[0] = cadd(t0, t2); d[Ns] = cadd(t1, t3); d[2 * Ns] = csub(t0, t2); d[3 * Ns] = csub(t1, t3);
+    } else {
+      // generic radix R (3, 5, any prime): O(R^2) DFT with table twiddles exp(-+2 pi i a q / R) = wm[(a q mod R) m/R]
+      const int rstep = m / R;
+      for (int q = 0; q < R; ++q) {
+        double2 acc = s[j];
+        for (int a = 1; a < R; ++a) {
+          double2 v = s[j + a * nb];
+          if (Ns > 1) v = cmul(v, twid(wm, a * k * tstep, inv));
+          acc = cadd(acc, cmul(v, twid(wm, ((a * q) % R) * rstep, inv)));
+        }
+        d[q * Ns] = acc;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void stage_any(int R, const double2* src, double2* dst, int NL, int LS, int m, int Ns, const double2* wm, bool inv) {
+  // runtime radix dispatch for the generic case (R prime > 5): same code path as the template's else-branch
+  const int nb = m / R, tstep = m / (Ns * R), rstep = m / R;
+  for (int idx = threadIdx.x; idx < NL * nb; idx += blockDim.x) {
+    const int l = idx / nb, j = idx - l * nb;
+    const int k = j % Ns;
+    const double2* s = src + l * LS;
+    double2* d = dst + l * LS + (j - k) * R + k;
+    for (int q = 0; q < R; ++q) {
+      double2 acc = s[j];
+      for (int a = 1; a < R; ++a) {
+        double2 v = s[j + a * nb];
+        if (Ns > 1) v = cmul(v, twid(wm, (int)(((long)a * k * tstep) % m), inv));
+        acc = cadd(acc, cmul(v, twid(wm, ((a * q) % R) * rstep, inv)));
+      }
+      d[q * Ns] = acc;
+    }
+  }
+}
+
+// position in the packed complex array (as a double index) of real sample e of a forward input line
+__device__ __forceinline__ int fwd_slot(int e, int n, int kind) {
+  if (kind == K_PP) return e;
+  return (e & 1) ? n - 1 - (e >> 1) : (e >> 1);            // Makhoul: v_j = x_2j, v_{n-1-j} = x_{2j+1}
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(256) fft_lines_k(FftArgs A, int NL, int LS) {
+  extern __shared__ double2 sm[];
+  double2* b0 = sm;
+  double2* b1 = sm + (size_t)NL * LS;
+  const int n = A.n, m = n >> 1;
+  const int l1_0 = blockIdx.x * NL, l2 = blockIdx.y;
+  const int nl = min(NL, A.nl1 - l1_0);
+  const bool inv = A.backward != 0;
+  const int kind = A.kind;
+  const double* gin = A.in + (long)l2 * A.il2 + (long)l1_0 * A.il1;
+  double* gout = A.out + (long)l2 * A.ol2 + (long)l1_0 * A.ol1;
+  // ---- load ---------------------------------------------------------------------------------------------
+  {
+    double* dst = (double*)(inv ? b1 : b0);          // forward: packed complex in b0; backward: raw reals in b1
+    const int LSD = 2 * LS;
+    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+      int l, e;
+      if (DIR == 0) { l = idx / n; e = idx - l * n; } else { e = idx / nl; l = idx - e * nl; }
+      double v = gin[(long)l * A.il1 + (long)e * A.ies];
+      int slot;
+      if (!inv) {
+        slot = fwd_slot(e, n, kind);
+        if (kind == K_DD && (e & 1)) v = -v;           // DST-II(x)_k = DCT-II((-1)^j x_j)_{n-1-k}
+      } else {
+        slot = kind == K_DD ? n - 1 - e : e;           // DST-III(a)_k = (-1)^k DCT-III(reversed a)_k
+      }
+      dst[l * LSD + slot] = v;
+    }
+  }
+  __syncthreads();
+  // ---- backward pre-stage: half spectrum -> packed complex Z (b1 reals -> b0 complex) --------------------------------
+  if (inv) {
+    const int np = m / 2 + 1;
+    for (int idx = threadIdx.x; idx < nl * np; idx += blockDim.x) {
+      const int l = idx / np, k = idx - l * np, mk = m - k;
+      const double* R = (const double*)(b1 + (size_t)l * LS);
+      double2 Xk, Xmk;
+      if (kind == K_PP) {
+        Xk = make_double2(R[k], (k > 0 && k < m) ? R[n - k] : 0.);
+        Xmk = make_double2(R[mk], (mk > 0 && mk < m) ? R[n - mk] : 0.);
+      } else {                                       // V_k = (a_k - i a_{n-k}) e^{+i pi k/(2n)}, a_n := 0
+        const double2 hk = cconj(__ldg(A.h4 + k)), hmk = cconj(__ldg(A.h4 + mk));
+        Xk = cmul(make_double2(R[k], k > 0 ? -R[n - k] : 0.), hk);
+        Xmk = cmul(make_double2(R[mk], -R[n - mk]), hmk);
+      }
+      const double2 Aa = cadd(Xk, cconj(Xmk));
+      const double2 Bb = cmul(csub(Xk, cconj(Xmk)), cconj(__ldg(A.wn + k)));
+      double2* Z = b0 + (size_t)l * LS;
+      Z[k] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
+      if (k > 0 && mk != k) Z[mk] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
+    }
+    __syncthreads();
+  }
+  // ---- complex FFT of length m (Stockham autosort, ping-pong b0 <-> b1) ------------------------------------------------
+  double2* src = b0;
+  double2* dst = b1;
+  int Ns = 1;
+  for (int s = 0; s < A.nfac; ++s) {
+    const int R = A.fac[s];
+    if (R == 4) stage<4>(src, dst, nl, LS, m, Ns, A.wm, inv);
+    else if (R == 2) stage<2>(src, dst, nl, LS, m, Ns, A.wm, inv);
+    else if (R == 3) stage<3>(src, dst, nl, LS, m, Ns, A.wm, inv);
+    else if (R == 5) stage<5>(src, dst, nl, LS, m, Ns, A.wm, inv);
+    else stage_any(R, src, dst, nl, LS, m, Ns, A.wm, inv);
+    Ns *= R;
+    __syncthreads();
+    double2* t = src; src = dst; dst = t;
+  }
+  // result is in `src`; `dst` is free
+  if (!inv) {
+    // ---- forward post-stage: Z -> X (even/odd split) -> output ordering, written as reals into dst ------------------------
+    const int np = m / 2 + 1;
+    for (int idx = threadIdx.x; idx < nl * np; idx += blockDim.x) {
+      const int l = idx / np, k = idx - l * np, mk = m - k;
+      const double2* Z = src + (size_t)l * LS;
+      double* R = (double*)(dst + (size_t)l * LS);
+      const double2 Zk = Z[k], Zmk = cconj(Z[k == 0 ? 0 : mk]);
+      const double2 E = make_double2(0.5 * (Zk.x + Zmk.x), 0.5 * (Zk.y + Zmk.y));
+      const double2 D = csub(Zk, Zmk);
+      const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);          // (Zk - conj Zmk)/(2i)
+      const double2 T = cmul(__ldg(A.wn + k), O);
+      const double2 Xk = cadd(E, T), Xmk = cconj(csub(E, T));        // X[k], X[m-k]
+      if (kind == K_PP) {
+        R[k] = Xk.x;
+        if (k > 0 && k < m) R[n - k] = Xk.y;
+        R[mk] = Xmk.x;
+        if (mk > 0 && mk < m) R[n - mk] = Xmk.y;
+      } else {
+        const double2 Yk = cmul(__ldg(A.h4 + k), Xk), Ymk = cmul(__ldg(A.h4 + mk), Xmk);
+        if (kind == K_NN) {
+          R[k] = 2. * Yk.x;
+          if (k > 0) R[n - k] = -2. * Yk.y;
+          R[mk] = 2. * Ymk.x;
+          if (mk < n && mk > 0) R[n - mk] = -2. * Ymk.y;
+        } else {                                                     // reversed order for the DST
+          R[n - 1 - k] = 2. * Yk.x;
+          if (k > 0) R[k - 1] = -2. * Yk.y;
+          R[n - 1 - mk] = 2. * Ymk.x;
+          if (mk > 0) R[mk - 1] = -2. * Ymk.y;
+        }
+      }
+    }
+    __syncthreads();
+    const int LSD = 2 * LS;
+    const double* Rb = (const double*)dst;
+    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+      int l, e;
+      if (DIR == 0) { l = idx / n; e = idx - l * n; } else { e = idx / nl; l = idx - e * nl; }
+      gout[(long)l * A.ol1 + (long)e * A.oes] = Rb[l * LSD + e] * A.scale;
+    }
+  } else {
+    // ---- backward store: z_j -> x_2j, x_2j+1 with the inverse Makhoul permutation ------------------------------------------
+    const int LSD = 2 * LS;
+    const double* Zb = (const double*)src;
+    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
+      int l, e;
+      if (DIR == 0) { l = idx / n; e = idx - l * n; } else { e = idx / nl; l = idx - e * nl; }
+      const int q = fwd_slot(e, n, kind);
+      double v = Zb[l * LSD + q];
+      if (kind == K_DD && (e & 1)) v = -v;
+      gout[(long)l * A.ol1 + (long)e * A.oes] = v * A.scale;
+    }
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------
+FftTables* k_tables(cales_ctx* ctx, int n) {
+  auto it = ctx->tables.find(n);
+  if (it != ctx->tables.end()) return &it->second;
+  // w: [0,m) exp(-2 pi i t/m) ; [m, m+n) exp(-2 pi i t/n) ; h: [0,n] exp(-pi i t/(2n)); long double on the host
+  const int m = n / 2;
+  std::vector<double2> w(m + n), h(n + 1);
+  const long double pi = acosl(-1.0L);
+  for (int t = 0; t < m; ++t) w[t] = make_double2((double)cosl(2 * pi * t / m), (double)-sinl(2 * pi * t / m));
+  for (int t = 0; t < n; ++t) w[m + t] = make_double2((double)cosl(2 * pi * t / n), (double)-sinl(2 * pi * t / n));
+  for (int t = 0; t <= n; ++t) h[t] = make_double2((double)cosl(pi * t / (2 * n)), (double)-sinl(pi * t / (2 * n)));
+  FftTables tb_;
+  if (cudaMalloc(&tb_.w, w.size() * sizeof(double2)) != cudaSuccess || cudaMalloc(&tb_.h, h.size() * sizeof(double2)) != cudaSuccess) {
+    cales_fail(ctx, CALES_ERR_NOMEM, "twiddle table allocation failed");
+    return nullptr;
+  }
+  cudaMemcpyAsync(tb_.w, w.data(), w.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
+  cudaMemcpyAsync(tb_.h, h.data(), h.size() * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);   // host vectors go out of scope
+  ctx->tables[n] = tb_;
+  return &ctx->tables[n];
+}
+
+static int kind_of(const char bc[2], char c_or_f) {
+  if (bc[0] == 'P' && bc[1] == 'P') return K_PP;
+  if (c_or_f == 'c' && bc[0] == 'N' && bc[1] == 'N') return K_NN;
+  if (c_or_f == 'c' && bc[0] == 'D' && bc[1] == 'D') return K_DD;
+  return -1;
+}
+
+// dir 0: lines along x of an array with row pitch ps1 and plane pitch ps2 (elements); dir 1: along y.
+int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
+               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale) {
+  const int kind = kind_of(bc, c_or_f);
+  if (kind < 0)
+    return cales_fail(ctx, CALES_ERR_INVALID, "transform for BC '%c%c' (%c-centred) is not implemented on the device path", bc[0], bc[1], c_or_f);
+  const int n = dir == 0 ? n1 : n2;
+  if (n < 2 || (n & 1)) return cales_fail(ctx, CALES_ERR_INVALID, "transform length %d: only even lengths are implemented", n);
+  FftTables* T = k_tables(ctx, n);
+  if (!T) return CALES_ERR_NOMEM;
+  FftArgs A;
+  A.in = in; A.out = out; A.n = n; A.kind = kind; A.backward = backward; A.scale = scale;
+  const int m = n / 2;
+  A.wm = T->w; A.wn = T->w + m; A.h4 = T->h;
+  if (dir == 0) { A.ies = 1; A.il1 = ip1; A.il2 = ip2; A.oes = 1; A.ol1 = op1; A.ol2 = op2; A.nl1 = n2; A.nl2 = n3; }
+  else { A.ies = ip1; A.il1 = 1; A.il2 = ip2; A.oes = op1; A.ol1 = 1; A.ol2 = op2; A.nl1 = n1; A.nl2 = n3; }
+  // factorise m: radix 4 first, then 2, 3, 5, then any remaining primes
+  int r = m; A.nfac = 0;
+  while (r % 4 == 0) { A.fac[A.nfac++] = 4; r /= 4; }
+  while (r % 2 == 0) { A.fac[A.nfac++] = 2; r /= 2; }
+  for (int p = 3; r > 1; p += 2)
+    while (r % p == 0) { A.fac[A.nfac++] = p; r /= p; if (A.nfac >= 23) break; }
+  if (m == 1) A.nfac = 0;
+  const int LS = m + 1;
+  const size_t per_line = 2 * (size_t)LS * sizeof(double2);
+  int NL = dir == 0 ? 16 : 16;
+  while (NL > 1 && NL * per_line > 96 * 1024) NL >>= 1;
+  if (NL * per_line > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "transform length %d exceeds the shared-memory line buffer", n);
+  const size_t sh = NL * per_line;
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[dir]) {
+    cudaFuncSetAttribute(dir == 0 ? fft_lines_k<0> : fft_lines_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set[dir] = true;
+  }
+  dim3 g(cdiv(A.nl1, NL), A.nl2);
+  if (dir == 0) fft_lines_k<0><<<g, 256, sh, ctx->stream>>>(A, NL, LS);
+  else fft_lines_k<1><<<g, 256, sh, ctx->stream>>>(A, NL, LS);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
+extern "C" int cales_fft_lines(cales_ctx* ctx, const int n[3], int dir, const char bc[2], char c_or_f, int backward, double* a) {
+  CHECK_CTX(ctx);
+  return k_fft_pass(ctx, dir, bc, c_or_f, backward, n[0], n[1], n[2], a, n[0], (long)n[0] * n[1], a, n[0], (long)n[0] * n[1], 1.0);
+}

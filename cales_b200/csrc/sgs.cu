@@ -1,0 +1,491 @@
+// Sub-grid-scale eddy viscosity.
+//   cmpt_sgs     src/sgs.f90:21-386   ('none', 'smag' 69-152 with van Driest damping, 'dsmag' 153-380)
+//   strain_rate  src/sgs.f90:1019-1110   filter3d 616-680   extrapolate 682-767   cmpt_alph2 769-822
+//   interpolate  850-870                 ave1d_channel 433-538 (the hard-wired `_CHANNEL` average, sgs.f90:8)
+// The dynamic procedure keeps the reference's operation order (Appendix B of SURVEY.md) but works on
+// batches: one halo exchange + ghost fill for the 7 (then 3) cell-centred arrays, one launch for the six
+// products, one for the six extrapolations and one for the six 27-point filters, the Germano contraction
+// and the x-y plane sums fused in one kernel, and the plane average consumed on the device.
+#include "common.cuh"
+#include "reduce.cuh"
+
+#define BX 64
+#define BY 4
+#define CSMAG 0.11
+#define BIG 1.7976931348623157e308
+
+struct Ptr6 { double* p[6]; };
+struct CPtr6 { const double* p[6]; };
+
+static inline int pick_kc(int ni, int nj, int nk) {
+  long cols = (long)cdiv(ni, BX) * cdiv(nj, BY);
+  int kc = nk;
+  while (kc > 8 && cols * cdiv(nk, kc) < 148 * 8) kc = (kc + 1) / 2;
+  return kc;
+}
+
+// ---- strain rate (sgs.f90:1019-1110) -----------------------------------------------------------------------------
+template <int SIJ>
+__global__ void __launch_bounds__(BX* BY) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
+                                                    const double* __restrict__ dzfi, const double* __restrict__ u,
+                                                    const double* __restrict__ v, const double* __restrict__ w,
+                                                    double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > d.n1 || j > d.n2) return;
+  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  const long s1 = d.s1, s2 = d.s2;
+  long c = d.idx(i, j, k0);
+  for (int k = k0; k <= k1; ++k, c += s2) {
+    const double u_mcm = u[c - 1 - s2], u_ccm = u[c - s2], u_mmc = u[c - 1 - s1], u_cmc = u[c - s1], u_mcc = u[c - 1], u_ccc = u[c],
+                 u_mpc = u[c - 1 + s1], u_cpc = u[c + s1], u_mcp = u[c - 1 + s2], u_ccp = u[c + s2];
+    const double v_cmm = v[c - s1 - s2], v_ccm = v[c - s2], v_mmc = v[c - 1 - s1], v_cmc = v[c - s1], v_pmc = v[c + 1 - s1],
+                 v_mcc = v[c - 1], v_ccc = v[c], v_pcc = v[c + 1], v_cmp = v[c - s1 + s2], v_ccp = v[c + s2];
+    const double w_cmm = w[c - s1 - s2], w_mcm = w[c - 1 - s2], w_ccm = w[c - s2], w_pcm = w[c + 1 - s2], w_cpm = w[c + s1 - s2],
+                 w_cmc = w[c - s1], w_mcc = w[c - 1], w_ccc = w[c], w_pcc = w[c + 1], w_cpc = w[c + s1];
+    const double dzci_k = dzci[k], dzci_km = dzci[k - 1];
+    const double s11 = (u_ccc - u_mcc) * dxi;
+    const double s22 = (v_ccc - v_cmc) * dyi;
+    const double s33 = (w_ccc - w_ccm) * dzfi[k];
+    const double s12 = .125 * ((u_cpc - u_ccc) * dyi + (v_pcc - v_ccc) * dxi + (u_ccc - u_cmc) * dyi + (v_pmc - v_cmc) * dxi +
+                               (u_mpc - u_mcc) * dyi + (v_ccc - v_mcc) * dxi + (u_mcc - u_mmc) * dyi + (v_cmc - v_mmc) * dxi);
+    const double s13 = .125 * ((u_ccp - u_ccc) * dzci_k + (w_pcc - w_ccc) * dxi + (u_ccc - u_ccm) * dzci_km + (w_pcm - w_ccm) * dxi +
+                               (u_mcp - u_mcc) * dzci_k + (w_ccc - w_mcc) * dxi + (u_mcc - u_mcm) * dzci_km + (w_ccm - w_mcm) * dxi);
+    const double s23 = .125 * ((v_ccp - v_ccc) * dzci_k + (w_cpc - w_ccc) * dyi + (v_ccc - v_ccm) * dzci_km + (w_cpm - w_ccm) * dyi +
+                               (v_cmp - v_cmc) * dzci_k + (w_ccc - w_cmc) * dyi + (v_cmc - v_cmm) * dzci_km + (w_ccm - w_cmm) * dyi);
+    const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
+    s0[c] = s;
+    if (SIJ) {
+      sij.p[0][c] = s11; sij.p[1][c] = s22; sij.p[2][c] = s33; sij.p[3][c] = s12; sij.p[4][c] = s13; sij.p[5][c] = s23;
+      if (s0copy) s0copy[c] = s;
+    }
+  }
+}
+
+static int strain_launch(cales_ctx* ctx, const int n[3], const double dli[3], const double* dzci, const double* dzfi, const double* u,
+                         const double* v, const double* w, double* s0, double* const* sij, double* s0copy) {
+  Dims d(n);
+  const int kc = pick_kc(n[0], n[1], n[2]);
+  dim3 g(cdiv(n[0], BX), cdiv(n[1], BY), cdiv(n[2], kc)), b(BX, BY);
+  Ptr6 P;
+  for (int m = 0; m < 6; ++m) P.p[m] = sij ? sij[m] : nullptr;
+  if (sij) strain_k<1><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, s0copy, kc);
+  else strain_k<0><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, nullptr, kc);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
+extern "C" int cales_strain_rate(cales_ctx* ctx, const int n[3], const double dli[3], const double* dzci, const double* dzfi,
+                                 const double* u, const double* v, const double* w, double* s0, double* sij) {
+  CHECK_CTX(ctx);
+  Dims d(n);
+  double* ps[6];
+  for (int m = 0; m < 6; ++m) ps[m] = sij ? sij + m * d.size() : nullptr;
+  return strain_launch(ctx, n, dli, dzci, dzfi, u, v, w, s0, sij ? ps : nullptr, nullptr);
+}
+
+// ---- filter3d (sgs.f90:616-680), NF arrays per launch (blockIdx.z / nkb selects the array) ---------------------------
+__global__ void __launch_bounds__(BX* BY) filter3d_k(Dims d, CPtr6 in, Ptr6 out, int kc, int nkb) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > d.n1 || j > d.n2) return;
+  const int f = blockIdx.z / nkb, kb = blockIdx.z - f * nkb;
+  const int k0 = kb * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  const double* __restrict__ p = in.p[f];
+  double* __restrict__ pf = out.p[f];
+  const long s1 = d.s1, s2 = d.s2;
+  long c = d.idx(i, j, k0);
+  for (int k = k0; k <= k1; ++k, c += s2) {
+#define Q(di, dj, dk) p[c + (di) + (dj) * s1 + (dk) * s2]
+    pf[c] = (8. * Q(0, 0, 0) +
+             4. * (Q(-1, 0, 0) + Q(0, -1, 0) + Q(0, 0, -1) + Q(1, 0, 0) + Q(0, 1, 0) + Q(0, 0, 1)) +
+             2. * (Q(0, -1, -1) + Q(-1, 0, -1) + Q(-1, -1, 0) + Q(0, 1, -1) + Q(1, 0, -1) + Q(1, -1, 0) +
+                   Q(0, -1, 1) + Q(-1, 0, 1) + Q(-1, 1, 0) + Q(0, 1, 1) + Q(1, 0, 1) + Q(1, 1, 0)) +
+             1. * (Q(-1, -1, -1) + Q(1, -1, -1) + Q(-1, 1, -1) + Q(1, 1, -1) + Q(-1, -1, 1) + Q(1, -1, 1) + Q(-1, 1, 1) + Q(1, 1, 1))) / 64.;
+#undef Q
+  }
+}
+
+static int filter_launch(cales_ctx* ctx, const int n[3], double* const* in, double* const* out, int nf) {
+  Dims d(n);
+  const int kc = pick_kc(n[0], n[1], n[2]);
+  const int nkb = cdiv(n[2], kc);
+  CPtr6 I; Ptr6 O;
+  for (int m = 0; m < nf; ++m) { I.p[m] = in[m]; O.p[m] = out[m]; }
+  filter3d_k<<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), nkb * nf), dim3(BX, BY), 0, ctx->stream>>>(d, I, O, kc, nkb);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
+extern "C" int cales_filter3d(cales_ctx* ctx, const int n[3], const double* p, double* pf) {
+  CHECK_CTX(ctx);
+  double* in[1] = {(double*)p};
+  double* out[1] = {pf};
+  return filter_launch(ctx, n, in, out, 1);
+}
+
+// ---- extrapolate (sgs.f90:682-767): one launch per direction for up to 6 arrays ---------------------------------------
+struct ExTask { double* p; int lo, hi; };   // lo/hi: extrapolate the lower/upper ghost plane of this direction
+struct ExBatch { ExTask t[6]; int nt, idir; const double* dzci; int use_factor; };
+
+__global__ void __launch_bounds__(256) extrap_k(Dims d, ExBatch b) {
+  const ExTask& t = b.t[blockIdx.z];
+  const int idir = b.idir;
+  const int m1 = idir == 0 ? d.n2 + 2 : d.n1 + 2, m2 = idir == 2 ? d.n2 + 2 : d.n3 + 2;
+  const int a = blockIdx.x * 64 + threadIdx.x, c = blockIdx.y * 4 + threadIdx.y;
+  if (a >= m1 || c >= m2) return;
+  const long sn = idir == 0 ? 1 : idir == 1 ? d.s1 : d.s2;
+  const long base = idir == 0 ? d.idx(0, a, c) : idir == 1 ? d.idx(a, 0, c) : d.idx(a, c, 0);
+  const int n = idir == 0 ? d.n1 : idir == 1 ? d.n2 : d.n3;
+  double* p = t.p;
+  double f0 = 1., f1 = 1.;
+  if (idir == 2 && b.use_factor) {                       // lwm variant: factor0 = dzc(0)*dzci(1), factor1 = dzc(n3)*dzci(n3-1)
+    f0 = (1. / b.dzci[0]) * b.dzci[1];
+    f1 = (1. / b.dzci[n]) * b.dzci[n - 1];
+  }
+#define P(q) p[base + sn * (long)(q)]
+  if (idir < 2) {
+    if (t.lo) P(0) = 2. * P(1) - P(2);
+    if (t.hi) P(n + 1) = 2. * P(n) - P(n - 1);
+  } else {
+    if (t.lo) P(0) = (1. + f0) * P(1) - f0 * P(2);
+    if (t.hi) P(n + 1) = (1. + f1) * P(n) - f1 * P(n - 1);
+  }
+#undef P
+}
+
+// is_done(ib,idir) per array: mode 0 = cbc variant (D walls), mode 1 = lwm variant (wall-model faces)
+static int extrap_launch(cales_ctx* ctx, const int n[3], const int is_bound[6], const double* dzci, double* const* ps, const int* ifaces,
+                         int np, int mode, const char* cbc, const int* lwm) {
+  Dims d(n);
+  for (int idir = 0; idir < 3; ++idir) {
+    ExBatch b; b.nt = 0; b.idir = idir; b.dzci = dzci; b.use_factor = mode == 1;
+    for (int f = 0; f < np; ++f) {
+      int done[2];
+      for (int ib = 0; ib < 2; ++ib) {
+        const bool wall = mode == 0 ? cbc[ib + 2 * idir + 6 * idir] == 'D' : lwm[tb(ib, idir)] != 0;
+        done[ib] = is_bound[tb(ib, idir)] && wall && ifaces[f] != idir + 1;
+      }
+      if (done[0] || done[1]) { b.t[b.nt].p = ps[f]; b.t[b.nt].lo = done[0]; b.t[b.nt].hi = done[1]; b.nt++; }
+    }
+    if (b.nt == 0) continue;
+    const int m1 = idir == 0 ? n[1] + 2 : n[0] + 2, m2 = idir == 2 ? n[1] + 2 : n[2] + 2;
+    extrap_k<<<dim3(cdiv(m1, 64), cdiv(m2, 4), b.nt), dim3(64, 4), 0, ctx->stream>>>(d, b);
+    KERNEL_CHECK(ctx);
+  }
+  return CALES_OK;
+}
+
+// ---- Smagorinsky + van Driest (sgs.f90:98-152) -------------------------------------------------------------------------
+struct SmagArgs {
+  double is_wall[6];
+  double dl0, dl1, l2, dxi, dyi, visc;
+  int any_wall;
+};
+
+__global__ void __launch_bounds__(BX* BY) smag_k(Dims d, SmagArgs A, const double* __restrict__ zc, const double* __restrict__ dzf,
+                                                  const double* __restrict__ dzci, const double* __restrict__ u,
+                                                  const double* __restrict__ v, const double* __restrict__ w,
+                                                  const double* __restrict__ s0, double* __restrict__ visct, int kc) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > d.n1 || j > d.n2) return;
+  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  const double visci = 1. / A.visc;
+  const double one_third = 1. / 3.;
+  const int n1 = d.n1, n2 = d.n2, n3 = d.n3;
+  for (int k = k0; k <= k1; ++k) {
+    double fd = 1.;
+    if (A.any_wall) {
+      double dw[6];
+      dw[0] = A.dl0 * (i - 0.5); dw[1] = A.dl0 * (n1 - i + 0.5);
+      dw[2] = A.dl1 * (j - 0.5); dw[3] = A.dl1 * (n2 - j + 0.5);
+      dw[4] = zc[k]; dw[5] = A.l2 - zc[k];
+      int loc = 0;
+      double dw_min = BIG;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        dw[q] = dw[q] * A.is_wall[q] + BIG * (1. - A.is_wall[q]);
+        if (q == 0 || dw[q] < dw_min) { dw_min = dw[q]; loc = q; }     // minloc: first minimum
+      }
+      double t1, t2, tauw_s;
+#define U(ii, jj, kk) u[d.idx(ii, jj, kk)]
+#define V(ii, jj, kk) v[d.idx(ii, jj, kk)]
+#define W(ii, jj, kk) w[d.idx(ii, jj, kk)]
+      if (loc == 0) {
+        t1 = V(1, j, k) - V(0, j, k) + V(1, j - 1, k) - V(0, j - 1, k);
+        t2 = W(1, j, k) - W(0, j, k) + W(1, j, k - 1) - W(0, j, k - 1);
+        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
+      } else if (loc == 1) {
+        t1 = V(n1, j, k) - V(n1 + 1, j, k) + V(n1, j - 1, k) - V(n1 + 1, j - 1, k);
+        t2 = W(n1, j, k) - W(n1 + 1, j, k) + W(n1, j, k - 1) - W(n1 + 1, j, k - 1);
+        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
+      } else if (loc == 2) {
+        t1 = U(i, 1, k) - U(i, 0, k) + U(i - 1, 1, k) - U(i - 1, 0, k);
+        t2 = W(i, 1, k) - W(i, 0, k) + W(i, 1, k - 1) - W(i, 0, k - 1);
+        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
+      } else if (loc == 3) {
+        t1 = U(i, n2, k) - U(i, n2 + 1, k) + U(i - 1, n2, k) - U(i - 1, n2 + 1, k);
+        t2 = W(i, n2, k) - W(i, n2 + 1, k) + W(i, n2, k - 1) - W(i, n2 + 1, k - 1);
+        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
+      } else if (loc == 4) {
+        t1 = U(i, j, 1) - U(i, j, 0) + U(i - 1, j, 1) - U(i - 1, j, 0);
+        t2 = V(i, j, 1) - V(i, j, 0) + V(i, j - 1, 1) - V(i, j - 1, 0);
+        tauw_s = sqrt(t1 * t1 + t2 * t2) * dzci[0];
+      } else {
+        t1 = U(i, j, n3) - U(i, j, n3 + 1) + U(i - 1, j, n3) - U(i - 1, j, n3 + 1);
+        t2 = V(i, j, n3) - V(i, j, n3 + 1) + V(i, j - 1, n3) - V(i, j - 1, n3 + 1);
+        tauw_s = sqrt(t1 * t1 + t2 * t2) * dzci[n3];
+      }
+#undef U
+#undef V
+#undef W
+      tauw_s = 0.5 * A.visc * tauw_s;
+      const double dw_plus = dw_min * sqrt(tauw_s) * visci;
+      fd = 1. - exp(-dw_plus / 25.);
+    }
+    const double del = pow(A.dl0 * A.dl1 * dzf[k], one_third);
+    const double t = CSMAG * del * fd;
+    const long c = d.idx(i, j, k);
+    visct[c] = t * t * s0[c];
+  }
+}
+
+// ---- dsmag building blocks ------------------------------------------------------------------------------------------------
+__global__ void copy3_k(long n, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                        double* __restrict__ da, double* __restrict__ db, double* __restrict__ dc) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) { da[i] = a[i]; db[i] = b[i]; dc[i] = c[i]; }
+}
+
+// wk(m) = s0*sij(m) over the full index range (sgs.f90:198-210)
+__global__ void prod_s_k(long n, const double* __restrict__ s0, CPtr6 sij, Ptr6 wk) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double s = s0[i];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) wk.p[m][i] = s * sij.p[m][i];
+  }
+}
+
+// wk = (uc*uc, vc*vc, wc*wc, uc*vc, uc*wc, vc*wc) over the full range (sgs.f90:283-295)
+__global__ void prod_u_k(long n, const double* __restrict__ uc, const double* __restrict__ vc, const double* __restrict__ wc, Ptr6 wk) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double a = uc[i], b = vc[i], c = wc[i];
+    wk.p[0][i] = a * a; wk.p[1][i] = b * b; wk.p[2][i] = c * c; wk.p[3][i] = a * b; wk.p[4][i] = a * c; wk.p[5][i] = b * c;
+  }
+}
+
+struct Alph { int wall[6]; };   // is_bound && cbc(ib,idir,idir)=='D' (cmpt_alph2, sgs.f90:783-816)
+
+// mij = 2*(mij - alph2*s0*sij) interior (sgs.f90:262-272) fused with interpolate (sgs.f90:850-870)
+__global__ void __launch_bounds__(BX* BY) mij_interp_k(Dims d, Alph al, const double* __restrict__ s0, CPtr6 sij, Ptr6 mij,
+                                                        const double* __restrict__ u, const double* __restrict__ v,
+                                                        const double* __restrict__ w, double* __restrict__ uc,
+                                                        double* __restrict__ vc, double* __restrict__ wc, int kc) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > d.n1 || j > d.n2) return;
+  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  long c = d.idx(i, j, k0);
+  for (int k = k0; k <= k1; ++k, c += d.s2) {
+    double alph2 = 4.00;
+    if ((al.wall[0] && i == 1) || (al.wall[1] && i == d.n1) || (al.wall[2] && j == 1) || (al.wall[3] && j == d.n2) ||
+        (al.wall[4] && k == 1) || (al.wall[5] && k == d.n3)) alph2 = 2.52;
+    const double s = s0[c];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) mij.p[m][c] = 2. * (mij.p[m][c] - alph2 * s * sij.p[m][c]);
+    uc[c] = 0.5 * (u[c] + u[c - 1]);
+    vc[c] = 0.5 * (v[c] + v[c - d.s1]);
+    wc[c] = 0.5 * (w[c] + w[c - d.s2]);
+  }
+}
+
+// Germano contraction (sgs.f90:328-358) fused with the x-y plane sums of ave1d_channel (sgs.f90:455-474):
+// one CTA per (k, x-y tile); per-plane partials are folded in a fixed order afterwards.
+__global__ void __launch_bounds__(BX* BY) contract_k(Dims d, CPtr6 mij, CPtr6 lij, const double* __restrict__ uf,
+                                                      const double* __restrict__ vf, const double* __restrict__ wf,
+                                                      double* __restrict__ part, int ntile) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1, k = blockIdx.z + 1;
+  double ml = 0., mm = 0.;
+  if (i <= d.n1 && j <= d.n2) {
+    const long c = d.idx(i, j, k);
+    double M[6], L[6];
+#pragma unroll
+    for (int m = 0; m < 6; ++m) { M[m] = mij.p[m][c]; L[m] = lij.p[m][c]; }
+    const double a = uf[c], b = vf[c], e = wf[c];
+    L[0] = L[0] - a * a; L[1] = L[1] - b * b; L[2] = L[2] - e * e;
+    L[3] = L[3] - a * b; L[4] = L[4] - a * e; L[5] = L[5] - b * e;
+    ml = M[0] * L[0] + M[1] * L[1] + M[2] * L[2] + (M[3] * L[3] + M[4] * L[4] + M[5] * L[5]) * 2.;
+    mm = M[0] * M[0] + M[1] * M[1] + M[2] * M[2] + (M[3] * M[3] + M[4] * M[4] + M[5] * M[5]) * 2.;
+  }
+  ml = block_sum<BX * BY>(ml);
+  mm = block_sum<BX * BY>(mm);
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int tile = blockIdx.x + gridDim.x * blockIdx.y;
+    part[(2 * (k - 1) + 0) * (long)ntile + tile] = ml;
+    part[(2 * (k - 1) + 1) * (long)ntile + tile] = mm;
+  }
+}
+
+// fold tile partials of plane k into p1d[kg] (kg = global k index), scaled by grid_area_ratio
+__global__ void plane_fold_k(const double* __restrict__ part, int ntile, int n3, int lo3, int ng3, double gar, double* __restrict__ p1d) {
+  const int q = blockIdx.x;          // q = 2*(k-1)+which
+  double v = 0.;
+  for (int t = threadIdx.x; t < ntile; t += 256) v = v + part[q * (long)ntile + t];
+  v = block_sum<256>(v);
+  if (threadIdx.x == 0) {
+    const int k = q / 2, which = q % 2;
+    p1d[which * ng3 + (lo3 - 1 + k)] = v * gar;
+  }
+}
+
+// visct = max(visct*<ML>/<MM>, 0) (sgs.f90:372-380)
+__global__ void __launch_bounds__(BX* BY) dsmag_final_k(Dims d, const double* __restrict__ p1d, int ng3, int lo3, double* __restrict__ visct, int kc) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > d.n1 || j > d.n2) return;
+  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  long c = d.idx(i, j, k0);
+  for (int k = k0; k <= k1; ++k, c += d.s2) {
+    const double vt = visct[c] * p1d[lo3 - 1 + k - 1] / p1d[ng3 + lo3 - 1 + k - 1];
+    visct[c] = fmax(vt, 0.);
+  }
+}
+
+// ---- cmpt_sgs ---------------------------------------------------------------------------------------------------------------
+extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3], const int ng[3], const int lo[3],
+                              const int hi[3], const char cbcvel[18], const char cbcsgs[6], const cales_bound* bcs,
+                              const int nb[6], const int is_bound[6], const int lwm[6], const double l[3], const double dl[3],
+                              const double dli[3], const double* zc, const double* zf, const double* dzc, const double* dzf,
+                              const double* dzci, const double* dzfi, double visc, double h, const int index_wm[6],
+                              const double* u, const double* v, const double* w, const cales_bound* bcuf,
+                              const cales_bound* bcvf, const cales_bound* bcwf, const cales_bound* bcu_mag,
+                              const cales_bound* bcv_mag, const cales_bound* bcw_mag, double* visct) {
+  CHECK_CTX(ctx);
+  (void)hi;
+  Dims d(n);
+  const size_t fb = (size_t)d.size() * sizeof(double);
+  const int kc = pick_kc(n[0], n[1], n[2]);
+  dim3 g(cdiv(n[0], BX), cdiv(n[1], BY), cdiv(n[2], kc)), b(BX, BY);
+  int rc;
+  if (!strcmp(sgstype, "none")) {
+    if (ctx->sgs_first) { ctx->sgs_first = false; CUDA_TRY(ctx, cudaMemsetAsync(visct, 0, fb, ctx->stream)); }
+    return CALES_OK;
+  }
+  bool any_wm = false;
+  for (int q = 0; q < 6; ++q) any_wm |= (is_bound[q] && lwm[q] != 0);
+  const int ifaces3[3] = {1, 2, 3}, ifaces0[6] = {0, 0, 0, 0, 0, 0};
+  const long nflat = d.size();
+  const int gflat = 148 * 8;
+  if (!strcmp(sgstype, "smag")) {
+    double* s0 = (double*)cales_scratch(ctx, "sgs_s0", fb, true);
+    if (!s0) return CALES_ERR_NOMEM;
+    const double *us = u, *vs = v, *ws = w;
+    if (any_wm) {                                            // sgs.f90:84-90: copies only matter where extrapolate acts
+      double* wk[3];
+      static const char* nm[3] = {"sgs_wk0", "sgs_wk1", "sgs_wk2"};
+      for (int c = 0; c < 3; ++c) if (!(wk[c] = (double*)cales_scratch(ctx, nm[c], fb))) return CALES_ERR_NOMEM;
+      copy3_k<<<gflat, 256, 0, ctx->stream>>>(nflat, u, v, w, wk[0], wk[1], wk[2]);
+      KERNEL_CHECK(ctx);
+      if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces3, 3, 1, nullptr, lwm))) return rc;
+      us = wk[0]; vs = wk[1]; ws = wk[2];
+    }
+    if ((rc = strain_launch(ctx, n, dli, dzci, dzfi, us, vs, ws, s0, nullptr, nullptr))) return rc;
+    SmagArgs A;
+    A.any_wall = 0;
+    for (int idir = 0; idir < 3; ++idir)
+      for (int ib = 0; ib < 2; ++ib) {
+        const bool wall = is_bound[tb(ib, idir)] && cbcvel[ib + 2 * idir + 6 * idir] == 'D';
+        A.is_wall[2 * idir + ib] = wall ? 1. : 0.;
+        A.any_wall |= wall;
+      }
+    A.dl0 = dl[0]; A.dl1 = dl[1]; A.l2 = l[2]; A.dxi = dli[0]; A.dyi = dli[1]; A.visc = visc;
+    smag_k<<<g, b, 0, ctx->stream>>>(d, A, zc, dzf, dzci, u, v, w, s0, visct, kc);
+    KERNEL_CHECK(ctx);
+    return CALES_OK;
+  }
+  if (strcmp(sgstype, "dsmag")) return cales_fail(ctx, CALES_ERR_INVALID, "unknown SGS model '%s'", sgstype);
+  // ---- dynamic Smagorinsky (sgs.f90:153-380) ----
+  static const char* nm1[7] = {"sgs_s0", "sgs_uc", "sgs_vc", "sgs_wc", "sgs_uf", "sgs_vf", "sgs_wf"};
+  double* a1[7];
+  for (int q = 0; q < 7; ++q) if (!(a1[q] = (double*)cales_scratch(ctx, nm1[q], fb, true))) return CALES_ERR_NOMEM;
+  double *s0 = a1[0], *uc = a1[1], *vc = a1[2], *wc = a1[3], *uf = a1[4], *vf = a1[5], *wf = a1[6];
+  double *wk[6], *sij[6], *mij[6];
+  static const char* nwk[6] = {"sgs_wk0", "sgs_wk1", "sgs_wk2", "sgs_wk3", "sgs_wk4", "sgs_wk5"};
+  static const char* nsij[6] = {"sgs_sij0", "sgs_sij1", "sgs_sij2", "sgs_sij3", "sgs_sij4", "sgs_sij5"};
+  static const char* nmij[6] = {"sgs_mij0", "sgs_mij1", "sgs_mij2", "sgs_mij3", "sgs_mij4", "sgs_mij5"};
+  for (int m = 0; m < 6; ++m) {
+    wk[m] = (double*)cales_scratch(ctx, nwk[m], fb, true);
+    sij[m] = (double*)cales_scratch(ctx, nsij[m], fb, true);
+    mij[m] = (double*)cales_scratch(ctx, nmij[m], fb, true);
+    if (!wk[m] || !sij[m] || !mij[m]) return CALES_ERR_NOMEM;
+  }
+  CPtr6 Csij, Cmij; Ptr6 Pwk, Pmij;
+  for (int m = 0; m < 6; ++m) { Csij.p[m] = sij[m]; Cmij.p[m] = mij[m]; Pwk.p[m] = wk[m]; Pmij.p[m] = mij[m]; }
+  // (2)-(3) strain rate of the (wall-model extrapolated) velocity; visct <- s0      sgs.f90:173-185
+  const double *us = u, *vs = v, *ws = w;
+  if (any_wm) {
+    copy3_k<<<gflat, 256, 0, ctx->stream>>>(nflat, u, v, w, wk[0], wk[1], wk[2]);
+    KERNEL_CHECK(ctx);
+    if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces3, 3, 1, nullptr, lwm))) return rc;
+    us = wk[0]; vs = wk[1]; ws = wk[2];
+  }
+  if ((rc = strain_launch(ctx, n, dli, dzci, dzfi, us, vs, ws, s0, sij, visct))) return rc;
+  // (4) ghost cells of s0 and sij                                                        sgs.f90:191-197
+  {
+    double* ps[7] = {s0, sij[0], sij[1], sij[2], sij[3], sij[4], sij[5]};
+    if ((rc = k_boundp_multi(ctx, cbcsgs, n, bcs, nb, is_bound, dl, dzc, ps, 7))) return rc;
+  }
+  // (5) Mij first part: filter(s0*sij)                                                   sgs.f90:198-223
+  prod_s_k<<<gflat, 256, 0, ctx->stream>>>(nflat, s0, Csij, Pwk);
+  KERNEL_CHECK(ctx);
+  if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces0, 6, 0, cbcvel, nullptr))) return rc;
+  if ((rc = filter_launch(ctx, n, wk, mij, 6))) return rc;
+  // (6) filtered velocity                                                                sgs.f90:225-235
+  copy3_k<<<gflat, 256, 0, ctx->stream>>>(nflat, u, v, w, wk[0], wk[1], wk[2]);
+  KERNEL_CHECK(ctx);
+  if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces3, 3, 0, cbcvel, nullptr))) return rc;
+  {
+    double* out[3] = {uf, vf, wf};
+    if ((rc = filter_launch(ctx, n, wk, out, 3))) return rc;
+  }
+  // (7) BCs on the filtered velocity, strain rate of it                                   sgs.f90:256-261
+  if ((rc = cales_bounduvw(ctx, cbcvel, n, bcuf, bcvf, bcwf, bcu_mag, bcv_mag, bcw_mag, nb, is_bound, lwm, l, dl, zc, zf, dzc, dzf,
+                           visc, h, index_wm, 0, 0, uf, vf, wf))) return rc;
+  if (any_wm) {
+    double* ps[3] = {uf, vf, wf};
+    if ((rc = extrap_launch(ctx, n, is_bound, dzci, ps, ifaces3, 3, 1, nullptr, lwm))) return rc;
+  }
+  if ((rc = strain_launch(ctx, n, dli, dzci, dzfi, uf, vf, wf, s0, sij, nullptr))) return rc;
+  // (8)-(9a) Mij second part and cell-centred velocity                                     sgs.f90:262-277
+  Alph al;
+  for (int idir = 0; idir < 3; ++idir)
+    for (int ib = 0; ib < 2; ++ib) al.wall[2 * idir + ib] = is_bound[tb(ib, idir)] && cbcvel[ib + 2 * idir + 6 * idir] == 'D';
+  mij_interp_k<<<g, b, 0, ctx->stream>>>(d, al, s0, Csij, Pmij, u, v, w, uc, vc, wc, kc);
+  KERNEL_CHECK(ctx);
+  {
+    double* ps[3] = {uc, vc, wc};
+    if ((rc = k_boundp_multi(ctx, cbcsgs, n, bcs, nb, is_bound, dl, dzc, ps, 3))) return rc;   // sgs.f90:280-282
+  }
+  // (9b) Lij (stored in sij)                                                               sgs.f90:283-315
+  prod_u_k<<<gflat, 256, 0, ctx->stream>>>(nflat, uc, vc, wc, Pwk);
+  KERNEL_CHECK(ctx);
+  if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces0, 6, 0, cbcvel, nullptr))) return rc;
+  if ((rc = filter_launch(ctx, n, wk, sij, 6))) return rc;
+  {
+    double* ps[3] = {uc, vc, wc};
+    double* out[3] = {uf, vf, wf};
+    if ((rc = extrap_launch(ctx, n, is_bound, dzci, ps, ifaces0, 3, 0, cbcvel, nullptr))) return rc;
+    if ((rc = filter_launch(ctx, n, ps, out, 3))) return rc;
+  }
+  // (10)-(11) contraction + x-y plane averages                                             sgs.f90:328-364
+  const int ntile = cdiv(n[0], BX) * cdiv(n[1], BY);
+  double* part = (double*)cales_scratch(ctx, "sgs_part", (size_t)2 * n[2] * ntile * sizeof(double));
+  double* p1d = (double*)cales_scratch(ctx, "sgs_p1d", (size_t)2 * ng[2] * sizeof(double));
+  if (!part || !p1d) return CALES_ERR_NOMEM;
+  CUDA_TRY(ctx, cudaMemsetAsync(p1d, 0, (size_t)2 * ng[2] * sizeof(double), ctx->stream));
+  contract_k<<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), n[2]), b, 0, ctx->stream>>>(d, Cmij, Csij, uf, vf, wf, part, ntile);
+  KERNEL_CHECK(ctx);
+  const double gar = dl[0] * dl[1] / (l[0] * l[1]);
+  plane_fold_k<<<2 * n[2], 256, 0, ctx->stream>>>(part, ntile, n[2], lo[2], ng[2], gar, p1d);
+  KERNEL_CHECK(ctx);
+  if ((rc = k_allreduce_sum(ctx, p1d, 2 * ng[2]))) return rc;                                // sgs.f90:475
+  // (12)                                                                                   sgs.f90:372-380
+  dsmag_final_k<<<g, b, 0, ctx->stream>>>(d, p1d, ng[2], lo[2], visct, kc);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}

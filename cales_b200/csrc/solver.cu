@@ -1,0 +1,295 @@
+// FFT-based direct Poisson/Helmholtz solver.
+//   initsolver/eigenvalues/tridmatrix  src/initsolver.f90:17-169       fftini/find_fft src/fft.f90:23-143,192-245
+//   solver        src/solver.f90:20-80  (GPU twin src/solver_gpu.f90:32-164)
+//   gaussel / gaussel_periodic / dgtsv_homebrewed   src/solver.f90:82-179
+//   solver_gaussel_z  src/solver.f90:182-233
+// Data flow on one rank (X-pencils): the forward x pass reads the haloed field directly and writes the
+// halo-free work array, y passes work in place on [x-chunk]x[all y] tiles, the z pass is one thread per
+// (i,j) column (coalesced in i) running the reference's Thomas recurrence in its exact operation order
+// (pivot regularisation `+eps` included), and the backward x pass writes the haloed field scaled by
+// normfft: five sweeps, 16 B/cell each, no transposes and no copy-in/out passes.
+#include <cmath>
+
+#include "common.cuh"
+
+int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
+               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale);
+int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
+
+#define EPS 2.220446049250313e-16
+
+// ---- tridiagonal solves along z -----------------------------------------------------------------------------------
+// One thread per column; the d(l) recurrence coefficients live in shared memory (SMEM=1) when
+// n*blockDim doubles fit, else in a global scratch array (the reference's choice, solver_gpu.f90:166-231).
+template <int SMEM, int LAM>
+__global__ void gaussel_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
+                          const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ p,
+                          double* __restrict__ dscr) {
+  extern __shared__ double dsm[];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nxy) return;
+  const double lam = LAM ? lambdaxy[col] : 0.;
+  double* pp = p + col;
+  double* d = SMEM ? dsm + threadIdx.x : dscr + col;
+  const long ds = SMEM ? blockDim.x : sz;
+  // solver.f90:165-178 in the reference's operation order
+  double z = 1. / (b[0] + lam + EPS);
+  double dl = c[0] * z;
+  d[0] = dl;
+  double pl = pp[0] * z;
+  pp[0] = pl;
+  for (int l = 1; l < n; ++l) {
+    const double al = a[l];
+    z = 1. / ((b[l] + lam) - al * dl + EPS);
+    dl = c[l] * z;
+    d[l * ds] = dl;
+    pl = (pp[l * sz] - al * pl) * z;
+    pp[l * sz] = pl;
+  }
+  for (int l = n - 2; l >= 0; --l) {
+    pl = pp[l * sz] - d[l * ds] * pl;
+    pp[l * sz] = pl;
+  }
+}
+
+// periodic: Sherman-Morrison-like split of solver.f90:109-151; p2 lives beside d in scratch
+template <int SMEM, int LAM>
+__global__ void gaussel_periodic_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
+                                   const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ p,
+                                   double* __restrict__ dscr, double* __restrict__ p2scr) {
+  extern __shared__ double dsm[];
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nxy) return;
+  const double lam = LAM ? lambdaxy[col] : 0.;
+  double* pp = p + col;
+  double* d = SMEM ? dsm + threadIdx.x : dscr + col;
+  double* p2 = SMEM ? dsm + (size_t)n * blockDim.x + threadIdx.x : p2scr + col;
+  const long ds = SMEM ? blockDim.x : sz;
+  const int nm = n - 1;
+  // two systems of size n-1 with the same matrix: rhs p(1:n-1) and [-a(1),0,...,0,-c(n-1)]
+  double z = 1. / (b[0] + lam + EPS);
+  double dl = c[0] * z;
+  d[0] = dl;
+  double p1l = pp[0] * z;
+  pp[0] = p1l;
+  double p2l = (nm == 1 ? (-a[0] - c[0]) : -a[0]) * z;     // n-1 == 1: p2(1) = -a(1) then overwritten by -c(n-1)
+  if (nm == 1) p2l = (-c[0]) * z;
+  p2[0] = p2l;
+  for (int l = 1; l < nm; ++l) {
+    const double al = a[l];
+    z = 1. / ((b[l] + lam) - al * dl + EPS);
+    dl = c[l] * z;
+    d[l * ds] = dl;
+    p1l = (pp[l * sz] - al * p1l) * z;
+    pp[l * sz] = p1l;
+    const double r2 = (l == nm - 1) ? -c[nm - 1] : 0.;
+    p2l = (r2 - al * p2l) * z;
+    p2[l * ds] = p2l;
+  }
+  for (int l = nm - 2; l >= 0; --l) {
+    const double dd = d[l * ds];
+    p1l = pp[l * sz] - dd * p1l;
+    pp[l * sz] = p1l;
+    p2l = p2[l * ds] - dd * p2l;
+    p2[l * ds] = p2l;
+  }
+  // p1l = p1(1), p2l = p2(1)
+  const double p1n = pp[(long)(nm - 1) * sz], p2n = p2[(long)(nm - 1) * ds];
+  const double pn = (pp[(long)(n - 1) * sz] - c[n - 1] * p1l - a[n - 1] * p1n) /
+                    ((b[n - 1] + lam) + c[n - 1] * p2l + a[n - 1] * p2n + EPS);
+  pp[(long)(n - 1) * sz] = pn;
+  for (int l = 0; l < nm; ++l) pp[l * sz] = pp[l * sz] + p2[l * ds] * pn;
+}
+
+// p: halo-free (nx,ny,>=n) array, plane stride sz = nx*ny
+int k_gaussel(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
+              const double* lambdaxy, double* p) {
+  const int nxy = nx * ny;
+  const int NT = 32;
+  const size_t need = (size_t)n * NT * sizeof(double) * (periodic ? 2 : 1);
+  const bool smem = need <= 160 * 1024;
+  double *dscr = nullptr, *p2scr = nullptr;
+  if (!smem) {
+    dscr = (double*)cales_scratch(ctx, "gauss_d", (size_t)sz * n * sizeof(double));
+    if (periodic) p2scr = (double*)cales_scratch(ctx, "gauss_p2", (size_t)sz * n * sizeof(double));
+    if (!dscr || (periodic && !p2scr)) return CALES_ERR_NOMEM;
+  }
+  dim3 g(cdiv(nxy, NT));
+#define LAUNCH(K, S, L, ...)                                                                                  \
+  do {                                                                                                        \
+    if (S) cudaFuncSetAttribute(K<S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);            \
+    K<S, L><<<g, NT, S ? need : 0, ctx->stream>>>(__VA_ARGS__);                                              \
+  } while (0)
+  if (!periodic) {
+    if (smem) { if (lambdaxy) LAUNCH(gaussel_k, 1, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr); else LAUNCH(gaussel_k, 1, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr); }
+    else { if (lambdaxy) LAUNCH(gaussel_k, 0, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr); else LAUNCH(gaussel_k, 0, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr); }
+  } else {
+    if (n < 3) return cales_fail(ctx, CALES_ERR_INVALID, "periodic tridiagonal solve needs n >= 3");
+    if (smem) { if (lambdaxy) LAUNCH(gaussel_periodic_k, 1, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); else LAUNCH(gaussel_periodic_k, 1, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); }
+    else { if (lambdaxy) LAUNCH(gaussel_periodic_k, 0, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); else LAUNCH(gaussel_periodic_k, 0, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); }
+  }
+#undef LAUNCH
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
+extern "C" int cales_gaussel(cales_ctx* ctx, int nx, int ny, int n, int periodic, const double* a, const double* b,
+                             const double* c, const double* lambdaxy, double* p) {
+  CHECK_CTX(ctx);
+  return k_gaussel(ctx, nx, ny, n, (long)nx * ny, periodic, a, b, c, lambdaxy, p);
+}
+
+// ---- initsolver --------------------------------------------------------------------------------------------------------
+static void eigenvalues(int n, const char cbc[2], char c_or_f, std::vector<double>& lam) {   // initsolver.f90:66-125
+  const double pi = acos(-1.0);
+  lam.assign(n, 0.);
+  const bool PP = cbc[0] == 'P' && cbc[1] == 'P', NN = cbc[0] == 'N' && cbc[1] == 'N', DD = cbc[0] == 'D' && cbc[1] == 'D';
+  for (int l = 1; l <= n; ++l) {
+    double v = 0.;
+    if (PP) v = -2. * (1. - cos((2 * (l - 1)) * pi / (1. * n)));
+    else if (NN) v = c_or_f == 'c' ? -2. * (1. - cos((l - 1) * pi / (1. * n))) : -2. * (1. - cos((l - 1) * pi / (1. * (n - 1 + 1))));
+    else if (DD) {
+      if (c_or_f == 'c') v = -2. * (1. - cos(l * pi / (1. * n)));
+      else v = l < n ? -2. * (1. - cos(l * pi / (1. * (n + 1 - 1)))) : 0.;
+    } else v = -2. * (1. - cos((2 * l - 1) * pi / (2. * n)));
+    lam[l - 1] = v;
+  }
+}
+
+extern "C" int cales_initsolver(cales_ctx* ctx, const int ng[3], const int n_x_fft[3], const int n_y_fft[3], const int lo_z[3],
+                                const int hi_z[3], const double dli[3], const double* dzci_g, const double* dzfi_g,
+                                const char cbc[6], const char c_or_f[3], double* lambdaxy, double* a, double* b, double* c,
+                                int* plan, double* normfft) {
+  CHECK_CTX(ctx);
+  (void)n_x_fft; (void)n_y_fft;
+  std::vector<double> lx, ly;
+  const char bcx[2] = {cbc[tb(0, 0)], cbc[tb(1, 0)]}, bcy[2] = {cbc[tb(0, 1)], cbc[tb(1, 1)]}, bcz[2] = {cbc[tb(0, 2)], cbc[tb(1, 2)]};
+  eigenvalues(ng[0], bcx, c_or_f[0], lx);
+  eigenvalues(ng[1], bcy, c_or_f[1], ly);
+  for (auto& v : lx) v = v * (dli[0] * dli[0]);
+  for (auto& v : ly) v = v * (dli[1] * dli[1]);
+  const int nzx = hi_z[0] - lo_z[0] + 1;
+  for (int j = lo_z[1]; j <= hi_z[1]; ++j)                  // initsolver.f90:51-55
+    for (int i = lo_z[0]; i <= hi_z[0]; ++i) lambdaxy[(i - lo_z[0]) + (long)nzx * (j - lo_z[1])] = lx[i - 1] + ly[j - 1];
+  const int n = ng[2];                                      // tridmatrix, initsolver.f90:127-169
+  for (int k = 1; k <= n; ++k) {
+    if (c_or_f[2] == 'c') { a[k - 1] = dzfi_g[k] * dzci_g[k - 1]; c[k - 1] = dzfi_g[k] * dzci_g[k]; }
+    else { a[k - 1] = dzfi_g[k] * dzci_g[k]; c[k - 1] = dzfi_g[k + 1] * dzci_g[k]; }
+    b[k - 1] = -(a[k - 1] + c[k - 1]);
+  }
+  double factor[2];
+  for (int ib = 0; ib < 2; ++ib) factor[ib] = bcz[ib] == 'P' ? 0. : bcz[ib] == 'D' ? -1. : 1.;
+  if (c_or_f[2] == 'c') {
+    b[0] = b[0] + factor[0] * a[0];
+    b[n - 1] = b[n - 1] + factor[1] * c[n - 1];
+  } else {
+    if (bcz[0] == 'N') b[0] = b[0] + factor[0] * a[0];
+    if (bcz[1] == 'N') b[n - 1] = b[n - 1] + factor[1] * c[n - 1];
+  }
+  // fftini: normfft (fft.f90:66-69,99,106,136,142) and the plan record
+  Plan pl;
+  pl.used = true;
+  double nf = 1.;
+  for (int d = 0; d < 2; ++d) {
+    const char* bc = d == 0 ? bcx : bcy;
+    double norm[2];
+    const bool PP = bc[0] == 'P' && bc[1] == 'P', NN = bc[0] == 'N' && bc[1] == 'N', DD = bc[0] == 'D' && bc[1] == 'D';
+    if (PP) { norm[0] = 1.; norm[1] = 0.; }
+    else if (c_or_f[d] == 'f' && NN) { norm[0] = 2.; norm[1] = -1.; }
+    else if (c_or_f[d] == 'f' && DD) { norm[0] = 2.; norm[1] = 1.; }
+    else { norm[0] = 2.; norm[1] = 0.; }
+    const int ix = (DD && c_or_f[d] == 'f') ? 1 : 0;
+    nf = nf * norm[0] * (ng[d] + norm[1] - ix);
+    pl.bc[d][0] = bc[0]; pl.bc[d][1] = bc[1]; pl.c_or_f[d] = c_or_f[d];
+  }
+  pl.normfft = 1. / nf;
+  memcpy(pl.ng, ng, sizeof pl.ng);
+  *normfft = pl.normfft;
+  int h = -1;
+  for (size_t q = 0; q < ctx->plans.size(); ++q) if (!ctx->plans[q].used) { h = (int)q; break; }
+  if (h < 0) { ctx->plans.push_back(pl); h = (int)ctx->plans.size() - 1; } else ctx->plans[h] = pl;
+  *plan = h;
+  return CALES_OK;
+}
+
+extern "C" int cales_fftend(cales_ctx* ctx, int plan) {
+  CHECK_CTX(ctx);
+  if (plan < 0 || plan >= (int)ctx->plans.size()) return cales_fail(ctx, CALES_ERR_INVALID, "fftend: bad plan handle %d", plan);
+  ctx->plans[plan].used = false;
+  return CALES_OK;
+}
+
+// ---- solver --------------------------------------------------------------------------------------------------------------
+extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int plan, double normfft, const double* lambdaxy,
+                            const double* a, const double* b, const double* c, const char bc[6], const char c_or_f[3], double* p) {
+  CHECK_CTX(ctx);
+  if (plan < 0 || plan >= (int)ctx->plans.size() || !ctx->plans[plan].used) return cales_fail(ctx, CALES_ERR_INVALID, "solver: bad plan handle %d", plan);
+  if (ctx->ipencil != 1) return cales_fail(ctx, CALES_ERR_INVALID, "solver: only X-aligned pencils (_DECOMP_X, the reference default) are implemented");
+  const Plan& pl = ctx->plans[plan];
+  Dims d(n);
+  const char bcz[2] = {bc[tb(0, 2)], bc[tb(1, 2)]};
+  const int q = (c_or_f[2] == 'f' && bcz[1] == 'D') ? 1 : 0;
+  const bool zper = bcz[0] == 'P' && bcz[1] == 'P';
+  int rc;
+  if (ctx->nranks == 1) {
+    const long p1 = n[0], p2 = (long)n[0] * n[1];
+    double* wk = (double*)cales_scratch(ctx, "solver_wk", (size_t)p2 * n[2] * sizeof(double));
+    if (!wk) return CALES_ERR_NOMEM;
+    // fwd x: haloed p -> wk ; fwd y in place ; z solve ; bwd y ; bwd x: wk -> haloed p * normfft
+    if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, n[0], n[1], n[2], p + d.idx(1, 1, 1), d.s1, d.s2, wk, p1, p2, 1.0))) return rc;
+    if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, n[0], n[1], n[2], wk, p1, p2, wk, p1, p2, 1.0))) return rc;
+    if ((rc = k_gaussel(ctx, n[0], n[1], n[2] - q, p2, zper, a, b, c, lambdaxy, wk))) return rc;
+    if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, n[0], n[1], n[2], wk, p1, p2, wk, p1, p2, 1.0))) return rc;
+    if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, n[0], n[1], n[2], wk, p1, p2, p + d.idx(1, 1, 1), d.s1, d.s2, normfft))) return rc;
+    return CALES_OK;
+  }
+  // distributed: x-pencil (ng1, n2, n3) -> y-pencil -> z-pencil and back (solver.f90:48-69)
+  const int* xs = ctx->xsz; const int* ys = ctx->ysz; const int* zs = ctx->zsz;
+  const size_t bx = (size_t)xs[0] * xs[1] * xs[2], by = (size_t)ys[0] * ys[1] * ys[2], bz = (size_t)zs[0] * zs[1] * zs[2];
+  size_t bmax = bx > by ? bx : by; bmax = bmax > bz ? bmax : bz;
+  double* w0 = (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
+  double* w1 = (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
+  if (!w0 || !w1) return CALES_ERR_NOMEM;
+  if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, w0, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+  if ((rc = k_transpose(ctx, 0, w0, w1))) return rc;                                    // x -> y
+  if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w1, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
+  if ((rc = k_transpose(ctx, 1, w1, w0))) return rc;                                    // y -> z
+  if ((rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w0))) return rc;
+  if ((rc = k_transpose(ctx, 2, w0, w1))) return rc;                                    // z -> y
+  if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, ys[0], ys[1], ys[2], w1, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
+  if ((rc = k_transpose(ctx, 3, w1, w0))) return rc;                                    // y -> x
+  if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, xs[0], xs[1], xs[2], w0, xs[0], (long)xs[0] * xs[1], p + d.idx(1, 1, 1), d.s1, d.s2, normfft))) return rc;
+  (void)ng;
+  return CALES_OK;
+}
+
+// copy interior <-> halo-free work array
+__global__ void strip_k(Dims d, const double* __restrict__ p, double* __restrict__ w, int to_work) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y, k = blockIdx.z;
+  if (i >= d.n1) return;
+  const long c = d.idx(i + 1, j + 1, k + 1), o = i + (long)d.n1 * (j + (long)d.n2 * k);
+  if (to_work) w[o] = p[c]; else ((double*)p)[c] = w[o];
+}
+
+extern "C" int cales_solver_gaussel_z(cales_ctx* ctx, const int n[3], const double* a, const double* b, const double* c,
+                                      const char bcz[2], const char c_or_f[3], double* p) {
+  CHECK_CTX(ctx);
+  Dims d(n);
+  const int q = (c_or_f[2] == 'f' && bcz[1] == 'D') ? 1 : 0;
+  const bool zper = bcz[0] == 'P' && bcz[1] == 'P';
+  int rc;
+  if (ctx->nranks == 1 || ctx->dims[1] == 1) {
+    // z is rank-local: solve directly on the haloed array (plane stride s2, columns = the full (n1+2)x(n2+2) plane
+    // would touch ghosts; restrict to interior rows by solving row by row)
+    const long p2 = (long)n[0] * n[1];
+    double* wk = (double*)cales_scratch(ctx, "solver_wk", (size_t)p2 * n[2] * sizeof(double));
+    if (!wk) return CALES_ERR_NOMEM;
+    strip_k<<<dim3(cdiv(n[0], 128), n[1], n[2]), 128, 0, ctx->stream>>>(d, p, wk, 1);
+    KERNEL_CHECK(ctx);
+    if ((rc = k_gaussel(ctx, n[0], n[1], n[2] - q, p2, zper, a, b, c, nullptr, wk))) return rc;
+    strip_k<<<dim3(cdiv(n[0], 128), n[1], n[2]), 128, 0, ctx->stream>>>(d, p, wk, 0);
+    KERNEL_CHECK(ctx);
+    return CALES_OK;
+  }
+  return cales_fail(ctx, CALES_ERR_INVALID, "solver_gaussel_z with z decomposed across ranks is not implemented yet");
+}

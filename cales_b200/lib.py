@@ -1,0 +1,114 @@
+"""ctypes binding of libcales_b200.so (the C ABI declared in include/cales_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcales_b200.so")
+
+c_int_p = C.POINTER(C.c_int)
+c_dbl_p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+class Bound(C.Structure):
+    """cales_bound: three device planes (src/typedef.f90:10-14)."""
+    _fields_ = [("x", vp), ("y", vp), ("z", vp)]
+
+
+class CalesError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _ia(a):
+    return np.ascontiguousarray(a, dtype=np.int32).ctypes.data_as(c_int_p)
+
+
+def _da(a):
+    return np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(c_dbl_p)
+
+
+def _ca(a):
+    """(0:1,3[,3]) character table in Fortran order -> bytes."""
+    a = np.asarray(a)
+    return b"".join(x.encode() for x in a.ravel(order="F"))
+
+
+def _tab(a):
+    """(0:1,3) integer/logical table in Fortran order."""
+    return np.ascontiguousarray(np.asarray(a).astype(np.int32).ravel(order="F"))
+
+
+SIGNATURES = {
+    "cales_version": (C.c_char_p, []),
+    "cales_last_error": (C.c_char_p, [vp]),
+    "cales_get_unique_id": (C.c_int, [C.c_char_p]),
+    "cales_init": (C.c_int, [C.POINTER(vp), c_int_p, c_int_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.c_int, vp, C.c_int]),
+    "cales_finalize": (C.c_int, [vp]),
+    "cales_get_decomp": (C.c_int, [vp] + [c_int_p] * 10),
+    "cales_distribute": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, c_int_p]),
+    "cales_pencil": (C.c_int, [c_int_p, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p]),
+    "cales_neighbours": (C.c_int, [c_int_p, C.c_int, C.c_char_p, C.c_int, c_int_p, c_int_p]),
+    "cales_stream_synchronize": (C.c_int, [vp]),
+    "cales_launch_count": (C.c_long, [vp]),
+    "cales_initsolver": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_char_p,
+                                   C.c_char_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p]),
+    "cales_fftend": (C.c_int, [vp, C.c_int]),
+    "cales_solver": (C.c_int, [vp, c_int_p, c_int_p, C.c_int, C.c_double, vp, vp, vp, vp, C.c_char_p, C.c_char_p, vp]),
+    "cales_solver_gaussel_z": (C.c_int, [vp, c_int_p, vp, vp, vp, C.c_char_p, C.c_char_p, vp]),
+    "cales_rk": (C.c_int, [vp, c_dbl_p, c_int_p, c_dbl_p, vp, vp, vp, vp, C.c_double, C.c_double, vp, c_int_p, c_dbl_p, c_dbl_p,
+                           vp, vp, vp, vp, c_dbl_p]),
+    "cales_mom_xyz_ad": (C.c_int, [vp, c_int_p, C.c_double, C.c_double, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cales_bulk_forcing": (C.c_int, [vp, c_int_p, c_int_p, c_dbl_p, vp, vp, vp]),
+    "cales_bulk_mean": (C.c_int, [vp, c_int_p, vp, vp, c_dbl_p]),
+    "cales_bounduvw": (C.c_int, [vp, C.c_char_p, c_int_p] + [C.POINTER(Bound)] * 6 + [c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p,
+                                 vp, vp, vp, vp, C.c_double, C.c_double, c_int_p, C.c_int, C.c_int, vp, vp, vp]),
+    "cales_boundp": (C.c_int, [vp, C.c_char_p, c_int_p, C.POINTER(Bound), c_int_p, c_int_p, c_dbl_p, vp, vp]),
+    "cales_cmpt_rhs_b": (C.c_int, [vp, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_char_p, C.POINTER(Bound), C.c_char_p, vp, vp, vp]),
+    "cales_updt_rhs_b": (C.c_int, [vp, C.c_char_p, C.c_char_p, c_int_p, c_int_p, vp, vp, vp, vp]),
+    "cales_scale": (C.c_int, [vp, C.c_long, C.c_double, vp, vp]),
+    "cales_helmholtz_coeffs": (C.c_int, [vp, C.c_int, C.c_long, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cales_fillps": (C.c_int, [vp, c_int_p, c_dbl_p, vp, C.c_double, vp, vp, vp, vp]),
+    "cales_correc": (C.c_int, [vp, c_int_p, c_dbl_p, vp, C.c_double, vp, vp, vp, vp]),
+    "cales_updatep": (C.c_int, [vp, c_int_p, c_dbl_p, vp, vp, C.c_double, vp, vp]),
+    "cales_cmpt_sgs": (C.c_int, [vp, C.c_char_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_char_p, C.c_char_p, C.POINTER(Bound),
+                                 c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, vp, vp, vp, vp, vp, vp, C.c_double,
+                                 C.c_double, c_int_p, vp, vp, vp] + [C.POINTER(Bound)] * 6 + [vp]),
+    "cales_strain_rate": (C.c_int, [vp, c_int_p, c_dbl_p, vp, vp, vp, vp, vp, vp, vp]),
+    "cales_filter3d": (C.c_int, [vp, c_int_p, vp, vp]),
+    "cales_chkdt": (C.c_int, [vp, c_int_p, c_dbl_p, vp, vp, C.c_double, vp, vp, vp, vp, c_dbl_p]),
+    "cales_chkdiv": (C.c_int, [vp, c_int_p, c_int_p, c_dbl_p, vp, vp, vp, vp, c_dbl_p, c_dbl_p]),
+    "cales_fft_lines": (C.c_int, [vp, c_int_p, C.c_int, C.c_char_p, C.c_char, C.c_int, vp]),
+    "cales_gaussel": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+    "cales_transpose": (C.c_int, [vp, C.c_int, vp, vp]),
+    "cales_updthalo": (C.c_int, [vp, c_int_p, c_int_p, vp]),
+}
+
+
+def load():
+    """Load libcales_b200.so and attach the signatures.  Fails loudly when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CalesError("libcales_b200.so not found at %s: build it with `make -C cales_b200/csrc` "
+                         "(there is no CPU fallback)" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(ctx, rc):
+    if rc != 0:
+        msg = load().cales_last_error(ctx)
+        raise CalesError("libcales_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

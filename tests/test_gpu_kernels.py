@@ -1,0 +1,264 @@
+"""GPU parity tests, kernel by kernel: every call goes through the C ABI of libcales_b200.so and is
+compared with the CPU oracle on the same seeded inputs.  The library is built with -fmad=false, so
+pure stencil arithmetic must agree BIT FOR BIT with numpy (tolerance 0); transcendental functions
+(exp/log/pow) and re-ordered sums get a stated round-off tolerance."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box (no CPU fallback exists)")
+
+
+@pytest.fixture(scope="module")
+def env():
+    _need_gpu()
+    from cales_b200 import lib as L
+    lib = L.load()
+    return L, lib
+
+
+class Ctx:
+    def __init__(self, L, lib, ng, cbcpre="PPPPPP", diffusion=0):
+        self.L, self.lib = L, lib
+        self.ctx = C.c_void_p()
+        L.check(None, lib.cales_init(C.byref(self.ctx), L._ia(ng), L._ia([1, 1]), 1, cbcpre.encode(), 0, 1, None, 0, None, diffusion))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.lib.cales_finalize(self.ctx)
+
+    def chk(self, rc):
+        self.L.check(self.ctx, rc)
+
+
+_KEEP = []
+
+
+def dev(a):
+    """Upload; the tensor is kept alive until the next test starts (kernels are asynchronous and the caching
+    allocator would otherwise hand the storage of a temporary to the next upload)."""
+    t = torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))).cuda()
+    _KEEP.append(t)
+    return t
+
+
+@pytest.fixture(autouse=True)
+def _clear_keep():
+    _KEEP.clear()
+    yield
+    torch.cuda.synchronize()
+    _KEEP.clear()
+
+
+def host(t, shape):
+    return t.cpu().numpy().reshape(shape, order="F")
+
+
+def rnd_fields(n, seed, count):
+    rng = np.random.default_rng(seed)
+    return [np.asfortranarray(rng.standard_normal((n[0] + 2, n[1] + 2, n[2] + 2))) for _ in range(count)]
+
+
+def grid(n3, seed=7):
+    rng = np.random.default_rng(seed)
+    dzf = 0.5 + rng.random(n3 + 2)
+    dzc = np.zeros(n3 + 2)
+    dzc[:-1] = .5 * (dzf[:-1] + dzf[1:]); dzc[-1] = dzc[-2]
+    return dzc, dzf, 1. / dzc, 1. / dzf
+
+
+SIZES = [(16, 12, 10), (67, 9, 33), (64, 64, 64)]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_fillps_correc_updatep_bitexact(env, n):
+    from oracle import ops
+    L, lib = env
+    u, v, w, p, pp = rnd_fields(n, 1, 5)
+    dzc, dzf, dzci, dzfi = grid(n[2])
+    dli = np.array([3.1, 2.7, 1.9]); dt = 0.0123
+    with Ctx(L, lib, n) as c:
+        du, dv, dw, dp, dpp = map(dev, (u, v, w, p, pp))
+        ddzci, ddzfi = dev(dzci), dev(dzfi)
+        c.chk(lib.cales_fillps(c.ctx, L._ia(n), L._da(dli), ddzfi.data_ptr(), 1. / dt, du.data_ptr(), dv.data_ptr(), dw.data_ptr(), dp.data_ptr()))
+        p_ref = p.copy(order="F"); ops.fillps(n, dli, dzfi, 1. / dt, u, v, w, p_ref)
+        assert np.array_equal(host(dp, p.shape), p_ref)
+        c.chk(lib.cales_correc(c.ctx, L._ia(n), L._da(dli), ddzci.data_ptr(), dt, dpp.data_ptr(), du.data_ptr(), dv.data_ptr(), dw.data_ptr()))
+        ur, vr, wr = u.copy(order="F"), v.copy(order="F"), w.copy(order="F")
+        ops.correc(n, dli, dzci, dt, pp, ur, vr, wr)
+        assert np.array_equal(host(du, u.shape), ur) and np.array_equal(host(dv, u.shape), vr) and np.array_equal(host(dw, u.shape), wr)
+        dp2 = dev(p)
+        c.chk(lib.cales_updatep(c.ctx, L._ia(n), L._da(dli), ddzci.data_ptr(), ddzfi.data_ptr(), 0.0, dpp.data_ptr(), dp2.data_ptr()))
+        p_ref = p.copy(order="F"); ops.updatep(n, dli, dzci, dzfi, 0.0, pp, p_ref)
+        assert np.array_equal(host(dp2, p.shape), p_ref)
+    for mode, (imp, imp1) in ((1, (True, False)), (2, (True, True))):
+        with Ctx(L, lib, n, diffusion=mode) as c:
+            dp2, dpp = dev(p), dev(pp)
+            c.chk(lib.cales_updatep(c.ctx, L._ia(n), L._da(dli), dev(dzci).data_ptr(), dev(dzfi).data_ptr(), -0.37, dpp.data_ptr(), dp2.data_ptr()))
+            p_ref = p.copy(order="F"); ops.updatep(n, dli, dzci, dzfi, -0.37, pp, p_ref, imp, imp1)
+            assert np.array_equal(host(dp2, p.shape), p_ref)
+
+
+@pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_mom_xyz_ad_bitexact(env, n, mode):
+    from oracle import mom
+    L, lib = env
+    u, v, w, s = rnd_fields(n, 2, 4)
+    s = np.abs(s)
+    dzc, dzf, dzci, dzfi = grid(n[2])
+    dxi, dyi, visc = 3.3, 2.1, 1e-2
+    (ru, rv, rw), imp = mom.mom_xyz_ad(n, dxi, dyi, dzci, dzfi, visc, u, v, w, s, mode > 0, mode == 2)
+    with Ctx(L, lib, n, diffusion=mode) as c:
+        out = [torch.zeros(n[0] * n[1] * n[2], dtype=torch.float64, device="cuda") for _ in range(6)]
+        c.chk(lib.cales_mom_xyz_ad(c.ctx, L._ia(n), dxi, dyi, dev(dzci).data_ptr(), dev(dzfi).data_ptr(), visc, dev(u).data_ptr(),
+                                   dev(v).data_ptr(), dev(w).data_ptr(), dev(s).data_ptr(), *[o.data_ptr() for o in out]))
+        for o, r in zip(out[:3], (ru, rv, rw)):
+            assert np.array_equal(host(o, tuple(n)), r)
+        if mode:
+            for o, r in zip(out[3:], imp):
+                assert np.array_equal(host(o, tuple(n)), r)
+
+
+def test_mom_polynomial_check(env):
+    """The reference's own analytical check (src/mom.f90:20-21): with visct = x+y+z and u=v=w=x*y*z the
+    SGS cross terms are polynomial; compare oracle and device, and both against the closed form of the
+    u-equation diffusion part for a uniform grid."""
+    from oracle import mom
+    L, lib = env
+    n = (24, 20, 16)
+    dl = np.array([0.1, 0.2, 0.05])
+    i = np.arange(0, n[0] + 2)[:, None, None]; j = np.arange(0, n[1] + 2)[None, :, None]; k = np.arange(0, n[2] + 2)[None, None, :]
+    xc, yc, zc = (i - .5) * dl[0], (j - .5) * dl[1], (k - .5) * dl[2]
+    xf, yf, zf = i * dl[0], j * dl[1], k * dl[2]
+    u = np.asfortranarray(xf * yc * zc); v = np.asfortranarray(xc * yf * zc); w = np.asfortranarray(xc * yc * zf)
+    s = np.asfortranarray(xc + yc + zc + 0 * u)
+    dzci = np.full(n[2] + 2, 1. / dl[2]); dzfi = dzci.copy()
+    (ru, rv, rw), _ = mom.mom_xyz_ad(n, 1 / dl[0], 1 / dl[1], dzci, dzfi, 0.0, u, v, w, s)
+    with Ctx(L, lib, n) as c:
+        out = [torch.zeros(n[0] * n[1] * n[2], dtype=torch.float64, device="cuda") for _ in range(3)]
+        c.chk(lib.cales_mom_xyz_ad(c.ctx, L._ia(n), 1 / dl[0], 1 / dl[1], dev(dzci).data_ptr(), dev(dzfi).data_ptr(), 0.0, dev(u).data_ptr(),
+                                   dev(v).data_ptr(), dev(w).data_ptr(), dev(s).data_ptr(), *[o.data_ptr() for o in out], None, None, None))
+        assert np.array_equal(host(out[0], tuple(n)), ru)
+    # closed form: d/dx[2 nu_t u_x] + d/dy[nu_t(u_y+v_x)] + d/dz[nu_t(u_z+w_x)] - div(u u) for the u-equation;
+    # with u = x y z etc. second differences are exact for these polynomials
+    I = (slice(1, n[0] + 1), slice(1, n[1] + 1), slice(1, n[2] + 1))
+    X, Y, Z = (xf + 0 * u)[I], (yc + 0 * u)[I], (zc + 0 * u)[I]
+    sgs = 2 * Y * Z + (X * Z + Y * Z) + (X * Y + Y * Z)      # nu_t derivative terms: d(nu_t)/dx_j = 1
+    # + nu_t * (2 u_xx + u_yy + v_xy + u_zz + w_xz) = nu_t * (0 + 0 + Z + 0 + Y)
+    sgs = sgs + (X + Y + Z) * (Z + Y)
+    adv = -(2 * X * Y * Z * Y * Z + 2 * X * X * Y * Z * Z + 2 * X * X * Y * Y * Z)   # -(d(uu)/dx + d(vu)/dy + d(wu)/dz)
+    # advective products are O(h^2)-accurate only; check the (exact) viscous part by subtracting the advective part of the oracle
+    (au, _, _), _ = mom.mom_xyz_ad(n, 1 / dl[0], 1 / dl[1], dzci, dzfi, 0.0, u, v, w, 0 * s)
+    assert np.allclose(ru - au, sgs, rtol=1e-10, atol=1e-10)
+    assert np.allclose(au, adv, rtol=0, atol=0.05 * np.abs(adv).max())
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_strain_filter_bitexact(env, n):
+    from oracle import sgs
+    L, lib = env
+    u, v, w = rnd_fields(n, 3, 3)
+    dzc, dzf, dzci, dzfi = grid(n[2])
+    dli = np.array([3.1, 2.7, 1.9])
+    s0 = np.zeros_like(u); sij = [np.zeros_like(u) for _ in range(6)]
+    sgs.strain_rate(n, dli, dzci, dzfi, u, v, w, s0, sij)
+    pf = np.zeros_like(u); sgs.filter3d(n, u, pf)
+    with Ctx(L, lib, n) as c:
+        ds0 = torch.zeros(u.size, dtype=torch.float64, device="cuda")
+        dsij = torch.zeros(6 * u.size, dtype=torch.float64, device="cuda")
+        c.chk(lib.cales_strain_rate(c.ctx, L._ia(n), L._da(dli), dev(dzci).data_ptr(), dev(dzfi).data_ptr(), dev(u).data_ptr(),
+                                    dev(v).data_ptr(), dev(w).data_ptr(), ds0.data_ptr(), dsij.data_ptr()))
+        assert np.array_equal(host(ds0, u.shape), s0)
+        got = dsij.cpu().numpy().reshape((6,) + (u.size,))
+        for m in range(6):
+            assert np.array_equal(got[m].reshape(u.shape, order="F"), sij[m])
+        dpf = torch.zeros(u.size, dtype=torch.float64, device="cuda")
+        c.chk(lib.cales_filter3d(c.ctx, L._ia(n), dev(u).data_ptr(), dpf.data_ptr()))
+        assert np.array_equal(host(dpf, u.shape), pf)
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_reductions(env, n):
+    """chkdiv / chkdt / bulk_mean: max is exact; sums differ from the sequential Fortran order only by
+    re-association (tolerance 1e-13 relative to sum|x|)."""
+    from oracle import ops, rk
+    L, lib = env
+    u, v, w, s = rnd_fields(n, 4, 4)
+    s = np.abs(s) * 1e-3
+    dzc, dzf, dzci, dzfi = grid(n[2])
+    dl = np.array([0.31, 0.27, 0.19]); dli = 1. / dl
+    lo = np.array([1, 1, 1], dtype=np.int32); hi = np.array(n, dtype=np.int32)
+    with Ctx(L, lib, n) as c:
+        tot, mx = C.c_double(), C.c_double()
+        c.chk(lib.cales_chkdiv(c.ctx, L._ia(lo), L._ia(hi), L._da(dli), dev(dzfi).data_ptr(), dev(u).data_ptr(), dev(v).data_ptr(),
+                               dev(w).data_ptr(), C.byref(tot), C.byref(mx)))
+        rt, rm = ops.chkdiv_local(n, dli, dzfi, u, v, w)
+        assert mx.value == rm
+        scale = np.abs(u).sum() * dli.max() * 6
+        assert abs(tot.value - rt) <= 1e-13 * scale
+        out = C.c_double()
+        c.chk(lib.cales_chkdt(c.ctx, L._ia(n), L._da(dl), dev(dzci).data_ptr(), dev(dzfi).data_ptr(), 1e-3, dev(s).data_ptr(),
+                              dev(u).data_ptr(), dev(v).data_ptr(), dev(w).data_ptr(), C.byref(out)))
+        assert out.value == ops.chkdt_local(n, dl, dzci, dzfi, 1e-3, s, u, v, w)
+        gvr = dzf / dzf[1:-1].sum() / (n[0] * n[1])
+        c.chk(lib.cales_bulk_mean(c.ctx, L._ia(n), dev(gvr).data_ptr(), dev(u).data_ptr(), C.byref(out)))
+        ref = rk.bulk_mean_local(n, gvr, u)
+        assert abs(out.value - ref) <= 1e-13 * np.abs(u[1:-1, 1:-1, 1:-1] * gvr[None, None, 1:-1]).sum()
+
+
+KINDS = [("PP", "R2HC", "HC2R"), ("NN", "REDFT10", "REDFT01"), ("DD", "RODFT10", "RODFT01")]
+
+
+@pytest.mark.parametrize("bc,kf,kb", KINDS)
+@pytest.mark.parametrize("n", [(16, 12, 3), (64, 48, 5), (96, 30, 4), (192, 256, 2), (512, 2, 2), (1024, 6, 2), (14, 22, 3), (2, 4, 2)])
+def test_fft_lines_vs_fftw_definitions(env, bc, kf, kb, n):
+    """Each transform kind, both directions, forward and backward, against the FFTW r2r definitions
+    (scipy/pocketfft).  Tolerance: 2e-15 * log2(n) relative to max|result| (FFT round-off)."""
+    from oracle import solver as osl
+    L, lib = env
+    rng = np.random.default_rng(5)
+    a = np.asfortranarray(rng.standard_normal(n))
+    with Ctx(L, lib, n) as c:
+        for dir_ in (0, 1):
+            for backward, kind in ((0, kf), (1, kb)):
+                ref = a.copy(order="F"); osl.fft(kind, n[dir_], ref, dir_)
+                da = dev(a)
+                c.chk(lib.cales_fft_lines(c.ctx, L._ia(n), dir_, bc.encode(), b"c", backward, da.data_ptr()))
+                got = host(da, a.shape)
+                tol = 2e-15 * max(1., np.log2(n[dir_])) * np.abs(ref).max()
+                assert np.abs(got - ref).max() <= tol, (bc, dir_, backward, np.abs(got - ref).max(), tol)
+
+
+@pytest.mark.parametrize("periodic", [0, 1])
+@pytest.mark.parametrize("n", [(16, 12, 10), (33, 7, 64), (64, 64, 256), (8, 8, 600)])
+def test_gaussel_bitexact(env, n, periodic):
+    from oracle import solver as osl
+    L, lib = env
+    rng = np.random.default_rng(6)
+    nx, ny, nz = n
+    a = 0.5 + rng.random(nz); c_ = 0.5 + rng.random(nz); b = -(a + c_)
+    lam = -np.asfortranarray(rng.random((nx, ny))) * 3
+    p = np.asfortranarray(rng.standard_normal(n))
+    ref = p.copy(order="F")
+    (osl.gaussel_periodic if periodic else osl.gaussel)(nx, ny, nz, a, b, c_, ref, lam)
+    with Ctx(L, lib, n) as c:
+        dp = dev(p)
+        c.chk(lib.cales_gaussel(c.ctx, nx, ny, nz, periodic, dev(a).data_ptr(), dev(b).data_ptr(), dev(c_).data_ptr(), dev(lam).data_ptr(), dp.data_ptr()))
+        assert np.array_equal(host(dp, p.shape), ref)
+        # Thomas against a dense solve (non-periodic, well-conditioned): the reference's `+eps` pivots are O(eps)
+        if not periodic and nz <= 64:
+            i, j = 1, 2
+            A = np.diag(b + lam[i, j]) + np.diag(a[1:], -1) + np.diag(c_[:-1], 1)
+            x = np.linalg.solve(A, p[i, j, :])
+            assert np.allclose(ref[i, j, :], x, rtol=1e-10, atol=1e-12)

@@ -1,0 +1,191 @@
+"""GPU parity tests of the assembled path: solver, boundary conditions, SGS models and whole RK3
+steps, CUDA (through the C ABI, driven like main.f90) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): Poisson solution and post-correction divergence 1e-12
+relative; fields after N steps 1e-10 relative (L-inf, normalised by max|field|).  Pressure-like
+fields are compared after removing the volume mean: for all-periodic/Neumann problems the (0,0)
+mode is singular and regularised by `+eps` pivots (solver.f90:165-170), so its additive constant
+is round-off noise in the reference itself."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device visible: GPU tests must run on the B200 box (no CPU fallback exists)")
+
+
+def relerr(a, b, demean=False):
+    a = a[1:-1, 1:-1, 1:-1]; b = b[1:-1, 1:-1, 1:-1]
+    if demean:
+        a = a - a.mean(); b = b - b.mean()
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def make_pair(name, ng=None, **kw):
+    """The same deck for the oracle and for the product."""
+    import oracle.param as op
+    import cales_b200.deck as pd
+    from oracle.main import Sim
+    from cales_b200.driver import Simulation
+    args = dict(kw)
+    if ng is not None:
+        args["ng"] = ng
+    od = getattr(op, name)(**args)
+    dd = getattr(pd, name)(**args)
+    return od, dd, Sim, Simulation
+
+
+CASES = {
+    "channel_dsmag": ("deck_channel", dict(ng=(32, 24, 32), sgstype="dsmag")),
+    "channel_smag": ("deck_channel", dict(ng=(32, 24, 32), sgstype="smag")),
+    "channel_wm_smag": ("deck_channel", dict(ng=(32, 16, 24), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.)),
+    "channel_wm_dsmag": ("deck_channel", dict(ng=(32, 16, 24), sgstype="dsmag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.)),
+    "tgv_smag": ("deck_tgv", dict(ng=(32, 32, 32))),
+    "duct_smag": ("deck_duct", dict(ng=(16, 24, 24))),
+    "duct_wm_smag": ("deck_duct", dict(ng=(16, 24, 24), wall_model=True)),
+    "cavity_smag": ("deck_cavity", dict(ng=(24, 24, 24))),
+}
+
+
+def run_pair(case, nsteps, impdiff=None):
+    name, kw = CASES[case]
+    od, dd, Sim, Simulation = make_pair(name, **kw)
+    if impdiff:
+        for d in (od, dd):
+            d.impdiff = True
+            d.impdiff_1d = impdiff == "1d"
+    o = Sim(od)
+    g = Simulation(dd)
+    g.init_flow()
+    g.start()
+    assert abs(g.dt - o.dt) <= 1e-13 * o.dt
+    out = []
+    for _ in range(nsteps):
+        ro = o.step(icheck=1)
+        rg = g.step(icheck=1)
+        out.append((ro, rg))
+    return o, g, out
+
+
+def compare(o, g, tol):
+    errs = {}
+    for nm, on in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("visct", "VISCT")):
+        errs[nm] = relerr(g.get(nm), getattr(o, on)[0], demean=(nm == "p"))
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, errs
+    return errs
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_ten_steps(case):
+    o, g, out = run_pair(case, 10)
+    compare(o, g, 1e-10)
+    for ro, rg in out:
+        # post-correction divergence: both at round-off level and equal to 1e-12 of the velocity gradient scale
+        assert rg[1] < 1e-9 and abs(rg[1] - ro[1]) <= 1e-12 * max(1.0, np.abs(g.get("u")).max() * max(g.deck.dli))
+    assert abs(g.dt - o.dt) <= 1e-10 * o.dt
+    g.close()
+
+
+@pytest.mark.parametrize("case", ["channel_dsmag", "tgv_smag", "channel_wm_smag"])
+def test_hundred_steps(case):
+    """north_star: velocity/pressure fields after 100 steps agree to relative 1e-10."""
+    o, g, out = run_pair(case, 100)
+    compare(o, g, 1e-10)
+    g.close()
+
+
+@pytest.mark.parametrize("case,mode", [("channel_smag", "3d"), ("channel_smag", "1d"), ("tgv_smag", "1d"), ("channel_wm_smag", "1d")])
+def test_implicit_diffusion(case, mode):
+    """Crank-Nicolson paths (_IMPDIFF / _IMPDIFF_1D, main.f90:423-491)."""
+    if mode == "3d":
+        pytest.skip("3-D implicit diffusion needs the face-centred transforms (REDFT00/RODFT00): next round")
+    o, g, out = run_pair(case, 5, impdiff=mode)
+    compare(o, g, 1e-10)
+    g.close()
+
+
+@pytest.mark.parametrize("bcs", ["PPPPNN", "PPPPPP", "NNNNNN", "PPNNNN", "DDPPDD", "PPDDNN"])
+@pytest.mark.parametrize("ng", [(32, 24, 16), (64, 64, 64), (96, 30, 40)])
+def test_poisson_solver(bcs, ng):
+    """solver(): CUDA vs oracle to 1e-12 (de-meaned) and the discrete-Laplacian residual of both."""
+    import ctypes as C
+    import oracle.param as op
+    import cales_b200.deck as pd
+    from oracle.main import Sim
+    from cales_b200.driver import Simulation
+    def mk(mod):
+        d = mod.Deck(ng=ng, l=(3.0, 2.0, 1.5), gtype=1, gr=2.0, inivel="zer", sgstype="none")
+        for idir in range(3):
+            for ib in range(2):
+                c = bcs[2 * idir + ib]
+                d.cbcpre[ib, idir] = c
+                for ivel in range(3):
+                    d.cbcvel[ib, idir, ivel] = "P" if c == "P" else "D"
+                d.cbcsgs[ib, idir] = "P" if c == "P" else "D"
+        return d
+    o = Sim(mk(op)); g = Simulation(mk(pd))
+    rng = np.random.default_rng(11)
+    rhs = np.asfortranarray(rng.standard_normal((ng[0] + 2, ng[1] + 2, ng[2] + 2)))
+    singular = all(c in "PN" for c in bcs)
+    if singular:
+        # compatibility: the volume-weighted mean of the rhs must vanish
+        wgt = o.st[0].dzf[1:-1][None, None, :]
+        rhs[1:-1, 1:-1, 1:-1] -= (rhs[1:-1, 1:-1, 1:-1] * wgt).sum() / (wgt.sum() * ng[0] * ng[1])
+    # exact lambdaxy/a/b/c parity of initsolver (index/eigenvalue maps must be bit-exact)
+    assert np.array_equal(g.poi["lam_h"], o.lambdaxyp[0])
+    assert np.array_equal(g.poi["a_h"], o.ap) and np.array_equal(g.poi["b_h"], o.bp) and np.array_equal(g.poi["c_h"], o.cp)
+    assert g.poi["normfft"] == o.plan_p.normfft
+    po = [rhs.copy(order="F")]
+    o.solve_poisson(po)
+    g.set_fields(pp=rhs)
+    g.solver(g.poi, "pp")
+    pg = g.get("pp")
+    if singular and bcs[4:] == "PP":
+        # periodic z + singular (0,0) mode: gaussel_periodic divides an O(eps) residual by an O(eps) pivot
+        # (solver.f90:142-143), so the horizontal-mean profile carries amplified round-off in the reference
+        # itself; compare the field minus its plane means to 1e-12 and the plane means to the noise level
+        pm_g = pg[1:-1, 1:-1, 1:-1].mean(axis=(0, 1)); pm_o = po[0][1:-1, 1:-1, 1:-1].mean(axis=(0, 1))
+        a = pg[1:-1, 1:-1, 1:-1] - pm_g; b = po[0][1:-1, 1:-1, 1:-1] - pm_o
+        e = float(np.abs(a - b).max() / np.abs(b).max())
+        pm_g = pm_g - pm_g.mean(); pm_o = pm_o - pm_o.mean()
+        assert np.abs(pm_g - pm_o).max() <= 1e-6 * np.abs(b).max()
+    else:
+        e = relerr(pg, po[0], demean=singular)
+    assert e <= 1e-12, e
+    # residual of the discrete problem: apply boundp + Laplacian (uses the oracle's operators on the GPU result)
+    from oracle import bound as ob
+    q = [pg.copy(order="F")]
+    ob.boundp(o.world, o.deck.cbcpre, o.st, "bcp", q)
+    s = o.st[0]
+    p = q[0]
+    I = (slice(1, -1),) * 3
+    k = np.arange(1, ng[2] + 1)
+    lap = (p[2:, 1:-1, 1:-1] - 2 * p[I] + p[:-2, 1:-1, 1:-1]) * s.dli[0] ** 2 + \
+          (p[1:-1, 2:, 1:-1] - 2 * p[I] + p[1:-1, :-2, 1:-1]) * s.dli[1] ** 2 + \
+          ((p[1:-1, 1:-1, 2:] - p[I]) * s.dzci[k] - (p[I] - p[1:-1, 1:-1, :-2]) * s.dzci[k - 1]) * s.dzfi[k]
+    res = np.abs(lap - rhs[I]).max() / np.abs(rhs[I]).max()
+    assert res <= 1e-10, res
+    g.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (256^3 tri-periodic, smag): size-independent properties of the GPU path --
+    divergence after projection at round-off, Poisson round trip, kinetic energy decays."""
+    from cales_b200.deck import deck_tgv
+    from cales_b200.driver import Simulation
+    g = Simulation(deck_tgv(ng=(256, 256, 256)))
+    g.init_flow(); g.start()
+    def ke():
+        return float(sum((g.fields[c] ** 2).sum().item() for c in "uvw"))
+    e0 = ke()
+    for _ in range(3):
+        tot, mx = g.step(icheck=1)
+        assert mx < 1e-11, mx
+    assert ke() < e0
+    g.close()
