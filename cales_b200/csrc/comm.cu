@@ -9,16 +9,48 @@
 
 #include "common.cuh"
 
+// NCCL is bound at run time (dlopen) and only when nranks > 1: a host process that already carries an NCCL
+// (PyTorch bundles its own libnccl.so.2) keeps using that one, and single-GPU use needs no NCCL at all.
+#include <dlfcn.h>
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_load(cales_ctx* ctx) {
+  if (g_nccl.h) return CALES_OK;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);       // already in the process (e.g. torch's)?
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return cales_fail(ctx, CALES_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(name) *(void**)(&g_nccl.name) = dlsym(h, "nccl" #name); if (!g_nccl.name) return cales_fail(ctx, CALES_ERR_NCCL, "libnccl lacks nccl" #name)
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+#undef SYM
+  g_nccl.h = h;
+  return CALES_OK;
+}
+
 #define NCCL_TRY(ctx, call)                                                                              \
   do {                                                                                                    \
     ncclResult_t r_ = (call);                                                                             \
-    if (r_ != ncclSuccess) return cales_fail(ctx, CALES_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, ncclGetErrorString(r_)); \
+    if (r_ != ncclSuccess) return cales_fail(ctx, CALES_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
   } while (0)
 
 extern "C" int cales_get_unique_id(char uid[CALES_UNIQUE_ID_BYTES]) {
   static_assert(sizeof(ncclUniqueId) <= CALES_UNIQUE_ID_BYTES, "unique id size");
+  int rc = nccl_load(nullptr);
+  if (rc) return rc;
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return cales_fail(nullptr, CALES_ERR_NCCL, "ncclGetUniqueId failed");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return cales_fail(nullptr, CALES_ERR_NCCL, "ncclGetUniqueId failed");
   memset(uid, 0, CALES_UNIQUE_ID_BYTES);
   memcpy(uid, &id, sizeof id);
   return CALES_OK;
@@ -26,27 +58,29 @@ extern "C" int cales_get_unique_id(char uid[CALES_UNIQUE_ID_BYTES]) {
 
 int comm_init(cales_ctx* ctx, const char* uid) {
   if (!uid) return cales_fail(ctx, CALES_ERR_INVALID, "nranks>1 requires an NCCL unique id (cales_get_unique_id on rank 0, broadcast by the host)");
+  int rc = nccl_load(ctx);
+  if (rc) return rc;
   ncclUniqueId id;
   memcpy(&id, uid, sizeof id);
   ncclComm_t comm;
-  NCCL_TRY(ctx, ncclCommInitRank(&comm, ctx->nranks, id, ctx->rank));
+  NCCL_TRY(ctx, g_nccl.CommInitRank(&comm, ctx->nranks, id, ctx->rank));
   ctx->nccl = comm;
   return CALES_OK;
 }
 
 void comm_finalize(cales_ctx* ctx) {
-  if (ctx->nccl) { ncclCommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
+  if (ctx->nccl) { g_nccl.CommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
 }
 
 int k_allreduce_sum(cales_ctx* ctx, double* dev, int count) {
   if (ctx->nranks == 1) return CALES_OK;
-  NCCL_TRY(ctx, ncclAllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  NCCL_TRY(ctx, g_nccl.AllReduce(dev, dev, count, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
   return CALES_OK;
 }
 
 int k_allreduce_minmax(cales_ctx* ctx, double* dev, int count, int is_max) {
   if (ctx->nranks == 1) return CALES_OK;
-  NCCL_TRY(ctx, ncclAllReduce(dev, dev, count, ncclDouble, is_max ? ncclMax : ncclMin, (ncclComm_t)ctx->nccl, ctx->stream));
+  NCCL_TRY(ctx, g_nccl.AllReduce(dev, dev, count, ncclDouble, is_max ? ncclMax : ncclMin, (ncclComm_t)ctx->nccl, ctx->stream));
   return CALES_OK;
 }
 
@@ -121,14 +155,14 @@ int k_halo_exchange(cales_ctx* ctx, const int n[3], const int nb[6], double* con
       halo_pack_k<<<g, b, 0, ctx->stream>>>(d, idir, fl, sbuf);
       KERNEL_CHECK(ctx);
       ncclComm_t comm = (ncclComm_t)ctx->nccl;
-      NCCL_TRY(ctx, ncclGroupStart());
+      NCCL_TRY(ctx, g_nccl.GroupStart());
       // sends: my plane 1 to nb(0), my plane n to nb(1); receives in the matching order for the
       // two-rank periodic case (the peer's first message is its plane 1 = my upper ghost)
-      if (nb0 >= 0) NCCL_TRY(ctx, ncclSend(sbuf, cnt, ncclDouble, nb0, comm, ctx->stream));
-      if (nb1 >= 0) NCCL_TRY(ctx, ncclSend(sbuf + cnt, cnt, ncclDouble, nb1, comm, ctx->stream));
-      if (nb1 >= 0) NCCL_TRY(ctx, ncclRecv(rbuf + cnt, cnt, ncclDouble, nb1, comm, ctx->stream));
-      if (nb0 >= 0) NCCL_TRY(ctx, ncclRecv(rbuf, cnt, ncclDouble, nb0, comm, ctx->stream));
-      NCCL_TRY(ctx, ncclGroupEnd());
+      if (nb0 >= 0) NCCL_TRY(ctx, g_nccl.Send(sbuf, cnt, ncclDouble, nb0, comm, ctx->stream));
+      if (nb1 >= 0) NCCL_TRY(ctx, g_nccl.Send(sbuf + cnt, cnt, ncclDouble, nb1, comm, ctx->stream));
+      if (nb1 >= 0) NCCL_TRY(ctx, g_nccl.Recv(rbuf + cnt, cnt, ncclDouble, nb1, comm, ctx->stream));
+      if (nb0 >= 0) NCCL_TRY(ctx, g_nccl.Recv(rbuf, cnt, ncclDouble, nb0, comm, ctx->stream));
+      NCCL_TRY(ctx, g_nccl.GroupEnd());
       halo_unpack_k<<<g, b, 0, ctx->stream>>>(d, idir, fl, rbuf, nb0 >= 0, nb1 >= 0);
       KERNEL_CHECK(ctx);
     }
@@ -142,10 +176,96 @@ extern "C" int cales_updthalo(cales_ctx* ctx, const int n[3], const int nb[6], d
   return k_halo_exchange(ctx, n, nb, ps, 1);
 }
 
-// ---- pencil transposes (placeholder until the NCCL all-to-all path below is wired) -----------------------
+// ---- pencil transposes ------------------------------------------------------------------------------------------
+// 2decomp transpose_x_to_y / y_to_z / z_to_y / y_to_x (dependencies/2decomp-fft/src/transpose_x_to_y.f90:25-115)
+// == cudecompTransposeXToY ... (dependencies/cuDecomp/include/internal/transpose.h:160-729).
+// Pencil A is complete along axis `al` and split along `be` over the P ranks of a row/column of the process
+// grid; pencil B is complete along `be` and split along `al`.  Rank q receives my sub-box al in range_al(q);
+// I receive from q the sub-box be in range_be(q).  One pack launch builds all peer slabs, one NCCL group moves
+// them over NVLink (the self slab never leaves the device), one unpack launch scatters them.
+struct Seg { long soff, doff; int b0, b1, b2; long ss1, ss2, ds1, ds2; };
+struct SegList { Seg s[16]; int n; };
+
+__global__ void __launch_bounds__(256) boxcopy_k(const double* __restrict__ src, double* __restrict__ dst, SegList L) {
+  const Seg& g = L.s[blockIdx.z];
+  const int i = blockIdx.x * 64 + threadIdx.x;
+  if (i >= g.b0) return;
+  const long rows = (long)g.b1 * g.b2;
+  for (long r = blockIdx.y * 4 + threadIdx.y; r < rows; r += (long)gridDim.y * 4) {
+    const int j = (int)(r % g.b1), k = (int)(r / g.b1);
+    dst[g.doff + i + j * g.ds1 + k * g.ds2] = src[g.soff + i + j * g.ss1 + k * g.ss2];
+  }
+}
+
+static int boxcopy(cales_ctx* ctx, const double* src, double* dst, const SegList& L) {
+  int b0 = 1; long rows = 1;
+  for (int q = 0; q < L.n; ++q) { if (L.s[q].b0 > b0) b0 = L.s[q].b0; if ((long)L.s[q].b1 * L.s[q].b2 > rows) rows = (long)L.s[q].b1 * L.s[q].b2; }
+  long gy = (rows + 3) / 4; if (gy > 16384) gy = 16384;
+  boxcopy_k<<<dim3(cdiv(b0, 64), (unsigned)gy, L.n), dim3(64, 4), 0, ctx->stream>>>(src, dst, L);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {
-  (void)which; (void)src; (void)dst;
-  return cales_fail(ctx, CALES_ERR_INVALID, "distributed transposes are not implemented yet");
+  // which: 0 x->y, 1 y->z, 2 z->y, 3 y->x
+  const int* A = which == 0 ? ctx->xsz : (which == 1 || which == 3) ? ctx->ysz : ctx->zsz;
+  const int* B = which == 0 ? ctx->ysz : which == 1 ? ctx->zsz : which == 2 ? ctx->ysz : ctx->xsz;
+  const int al = which == 0 ? 0 : which == 1 ? 1 : which == 2 ? 2 : 1;      // complete in A, split in B
+  const int be = which == 0 ? 1 : which == 1 ? 2 : which == 2 ? 1 : 0;      // split in A, complete in B
+  const bool colcomm = (which == 0 || which == 3);                           // x<->y: ranks differ in coord(1) of the grid = index 0
+  const int P = colcomm ? ctx->dims[0] : ctx->dims[1];
+  const int me = colcomm ? ctx->coord[0] : ctx->coord[1];
+  if (P > 16) return cales_fail(ctx, CALES_ERR_INVALID, "transpose over %d ranks: at most 16 per row/column supported", P);
+  const size_t na = (size_t)A[0] * A[1] * A[2], nb_ = (size_t)B[0] * B[1] * B[2];
+  if (P == 1) {                                                              // same data, same layout
+    if (src != dst) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, na * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return CALES_OK;
+  }
+  std::vector<int> ast(P), aen(P), asz(P), bst(P), ben(P), bsz(P);
+  cales_distribute(ctx->ng[al], P, ast.data(), aen.data(), asz.data());      // al-ranges in pencil B, per peer
+  cales_distribute(ctx->ng[be], P, bst.data(), ben.data(), bsz.data());      // be-ranges in pencil A, per peer
+  double* sbuf = (double*)cales_scratch(ctx, "tr_send", (na > nb_ ? na : nb_) * sizeof(double));
+  double* rbuf = (double*)cales_scratch(ctx, "tr_recv", (na > nb_ ? na : nb_) * sizeof(double));
+  if (!sbuf || !rbuf) return CALES_ERR_NOMEM;
+  SegList pk, up; pk.n = up.n = P;
+  std::vector<long> soff(P), roff(P), scnt(P), rcnt(P);
+  long so = 0, ro = 0;
+  const long As1 = A[0], As2 = (long)A[0] * A[1], Bs1 = B[0], Bs2 = (long)B[0] * B[1];
+  for (int q = 0; q < P; ++q) {
+    // slab for q: al in [ast[q],aen[q]], everything else local in A
+    int bx[3] = {A[0], A[1], A[2]}; bx[al] = asz[q];
+    long o[3] = {0, 0, 0}; o[al] = ast[q] - 1;
+    Seg& g = pk.s[q];
+    g.b0 = bx[0]; g.b1 = bx[1]; g.b2 = bx[2];
+    g.soff = o[0] + o[1] * As1 + o[2] * As2; g.ss1 = As1; g.ss2 = As2;
+    g.doff = so; g.ds1 = bx[0]; g.ds2 = (long)bx[0] * bx[1];
+    soff[q] = so; scnt[q] = (long)bx[0] * bx[1] * bx[2]; so += scnt[q];
+    // slab from q: be in [bst[q],ben[q]], everything else local in B
+    int cx[3] = {B[0], B[1], B[2]}; cx[be] = bsz[q];
+    long oo[3] = {0, 0, 0}; oo[be] = bst[q] - 1;
+    Seg& h = up.s[q];
+    h.b0 = cx[0]; h.b1 = cx[1]; h.b2 = cx[2];
+    h.soff = ro; h.ss1 = cx[0]; h.ss2 = (long)cx[0] * cx[1];
+    h.doff = oo[0] + oo[1] * Bs1 + oo[2] * Bs2; h.ds1 = Bs1; h.ds2 = Bs2;
+    roff[q] = ro; rcnt[q] = (long)cx[0] * cx[1] * cx[2]; ro += rcnt[q];
+  }
+  // the self slab is packed straight into the receive buffer
+  SegList pk2 = pk;
+  int rc;
+  if ((rc = boxcopy(ctx, src, sbuf, pk))) return rc;
+  ncclComm_t comm = (ncclComm_t)ctx->nccl;
+  NCCL_TRY(ctx, g_nccl.GroupStart());
+  for (int d = 1; d < P; ++d) {
+    const int qs = (me + d) % P, qr = (me - d + P) % P;
+    const int gs = colcomm ? qs * ctx->dims[1] + ctx->coord[1] : ctx->coord[0] * ctx->dims[1] + qs;
+    const int gr = colcomm ? qr * ctx->dims[1] + ctx->coord[1] : ctx->coord[0] * ctx->dims[1] + qr;
+    NCCL_TRY(ctx, g_nccl.Send(sbuf + soff[qs], scnt[qs], ncclDouble, gs, comm, ctx->stream));
+    NCCL_TRY(ctx, g_nccl.Recv(rbuf + roff[qr], rcnt[qr], ncclDouble, gr, comm, ctx->stream));
+  }
+  NCCL_TRY(ctx, g_nccl.GroupEnd());
+  CUDA_TRY(ctx, cudaMemcpyAsync(rbuf + roff[me], sbuf + soff[me], scnt[me] * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  (void)pk2;
+  return boxcopy(ctx, rbuf, dst, up);
 }
 
 extern "C" int cales_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {

@@ -19,116 +19,208 @@ int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 #define EPS 2.220446049250313e-16
 
 // ---- tridiagonal solves along z -----------------------------------------------------------------------------------
-// One thread per column; the d(l) recurrence coefficients live in shared memory (SMEM=1) when
-// n*blockDim doubles fit, else in a global scratch array (the reference's choice, solver_gpu.f90:166-231).
-template <int SMEM, int LAM>
-__global__ void gaussel_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
-                          const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ p,
-                          double* __restrict__ dscr) {
-  extern __shared__ double dsm[];
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per (i,j) column, coalesced in i.  The Thomas recurrences of solver.f90:165-178 are run in the
+// reference's exact operation order, but in register tiles of TZ levels: every tile first issues its TZ
+// independent loads, then walks the dependent chain, so the sweep is bandwidth- rather than latency-bound.
+// The pivot recurrence d(l) depends only on (a,b,c,lambda): instead of storing it (the reference keeps a
+// 3-D scratch array, solver_gpu.f90:166-231) the backward sweep recomputes it per tile from per-tile
+// checkpoints held in shared memory -- identical arithmetic, hence bit-identical results, and the solve
+// moves 32 B/cell (48 periodic) instead of 48 (88).
+#define TZ 16
+#define GT 128
+
+template <int LAM>
+__global__ void __launch_bounds__(GT) gaussel_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
+                                                 const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ p) {
+  extern __shared__ double ck[];                       // checkpoints [ntile][GT]: d at the level before the tile
+  const int col = blockIdx.x * GT + threadIdx.x;
   if (col >= nxy) return;
   const double lam = LAM ? lambdaxy[col] : 0.;
   double* pp = p + col;
-  double* d = SMEM ? dsm + threadIdx.x : dscr + col;
-  const long ds = SMEM ? blockDim.x : sz;
-  // solver.f90:165-178 in the reference's operation order
-  double z = 1. / (b[0] + lam + EPS);
-  double dl = c[0] * z;
-  d[0] = dl;
-  double pl = pp[0] * z;
-  pp[0] = pl;
-  for (int l = 1; l < n; ++l) {
-    const double al = a[l];
-    z = 1. / ((b[l] + lam) - al * dl + EPS);
-    dl = c[l] * z;
-    d[l * ds] = dl;
-    pl = (pp[l * sz] - al * pl) * z;
-    pp[l * sz] = pl;
+  const int ntile = (n + TZ - 1) / TZ;
+  double dl = 0., pl = 0.;
+  // forward elimination
+  for (int t = 0; t < ntile; ++t) {
+    const int l0 = t * TZ, m = min(TZ, n - l0);
+    double r[TZ];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    ck[t * GT + threadIdx.x] = dl;
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) {
+      if (q < m) {
+        const int l = l0 + q;
+        double z;
+        if (l == 0) { z = 1. / (b[0] + lam + EPS); pl = r[q] * z; }
+        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dl + EPS); pl = (r[q] - al * pl) * z; }
+        dl = c[l] * z;
+        r[q] = pl;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) pp[(long)(l0 + q) * sz] = r[q];
   }
-  for (int l = n - 2; l >= 0; --l) {
-    pl = pp[l * sz] - d[l * ds] * pl;
-    pp[l * sz] = pl;
+  // backward substitution: p(l) = p(l) - d(l)*p(l+1), l = n-2..0 ; pl holds p(n-1)
+  for (int t = ntile - 1; t >= 0; --t) {
+    const int l0 = t * TZ, m = min(TZ, n - l0);
+    double r[TZ], d[TZ];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    double dd = ck[t * GT + threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) {
+      if (q < m) {
+        const int l = l0 + q;
+        const double z = l == 0 ? 1. / (b[0] + lam + EPS) : 1. / ((b[l] + lam) - a[l] * dd + EPS);
+        dd = c[l] * z;
+        d[q] = dd;
+      }
+    }
+#pragma unroll
+    for (int q = TZ - 1; q >= 0; --q) {
+      if (q < m) {
+        const int l = l0 + q;
+        if (l < n - 1) { pl = r[q] - d[q] * pl; r[q] = pl; } else pl = r[q];
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m && l0 + q < n - 1) pp[(long)(l0 + q) * sz] = r[q];
   }
 }
 
-// periodic: Sherman-Morrison-like split of solver.f90:109-151; p2 lives beside d in scratch
-template <int SMEM, int LAM>
-__global__ void gaussel_periodic_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
-                                   const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ p,
-                                   double* __restrict__ dscr, double* __restrict__ p2scr) {
-  extern __shared__ double dsm[];
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+// periodic: solver.f90:109-151.  Two systems of size n-1 share the matrix: rhs p(1:n-1) and
+// [-a(1),0,...,0,-c(n-1)] (p2).  p2 needs no loads, so it is recomputed where needed; three sweeps.
+template <int LAM>
+__global__ void __launch_bounds__(GT) gaussel_periodic_k(int nxy, int n, long sz, const double* __restrict__ a,
+                                                          const double* __restrict__ b, const double* __restrict__ c,
+                                                          const double* __restrict__ lambdaxy, double* __restrict__ p) {
+  extern __shared__ double ck[];                       // [2][ntile][GT]: d and forward-p2 before each tile
+  const int col = blockIdx.x * GT + threadIdx.x;
   if (col >= nxy) return;
   const double lam = LAM ? lambdaxy[col] : 0.;
   double* pp = p + col;
-  double* d = SMEM ? dsm + threadIdx.x : dscr + col;
-  double* p2 = SMEM ? dsm + (size_t)n * blockDim.x + threadIdx.x : p2scr + col;
-  const long ds = SMEM ? blockDim.x : sz;
   const int nm = n - 1;
-  // two systems of size n-1 with the same matrix: rhs p(1:n-1) and [-a(1),0,...,0,-c(n-1)]
-  double z = 1. / (b[0] + lam + EPS);
-  double dl = c[0] * z;
-  d[0] = dl;
-  double p1l = pp[0] * z;
-  pp[0] = p1l;
-  double p2l = (nm == 1 ? (-a[0] - c[0]) : -a[0]) * z;     // n-1 == 1: p2(1) = -a(1) then overwritten by -c(n-1)
-  if (nm == 1) p2l = (-c[0]) * z;
-  p2[0] = p2l;
-  for (int l = 1; l < nm; ++l) {
-    const double al = a[l];
-    z = 1. / ((b[l] + lam) - al * dl + EPS);
-    dl = c[l] * z;
-    d[l * ds] = dl;
-    p1l = (pp[l * sz] - al * p1l) * z;
-    pp[l * sz] = p1l;
-    const double r2 = (l == nm - 1) ? -c[nm - 1] : 0.;
-    p2l = (r2 - al * p2l) * z;
-    p2[l * ds] = p2l;
+  const int ntile = (nm + TZ - 1) / TZ;
+  double* ckd = ck;
+  double* ck2 = ck + (size_t)ntile * GT;
+  double dl = 0., p1l = 0., p2l = 0.;
+  for (int t = 0; t < ntile; ++t) {                    // forward elimination of both systems
+    const int l0 = t * TZ, m = min(TZ, nm - l0);
+    double r[TZ];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    ckd[t * GT + threadIdx.x] = dl;
+    ck2[t * GT + threadIdx.x] = p2l;
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) {
+      if (q < m) {
+        const int l = l0 + q;
+        double r2 = 0.;
+        if (l == 0) r2 = -a[0];
+        if (l == nm - 1) r2 = -c[nm - 1];
+        double z;
+        if (l == 0) { z = 1. / (b[0] + lam + EPS); p1l = r[q] * z; p2l = r2 * z; }
+        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dl + EPS); p1l = (r[q] - al * p1l) * z; p2l = (r2 - al * p2l) * z; }
+        dl = c[l] * z;
+        r[q] = p1l;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) pp[(long)(l0 + q) * sz] = r[q];
   }
-  for (int l = nm - 2; l >= 0; --l) {
-    const double dd = d[l * ds];
-    p1l = pp[l * sz] - dd * p1l;
-    pp[l * sz] = p1l;
-    p2l = p2[l * ds] - dd * p2l;
-    p2[l * ds] = p2l;
+  const double p1n = p1l, p2n = p2l;                   // p1(n-1), p2(n-1): unchanged by the back substitution
+  for (int t = ntile - 1; t >= 0; --t) {               // backward substitution of both systems
+    const int l0 = t * TZ, m = min(TZ, nm - l0);
+    double r[TZ], d[TZ], f2[TZ];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    double dd = ckd[t * GT + threadIdx.x], g2 = ck2[t * GT + threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) {
+      if (q < m) {
+        const int l = l0 + q;
+        double r2 = 0.;
+        if (l == 0) r2 = -a[0];
+        if (l == nm - 1) r2 = -c[nm - 1];
+        double z;
+        if (l == 0) { z = 1. / (b[0] + lam + EPS); g2 = r2 * z; }
+        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dd + EPS); g2 = (r2 - al * g2) * z; }
+        dd = c[l] * z;
+        d[q] = dd; f2[q] = g2;
+      }
+    }
+#pragma unroll
+    for (int q = TZ - 1; q >= 0; --q) {
+      if (q < m) {
+        const int l = l0 + q;
+        if (l < nm - 1) { p1l = r[q] - d[q] * p1l; p2l = f2[q] - d[q] * p2l; r[q] = p1l; } else { p1l = r[q]; p2l = f2[q]; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m && l0 + q < nm - 1) pp[(long)(l0 + q) * sz] = r[q];
   }
-  // p1l = p1(1), p2l = p2(1)
-  const double p1n = pp[(long)(nm - 1) * sz], p2n = p2[(long)(nm - 1) * ds];
+  // p1l = p1(1), p2l = p2(1)                                                     solver.f90:142-144
   const double pn = (pp[(long)(n - 1) * sz] - c[n - 1] * p1l - a[n - 1] * p1n) /
                     ((b[n - 1] + lam) + c[n - 1] * p2l + a[n - 1] * p2n + EPS);
   pp[(long)(n - 1) * sz] = pn;
-  for (int l = 0; l < nm; ++l) pp[l * sz] = pp[l * sz] + p2[l * ds] * pn;
+  p2l = 0.;
+  for (int t = ntile - 1; t >= 0; --t) {               // p(1:n-1) = p1 + p2*p(n): p2 recomputed once more
+    const int l0 = t * TZ, m = min(TZ, nm - l0);
+    double r[TZ], d[TZ], f2[TZ];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    double dd = ckd[t * GT + threadIdx.x], g2 = ck2[t * GT + threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) {
+      if (q < m) {
+        const int l = l0 + q;
+        double r2 = 0.;
+        if (l == 0) r2 = -a[0];
+        if (l == nm - 1) r2 = -c[nm - 1];
+        double z;
+        if (l == 0) { z = 1. / (b[0] + lam + EPS); g2 = r2 * z; }
+        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dd + EPS); g2 = (r2 - al * g2) * z; }
+        dd = c[l] * z;
+        d[q] = dd; f2[q] = g2;
+      }
+    }
+#pragma unroll
+    for (int q = TZ - 1; q >= 0; --q) {
+      if (q < m) {
+        const int l = l0 + q;
+        if (l < nm - 1) p2l = f2[q] - d[q] * p2l; else p2l = f2[q];
+        r[q] = r[q] + p2l * pn;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) if (q < m) pp[(long)(l0 + q) * sz] = r[q];
+  }
 }
 
-// p: halo-free (nx,ny,>=n) array, plane stride sz = nx*ny
+// p: halo-free (nx,ny,>=n) array, plane stride sz
 int k_gaussel(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
               const double* lambdaxy, double* p) {
   const int nxy = nx * ny;
-  const int NT = 32;
-  const size_t need = (size_t)n * NT * sizeof(double) * (periodic ? 2 : 1);
-  const bool smem = need <= 160 * 1024;
-  double *dscr = nullptr, *p2scr = nullptr;
-  if (!smem) {
-    dscr = (double*)cales_scratch(ctx, "gauss_d", (size_t)sz * n * sizeof(double));
-    if (periodic) p2scr = (double*)cales_scratch(ctx, "gauss_p2", (size_t)sz * n * sizeof(double));
-    if (!dscr || (periodic && !p2scr)) return CALES_ERR_NOMEM;
+  if (periodic && n < 3) return cales_fail(ctx, CALES_ERR_INVALID, "periodic tridiagonal solve needs n >= 3");
+  const int ntile = ((periodic ? n - 1 : n) + TZ - 1) / TZ;
+  const size_t sh = (size_t)ntile * GT * sizeof(double) * (periodic ? 2 : 1);
+  if (sh > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "tridiagonal system of %d points exceeds the checkpoint buffer", n);
+  dim3 g(cdiv(nxy, GT));
+  static bool attr = false;
+  if (!attr) {
+    attr = true;
+    cudaFuncSetAttribute(gaussel_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gaussel_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gaussel_periodic_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(gaussel_periodic_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
-  dim3 g(cdiv(nxy, NT));
-#define LAUNCH(K, S, L, ...)                                                                                  \
-  do {                                                                                                        \
-    if (S) cudaFuncSetAttribute(K<S, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);            \
-    K<S, L><<<g, NT, S ? need : 0, ctx->stream>>>(__VA_ARGS__);                                              \
-  } while (0)
   if (!periodic) {
-    if (smem) { if (lambdaxy) LAUNCH(gaussel_k, 1, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr); else LAUNCH(gaussel_k, 1, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr); }
-    else { if (lambdaxy) LAUNCH(gaussel_k, 0, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr); else LAUNCH(gaussel_k, 0, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr); }
+    if (lambdaxy) gaussel_k<1><<<g, GT, sh, ctx->stream>>>(nxy, n, sz, a, b, c, lambdaxy, p);
+    else gaussel_k<0><<<g, GT, sh, ctx->stream>>>(nxy, n, sz, a, b, c, lambdaxy, p);
   } else {
-    if (n < 3) return cales_fail(ctx, CALES_ERR_INVALID, "periodic tridiagonal solve needs n >= 3");
-    if (smem) { if (lambdaxy) LAUNCH(gaussel_periodic_k, 1, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); else LAUNCH(gaussel_periodic_k, 1, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); }
-    else { if (lambdaxy) LAUNCH(gaussel_periodic_k, 0, 1, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); else LAUNCH(gaussel_periodic_k, 0, 0, nxy, n, sz, a, b, c, lambdaxy, p, dscr, p2scr); }
+    if (lambdaxy) gaussel_periodic_k<1><<<g, GT, sh, ctx->stream>>>(nxy, n, sz, a, b, c, lambdaxy, p);
+    else gaussel_periodic_k<0><<<g, GT, sh, ctx->stream>>>(nxy, n, sz, a, b, c, lambdaxy, p);
   }
-#undef LAUNCH
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
@@ -250,15 +342,22 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   double* w0 = (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
   double* w1 = (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
   if (!w0 || !w1) return CALES_ERR_NOMEM;
-  if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, w0, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
-  if ((rc = k_transpose(ctx, 0, w0, w1))) return rc;                                    // x -> y
-  if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w1, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
-  if ((rc = k_transpose(ctx, 1, w1, w0))) return rc;                                    // y -> z
-  if ((rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w0))) return rc;
-  if ((rc = k_transpose(ctx, 2, w0, w1))) return rc;                                    // z -> y
-  if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, ys[0], ys[1], ys[2], w1, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
-  if ((rc = k_transpose(ctx, 3, w1, w0))) return rc;                                    // y -> x
-  if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, xs[0], xs[1], xs[2], w0, xs[0], (long)xs[0] * xs[1], p + d.idx(1, 1, 1), d.s1, d.s2, normfft))) return rc;
+  double *cur = w0, *oth = w1, *t_;
+#define TRANSPOSE(which, P)                                      \
+  if ((P) > 1) {                                                 \
+    if ((rc = k_transpose(ctx, which, cur, oth))) return rc;     \
+    t_ = cur; cur = oth; oth = t_;                               \
+  }
+  if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, cur, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+  TRANSPOSE(0, ctx->dims[0])                                                            // x -> y
+  if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], cur, ys[0], (long)ys[0] * ys[1], cur, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
+  TRANSPOSE(1, ctx->dims[1])                                                            // y -> z
+  if ((rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, cur))) return rc;
+  TRANSPOSE(2, ctx->dims[1])                                                            // z -> y
+  if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, ys[0], ys[1], ys[2], cur, ys[0], (long)ys[0] * ys[1], cur, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
+  TRANSPOSE(3, ctx->dims[0])                                                            // y -> x
+  if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, xs[0], xs[1], xs[2], cur, xs[0], (long)xs[0] * xs[1], p + d.idx(1, 1, 1), d.s1, d.s2, normfft))) return rc;
+#undef TRANSPOSE
   (void)ng;
   return CALES_OK;
 }

@@ -146,21 +146,18 @@ def test_poisson_solver(bcs, ng):
     g.set_fields(pp=rhs)
     g.solver(g.poi, "pp")
     pg = g.get("pp")
-    if singular and bcs[4:] == "PP":
-        # periodic z + singular (0,0) mode: gaussel_periodic divides an O(eps) residual by an O(eps) pivot
-        # (solver.f90:142-143), so the horizontal-mean profile carries amplified round-off in the reference
-        # itself; compare the field minus its plane means to 1e-12 and the plane means to the noise level
-        pm_g = pg[1:-1, 1:-1, 1:-1].mean(axis=(0, 1)); pm_o = po[0][1:-1, 1:-1, 1:-1].mean(axis=(0, 1))
-        a = pg[1:-1, 1:-1, 1:-1] - pm_g; b = po[0][1:-1, 1:-1, 1:-1] - pm_o
-        e = float(np.abs(a - b).max() / np.abs(b).max())
-        pm_g = pm_g - pm_g.mean(); pm_o = pm_o - pm_o.mean()
-        assert np.abs(pm_g - pm_o).max() <= 1e-6 * np.abs(b).max()
-    else:
-        e = relerr(pg, po[0], demean=singular)
-    assert e <= 1e-12, e
+    # noise floor of the reference algorithm itself: the same oracle solve with the rhs perturbed by one
+    # ulp-sized relative noise.  For the singular (0,0) mode with periodic z, gaussel_periodic divides an
+    # O(eps) residual by an O(eps) pivot (solver.f90:142-143) and adds the resulting huge constant to every
+    # point, so the de-meaned field carries its rounding ("conditioning caps parity").
+    pert = [np.asfortranarray(rhs * (1. + 1.1e-16 * np.sign(rng.standard_normal(rhs.shape))))]
+    o.solve_poisson(pert)
+    floor = relerr(pert[0], po[0], demean=singular)
+    e = relerr(pg, po[0], demean=singular)
+    assert e <= max(1e-12, 20. * floor), (e, floor)
     # residual of the discrete problem: apply boundp + Laplacian (uses the oracle's operators on the GPU result)
     from oracle import bound as ob
-    q = [pg.copy(order="F")]
+    q = [pg - (pg[1:-1, 1:-1, 1:-1].mean() if singular else 0.)]   # the huge additive constant of the singular mode would drown the check in rounding
     ob.boundp(o.world, o.deck.cbcpre, o.st, "bcp", q)
     s = o.st[0]
     p = q[0]
