@@ -206,65 +206,81 @@ static int boxcopy(cales_ctx* ctx, const double* src, double* dst, const SegList
   return CALES_OK;
 }
 
+// Pure-integer exchange plan of one transpose (usable without a device; the world_size-2 gloo test drives it).
+// For every peer q of my row/column: global rank, the sub-box of pencil A sent to q and the sub-box of pencil B
+// received from q, each as {offset(3), extent(3)} in local 0-based indices.  Returns the pencil shapes too.
+extern "C" int cales_transpose_plan(const int ng[3], const int dims[2], int rank, int which, int* npeers, int* peers,
+                                    int* sendbox, int* recvbox, int shapeA[3], int shapeB[3]) {
+  if (which < 0 || which > 3 || rank < 0 || rank >= dims[0] * dims[1]) return CALES_ERR_INVALID;
+  int lo[3], hi[3], A[3], B[3];
+  const int axA = which == 0 ? 1 : (which == 1 || which == 3) ? 2 : 3;
+  const int axB = which == 0 ? 2 : which == 1 ? 3 : which == 2 ? 2 : 1;
+  cales_pencil(ng, dims, rank, axA, lo, hi, A);
+  cales_pencil(ng, dims, rank, axB, lo, hi, B);
+  const int al = which == 0 ? 0 : which == 1 ? 1 : which == 2 ? 2 : 1;
+  const int be = which == 0 ? 1 : which == 1 ? 2 : which == 2 ? 1 : 0;
+  const bool colcomm = (which == 0 || which == 3);
+  const int P = colcomm ? dims[0] : dims[1];
+  const int coord[2] = {rank / dims[1], rank % dims[1]};
+  std::vector<int> ast(P), aen(P), asz(P), bst(P), ben(P), bsz(P);
+  cales_distribute(ng[al], P, ast.data(), aen.data(), asz.data());
+  cales_distribute(ng[be], P, bst.data(), ben.data(), bsz.data());
+  *npeers = P;
+  for (int q = 0; q < P; ++q) {
+    peers[q] = colcomm ? q * dims[1] + coord[1] : coord[0] * dims[1] + q;
+    int* sb = sendbox + 6 * q; int* rb = recvbox + 6 * q;
+    for (int d = 0; d < 3; ++d) { sb[d] = 0; sb[3 + d] = A[d]; rb[d] = 0; rb[3 + d] = B[d]; }
+    sb[al] = ast[q] - 1; sb[3 + al] = asz[q];
+    rb[be] = bst[q] - 1; rb[3 + be] = bsz[q];
+  }
+  for (int d = 0; d < 3; ++d) { shapeA[d] = A[d]; shapeB[d] = B[d]; }
+  return CALES_OK;
+}
+
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {
   // which: 0 x->y, 1 y->z, 2 z->y, 3 y->x
-  const int* A = which == 0 ? ctx->xsz : (which == 1 || which == 3) ? ctx->ysz : ctx->zsz;
-  const int* B = which == 0 ? ctx->ysz : which == 1 ? ctx->zsz : which == 2 ? ctx->ysz : ctx->xsz;
-  const int al = which == 0 ? 0 : which == 1 ? 1 : which == 2 ? 2 : 1;      // complete in A, split in B
-  const int be = which == 0 ? 1 : which == 1 ? 2 : which == 2 ? 1 : 0;      // split in A, complete in B
-  const bool colcomm = (which == 0 || which == 3);                           // x<->y: ranks differ in coord(1) of the grid = index 0
-  const int P = colcomm ? ctx->dims[0] : ctx->dims[1];
+  int P, peers[16], sendbox[96], recvbox[96], A[3], B[3];
+  const bool colcomm = (which == 0 || which == 3);
+  if ((colcomm ? ctx->dims[0] : ctx->dims[1]) > 16) return cales_fail(ctx, CALES_ERR_INVALID, "transpose: at most 16 ranks per row/column supported");
+  if (cales_transpose_plan(ctx->ng, ctx->dims, ctx->rank, which, &P, peers, sendbox, recvbox, A, B)) return cales_fail(ctx, CALES_ERR_INVALID, "transpose plan failed");
   const int me = colcomm ? ctx->coord[0] : ctx->coord[1];
-  if (P > 16) return cales_fail(ctx, CALES_ERR_INVALID, "transpose over %d ranks: at most 16 per row/column supported", P);
   const size_t na = (size_t)A[0] * A[1] * A[2], nb_ = (size_t)B[0] * B[1] * B[2];
   if (P == 1) {                                                              // same data, same layout
     if (src != dst) CUDA_TRY(ctx, cudaMemcpyAsync(dst, src, na * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return CALES_OK;
   }
-  std::vector<int> ast(P), aen(P), asz(P), bst(P), ben(P), bsz(P);
-  cales_distribute(ctx->ng[al], P, ast.data(), aen.data(), asz.data());      // al-ranges in pencil B, per peer
-  cales_distribute(ctx->ng[be], P, bst.data(), ben.data(), bsz.data());      // be-ranges in pencil A, per peer
   double* sbuf = (double*)cales_scratch(ctx, "tr_send", (na > nb_ ? na : nb_) * sizeof(double));
   double* rbuf = (double*)cales_scratch(ctx, "tr_recv", (na > nb_ ? na : nb_) * sizeof(double));
   if (!sbuf || !rbuf) return CALES_ERR_NOMEM;
   SegList pk, up; pk.n = up.n = P;
-  std::vector<long> soff(P), roff(P), scnt(P), rcnt(P);
+  long soff[16], roff[16], scnt[16], rcnt[16];
   long so = 0, ro = 0;
   const long As1 = A[0], As2 = (long)A[0] * A[1], Bs1 = B[0], Bs2 = (long)B[0] * B[1];
   for (int q = 0; q < P; ++q) {
-    // slab for q: al in [ast[q],aen[q]], everything else local in A
-    int bx[3] = {A[0], A[1], A[2]}; bx[al] = asz[q];
-    long o[3] = {0, 0, 0}; o[al] = ast[q] - 1;
+    const int* sb = sendbox + 6 * q; const int* rb = recvbox + 6 * q;
     Seg& g = pk.s[q];
-    g.b0 = bx[0]; g.b1 = bx[1]; g.b2 = bx[2];
-    g.soff = o[0] + o[1] * As1 + o[2] * As2; g.ss1 = As1; g.ss2 = As2;
-    g.doff = so; g.ds1 = bx[0]; g.ds2 = (long)bx[0] * bx[1];
-    soff[q] = so; scnt[q] = (long)bx[0] * bx[1] * bx[2]; so += scnt[q];
-    // slab from q: be in [bst[q],ben[q]], everything else local in B
-    int cx[3] = {B[0], B[1], B[2]}; cx[be] = bsz[q];
-    long oo[3] = {0, 0, 0}; oo[be] = bst[q] - 1;
+    g.b0 = sb[3]; g.b1 = sb[4]; g.b2 = sb[5];
+    g.soff = sb[0] + sb[1] * As1 + sb[2] * As2; g.ss1 = As1; g.ss2 = As2;
+    g.doff = so; g.ds1 = sb[3]; g.ds2 = (long)sb[3] * sb[4];
+    soff[q] = so; scnt[q] = (long)sb[3] * sb[4] * sb[5]; so += scnt[q];
     Seg& h = up.s[q];
-    h.b0 = cx[0]; h.b1 = cx[1]; h.b2 = cx[2];
-    h.soff = ro; h.ss1 = cx[0]; h.ss2 = (long)cx[0] * cx[1];
-    h.doff = oo[0] + oo[1] * Bs1 + oo[2] * Bs2; h.ds1 = Bs1; h.ds2 = Bs2;
-    roff[q] = ro; rcnt[q] = (long)cx[0] * cx[1] * cx[2]; ro += rcnt[q];
+    h.b0 = rb[3]; h.b1 = rb[4]; h.b2 = rb[5];
+    h.soff = ro; h.ss1 = rb[3]; h.ss2 = (long)rb[3] * rb[4];
+    h.doff = rb[0] + rb[1] * Bs1 + rb[2] * Bs2; h.ds1 = Bs1; h.ds2 = Bs2;
+    roff[q] = ro; rcnt[q] = (long)rb[3] * rb[4] * rb[5]; ro += rcnt[q];
   }
-  // the self slab is packed straight into the receive buffer
-  SegList pk2 = pk;
   int rc;
   if ((rc = boxcopy(ctx, src, sbuf, pk))) return rc;
   ncclComm_t comm = (ncclComm_t)ctx->nccl;
   NCCL_TRY(ctx, g_nccl.GroupStart());
   for (int d = 1; d < P; ++d) {
     const int qs = (me + d) % P, qr = (me - d + P) % P;
-    const int gs = colcomm ? qs * ctx->dims[1] + ctx->coord[1] : ctx->coord[0] * ctx->dims[1] + qs;
-    const int gr = colcomm ? qr * ctx->dims[1] + ctx->coord[1] : ctx->coord[0] * ctx->dims[1] + qr;
-    NCCL_TRY(ctx, g_nccl.Send(sbuf + soff[qs], scnt[qs], ncclDouble, gs, comm, ctx->stream));
-    NCCL_TRY(ctx, g_nccl.Recv(rbuf + roff[qr], rcnt[qr], ncclDouble, gr, comm, ctx->stream));
+    NCCL_TRY(ctx, g_nccl.Send(sbuf + soff[qs], scnt[qs], ncclDouble, peers[qs], comm, ctx->stream));
+    NCCL_TRY(ctx, g_nccl.Recv(rbuf + roff[qr], rcnt[qr], ncclDouble, peers[qr], comm, ctx->stream));
   }
   NCCL_TRY(ctx, g_nccl.GroupEnd());
+  // the self slab never leaves the device
   CUDA_TRY(ctx, cudaMemcpyAsync(rbuf + roff[me], sbuf + soff[me], scnt[me] * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-  (void)pk2;
   return boxcopy(ctx, rbuf, dst, up);
 }
 

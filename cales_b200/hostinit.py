@@ -31,13 +31,15 @@ def initgrid(gtype, n, gr, lz):
     elif gtype == 6:
         dzc_ = float(f32(f32(0.1) * f32(32.0)) / f32(n))
         z = z0 - (dzc_ * n / 2. - 1.) / (2. * pi) * np.sin(2. * pi * z0)
-    else:  # gtype 5, Pirozzoli & Orlandi natural stretching
+    else:  # gtype 5, Pirozzoli & Orlandi natural stretching (scalar arithmetic, as the Fortran routine)
         kb, alpha, c_eta, dyp = 32., pi / 1.5, 0.8, 0.05
         nn = n / 2.
         retau = 1. / (1. + (nn / kb) ** 2) * (dyp * nn + (3. / 4. * alpha * c_eta * nn) ** (4. / 3.) * (nn / kb) ** 2)
-        kk = 1. * np.minimum(k, n - k)
-        z = 1. / (1. + (kk / kb) ** 2) * (dyp * kk + (3. / 4. * alpha * c_eta * kk) ** (4. / 3.) * (kk / kb) ** 2) / (2. * retau)
-        z = np.where(k > n - k, 1. - z, z)
+        z = np.zeros(n)
+        for kg in range(1, n + 1):
+            kk = 1. * min(kg, n - kg)
+            zz = 1. / (1. + (kk / kb) ** 2) * (dyp * kk + (3. / 4. * alpha * c_eta * kk) ** (4. / 3.) * (kk / kb) ** 2) / (2. * retau)
+            z[kg - 1] = 1. - zz if kg > n - kg else zz
     zf = np.zeros(n + 2); dzf = np.zeros(n + 2); dzc = np.zeros(n + 2); zc = np.zeros(n + 2)
     zf[1:n + 1] = z * lz
     dzf[1:n + 1] = zf[1:n + 1] - zf[0:n]

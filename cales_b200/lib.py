@@ -55,6 +55,7 @@ SIGNATURES = {
     "cales_distribute": (C.c_int, [C.c_int, C.c_int, c_int_p, c_int_p, c_int_p]),
     "cales_pencil": (C.c_int, [c_int_p, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p]),
     "cales_neighbours": (C.c_int, [c_int_p, C.c_int, C.c_char_p, C.c_int, c_int_p, c_int_p]),
+    "cales_transpose_plan": (C.c_int, [c_int_p, c_int_p, C.c_int, C.c_int, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     "cales_stream_synchronize": (C.c_int, [vp]),
     "cales_launch_count": (C.c_long, [vp]),
     "cales_initsolver": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, C.c_char_p,

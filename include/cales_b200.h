@@ -81,6 +81,11 @@ int cales_get_decomp(const cales_ctx* ctx, int lo[3], int hi[3], int n[3], int n
 int cales_distribute(int data1, int proc, int* st, int* en, int* sz);
 int cales_pencil(const int ng[3], const int dims[2], int rank, int axis /*1,2,3*/, int lo[3], int hi[3], int sz[3]);
 int cales_neighbours(const int dims[2], int ipencil, const char cbcpre[6], int rank, int nb[6], int is_bound[6]);
+/* exchange plan of one pencil transpose (which = 0 x->y, 1 y->z, 2 z->y, 3 y->x), the send/recv counts and offsets of
+ * cuDecomp transpose.h:310-327 / 2decomp transpose_x_to_y.f90:87-96: per peer q of my row/column its global rank, the
+ * sub-box {offset(3),extent(3)} of my source pencil sent to q and of my destination pencil received from q. */
+int cales_transpose_plan(const int ng[3], const int dims[2], int rank, int which, int* npeers, int* peers, int* sendbox,
+                         int* recvbox, int shapeA[3], int shapeB[3]);
 
 int cales_stream_synchronize(cales_ctx* ctx);
 /* number of kernels this library has launched on the context so far (bench.py `gpu_launches`) */

@@ -156,49 +156,48 @@ def _parse_values(s):
 
 
 def read_input(path):
-    """Read &dns and &les of an input.nml into a Deck.  Groups may be terminated by '/' or,
+    """Read &dns and &les of an input.nml into a Deck (param.f90:88-152).  Groups may be terminated by '/' or,
     as in some DNS decks, by a backslash."""
-    txt = open(path).read()
-    groups = {}
-    for m in re.finditer(r"&(\w+)(.*?)(?:^\s*[/\\]\s*$)", txt, re.S | re.M):
-        groups[m.group(1).lower()] = m.group(2)
+    txt = "\n".join(line.split("!")[0] for line in open(path).read().splitlines())
     d = Deck()
-    vals = {}
-    for g in ("dns", "les"):
-        body = groups.get(g, "")
-        # split into "name(...) = values" assignments; a value list runs until the next "name ="
-        for m in re.finditer(r"(\w+)\s*(\([^)]*\))?\s*=\s*(.*?)(?=(?:,\s*|\s+)\w+\s*(?:\([^)]*\))?\s*=|\Z)", body, re.S):
-            vals[m.group(1).lower()] = _parse_values(m.group(3))
-    def get(name, default=None):
-        return vals.get(name, default)
-    d.ng = tuple(get("ng", d.ng)); d.l = tuple(float(x) for x in get("l", d.l))
-    d.gtype = get("gtype", [d.gtype])[0]; d.gr = float(get("gr", [d.gr])[0])
+    arrays = {"cbcvel": d.cbcvel, "bcvel": d.bcvel, "cbcpre": d.cbcpre, "cbcsgs": d.cbcsgs, "bcpre": d.bcpre, "bcsgs": d.bcsgs,
+              "lwm": d.lwm}
+    scal = {}
+    for gm in re.finditer(r"&(\w+)(.*?)^\s*[/\\]\s*$", txt, re.S | re.M):
+        if gm.group(1).lower() not in ("dns", "les"):
+            continue
+        body = gm.group(2)
+        ms = list(re.finditer(r"([A-Za-z_]\w*)\s*(\([^)]*\))?\s*=", body))
+        for i, m in enumerate(ms):
+            name = m.group(1).lower()
+            vals = _parse_values(body[m.end():ms[i + 1].start() if i + 1 < len(ms) else len(body)])
+            if name in arrays:
+                arr = arrays[name]
+                spec = (m.group(2) or "").strip("()").split(",")
+                if arr.ndim == 3:
+                    k = int(spec[2]) - 1 if len(spec) == 3 and ":" not in spec[2] else None
+                    ks = [k] if k is not None else range(3)
+                    it = iter(vals)
+                    for kk in ks:
+                        for idir in range(3):
+                            for ib in range(2):
+                                arr[ib, idir, kk] = next(it)
+                else:
+                    it = iter(vals)
+                    for idir in range(3):
+                        for ib in range(2):
+                            arr[ib, idir] = next(it)
+            else:
+                scal[name] = vals
+    def get(name, default):
+        return scal.get(name, default)
+    d.ng = tuple(int(x) for x in get("ng", d.ng)); d.l = tuple(float(x) for x in get("l", d.l))
+    d.gtype = int(get("gtype", [d.gtype])[0]); d.gr = float(get("gr", [d.gr])[0])
     d.cfl = float(get("cfl", [d.cfl])[0]); d.dtmax = float(get("dtmax", [d.dtmax])[0])
     d.dt_f = float(get("dt_f", [d.dt_f])[0]); d.visci = float(get("visci", [d.visci])[0])
-    d.inivel = get("inivel", [d.inivel])[0]; d.is_wallturb = get("is_wallturb", [d.is_wallturb])[0]
-    # Fortran fills cbcvel(0:1,1:3,ivel) in column-major order: ib fastest, then idir
-    for ivel, key in enumerate(("cbcvel",)):
-        pass
-    def fill3(name, arr):
-        # several assignments "name(0:1,1:3,k) = ..." share one key in a naive parse; re-scan
-        for m in re.finditer(name + r"\(0:1,1:3,(\d)\)\s*=\s*(.*?)\n", groups.get("dns", "")):
-            v = _parse_values(m.group(2))
-            k = int(m.group(1)) - 1
-            for idir in range(3):
-                for ib in range(2):
-                    arr[ib, idir, k] = v[2 * idir + ib]
-    def fill2(name, arr, grp="dns"):
-        m = re.search(name + r"\(0:1,1:3\)\s*=\s*(.*?)\n", groups.get(grp, ""))
-        if m:
-            v = _parse_values(m.group(1))
-            for idir in range(3):
-                for ib in range(2):
-                    arr[ib, idir] = v[2 * idir + ib]
-    fill3("cbcvel", d.cbcvel); fill3("bcvel", d.bcvel)
-    fill2("cbcpre", d.cbcpre); fill2("cbcsgs", d.cbcsgs); fill2("bcpre", d.bcpre); fill2("bcsgs", d.bcsgs)
-    fill2("lwm", d.lwm, "les")
+    d.inivel = get("inivel", [d.inivel])[0]; d.is_wallturb = bool(get("is_wallturb", [d.is_wallturb])[0])
     d.bforce = tuple(float(x) for x in get("bforce", d.bforce))
-    d.is_forced = tuple(get("is_forced", d.is_forced)); d.velf = tuple(float(x) for x in get("velf", d.velf))
-    d.dims = tuple(get("dims", d.dims))
+    d.is_forced = tuple(bool(x) for x in get("is_forced", d.is_forced)); d.velf = tuple(float(x) for x in get("velf", d.velf))
+    d.dims = tuple(int(x) for x in get("dims", d.dims))
     d.sgstype = get("sgstype", [d.sgstype])[0]; d.hwm = float(get("hwm", [d.hwm])[0])
     return d

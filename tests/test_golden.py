@@ -1,0 +1,42 @@
+"""Golden fixtures (tests/golden/*.npz, made by tests/make_golden.py): the oracle must keep reproducing them
+(CPU test) and the CUDA path must reproduce them through the C ABI (GPU test)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from make_golden import GOLDEN, ROOT, run  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(GOLDEN))
+def test_oracle_reproduces_golden(name):
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    r = run(name)
+    for k in ("u", "v", "w", "p", "visct"):
+        assert np.abs(r[k] - g[k]).max() <= 1e-12 * max(np.abs(g[k]).max(), 1e-30), k
+    assert abs(float(r["dt"]) - float(g["dt"])) <= 1e-13 * float(g["dt"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(GOLDEN))
+def test_cuda_reproduces_golden(name):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device visible")
+    import cales_b200.deck as pd
+    from cales_b200.driver import Simulation
+    deck, kw, nsteps = GOLDEN[name]
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    s = Simulation(getattr(pd, deck)(**kw))
+    s.init_flow(); s.start()
+    for _ in range(nsteps):
+        res = s.step(icheck=1)
+    for k in ("u", "v", "w", "p", "visct"):
+        a = s.get(k)[1:-1, 1:-1, 1:-1]
+        if k == "p":
+            a = a - a.mean()
+        assert np.abs(a - g[k]).max() <= 1e-10 * max(np.abs(g[k]).max(), 1e-30), k
+    assert abs(s.dt - float(g["dt"])) <= 1e-10 * float(g["dt"]) and res[1] < 1e-11
+    s.close()
