@@ -42,17 +42,20 @@ __device__ __forceinline__ double2 twid(const double2* __restrict__ w, int t, bo
   return v;
 }
 
-// one Stockham stage of radix R over NL lines: src -> dst (both [NL][LS] complex)
-template <int R>
-__device__ __forceinline__ void stage(const double2* __restrict__ src, double2* __restrict__ dst, int NL, int LS, int m, int Ns,
+// Thread mapping: a CTA of FT threads owns NL lines; TPL = FT/NL consecutive threads work on one line, so no
+// integer division appears in any loop (NL, TPL are compile-time powers of two).
+#define FT 128
+
+// one Stockham stage of radix R for my line: src -> dst (complex, m points); lane = my index within the line team
+template <int R, int TPL>
+__device__ __forceinline__ void stage(const double2* __restrict__ s, double2* __restrict__ dbase, int lane, int m, int Ns,
                                       const double2* __restrict__ wm, bool inv) {
   const int nb = m / R;
   const int tstep = m / (Ns * R);
-  for (int idx = threadIdx.x; idx < NL * nb; idx += blockDim.x) {
-    const int l = idx / nb, j = idx - l * nb;
-    const int k = j % Ns;
-    const double2* s = src + l * LS;
-    double2* d = dst + l * LS + (j - k) * R + k;
+  const bool p2 = (Ns & (Ns - 1)) == 0;
+  for (int j = lane; j < nb; j += TPL) {
+    const int k = p2 ? (j & (Ns - 1)) : (j % Ns);
+    double2* d = dbase + (j - k) * R + k;
     if (R == 2) {
       double2 a = s[j], b = s[j + nb];
       if (Ns > 1) b = cmul(b, twid(wm, k * tstep, inv));
@@ -67,7 +70,7 @@ __device__ __forceinline__ void stage(const double2* __restrict__ src, double2* 
       const double2 t0 = cadd(a, c), t1 = csub(a, c), t2 = cadd(b, e), t3 = cmuli(csub(b, e), inv);
       d[0] = cadd(t0, t2); d[Ns] = cadd(t1, t3); d[2 * Ns] = csub(t0, t2); d[3 * Ns] = csub(t1, t3);
     } else {
-      // generic radix R (3, 5, any prime): O(R^2) DFT with table twiddles exp(-+2 pi i a q / R) = wm[(a q mod R) m/R]
+      // generic radix R (3, 5, any prime; R == 0 means "runtime radix in Rrt"): O(R^2) DFT with table twiddles
       const int rstep = m / R;
       for (int q = 0; q < R; ++q) {
         double2 acc = s[j];
@@ -82,14 +85,13 @@ __device__ __forceinline__ void stage(const double2* __restrict__ src, double2* 
   }
 }
 
-__device__ __forceinline__ void stage_any(int R, const double2* src, double2* dst, int NL, int LS, int m, int Ns, const double2* wm, bool inv) {
-  // runtime radix dispatch for the generic case (R prime > 5): same code path as the template's else-branch
+template <int TPL>
+__device__ __forceinline__ void stage_any(int R, const double2* __restrict__ s, double2* __restrict__ dbase, int lane, int m, int Ns,
+                                          const double2* __restrict__ wm, bool inv) {
   const int nb = m / R, tstep = m / (Ns * R), rstep = m / R;
-  for (int idx = threadIdx.x; idx < NL * nb; idx += blockDim.x) {
-    const int l = idx / nb, j = idx - l * nb;
+  for (int j = lane; j < nb; j += TPL) {
     const int k = j % Ns;
-    const double2* s = src + l * LS;
-    double2* d = dst + l * LS + (j - k) * R + k;
+    double2* d = dbase + (j - k) * R + k;
     for (int q = 0; q < R; ++q) {
       double2 acc = s[j];
       for (int a = 1; a < R; ++a) {
@@ -108,8 +110,9 @@ __device__ __forceinline__ int fwd_slot(int e, int n, int kind) {
   return (e & 1) ? n - 1 - (e >> 1) : (e >> 1);            // Makhoul: v_j = x_2j, v_{n-1-j} = x_{2j+1}
 }
 
-template <int DIR>
-__global__ void __launch_bounds__(256) fft_lines_k(FftArgs A, int NL, int LS) {
+template <int DIR, int NL>
+__global__ void __launch_bounds__(FT) fft_lines_k(FftArgs A, int LS) {
+  constexpr int TPL = FT / NL;
   extern __shared__ double2 sm[];
   double2* b0 = sm;
   double2* b1 = sm + (size_t)NL * LS;
@@ -120,14 +123,20 @@ __global__ void __launch_bounds__(256) fft_lines_k(FftArgs A, int NL, int LS) {
   const int kind = A.kind;
   const double* gin = A.in + (long)l2 * A.il2 + (long)l1_0 * A.il1;
   double* gout = A.out + (long)l2 * A.ol2 + (long)l1_0 * A.ol1;
+  const int LSD = 2 * LS;
+  // global <-> shared mapping: x-lines: TPL consecutive threads sweep one line; y-lines: NL consecutive threads
+  // take the same element of NL neighbouring lines (contiguous in memory)
+  const int gl = DIR == 0 ? threadIdx.x / TPL : threadIdx.x % NL;       // line of my global accesses
+  const int ge0 = DIR == 0 ? threadIdx.x % TPL : threadIdx.x / NL;      // first element
+  const int gstep = TPL;
+  // compute mapping: my line and my lane within its team
+  const int cl = threadIdx.x / TPL, lane = threadIdx.x % TPL;
   // ---- load ---------------------------------------------------------------------------------------------
-  {
-    double* dst = (double*)(inv ? b1 : b0);          // forward: packed complex in b0; backward: raw reals in b1
-    const int LSD = 2 * LS;
-    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-      int l, e;
-      if (DIR == 0) { l = idx / n; e = idx - l * n; } else { e = idx / nl; l = idx - e * nl; }
-      double v = gin[(long)l * A.il1 + (long)e * A.ies];
+  if (gl < nl) {
+    double* dst = (double*)(inv ? b1 : b0) + gl * LSD;  // forward: packed complex in b0; backward: raw reals in b1
+    const double* g = gin + (long)gl * A.il1;
+    for (int e = ge0; e < n; e += gstep) {
+      double v = g[(long)e * A.ies];
       int slot;
       if (!inv) {
         slot = fwd_slot(e, n, kind);
@@ -135,30 +144,33 @@ __global__ void __launch_bounds__(256) fft_lines_k(FftArgs A, int NL, int LS) {
       } else {
         slot = kind == K_DD ? n - 1 - e : e;           // DST-III(a)_k = (-1)^k DCT-III(reversed a)_k
       }
-      dst[l * LSD + slot] = v;
+      dst[slot] = v;
     }
   }
   __syncthreads();
+  const bool on = cl < nl;
   // ---- backward pre-stage: half spectrum -> packed complex Z (b1 reals -> b0 complex) --------------------------------
   if (inv) {
-    const int np = m / 2 + 1;
-    for (int idx = threadIdx.x; idx < nl * np; idx += blockDim.x) {
-      const int l = idx / np, k = idx - l * np, mk = m - k;
-      const double* R = (const double*)(b1 + (size_t)l * LS);
-      double2 Xk, Xmk;
-      if (kind == K_PP) {
-        Xk = make_double2(R[k], (k > 0 && k < m) ? R[n - k] : 0.);
-        Xmk = make_double2(R[mk], (mk > 0 && mk < m) ? R[n - mk] : 0.);
-      } else {                                       // V_k = (a_k - i a_{n-k}) e^{+i pi k/(2n)}, a_n := 0
-        const double2 hk = cconj(__ldg(A.h4 + k)), hmk = cconj(__ldg(A.h4 + mk));
-        Xk = cmul(make_double2(R[k], k > 0 ? -R[n - k] : 0.), hk);
-        Xmk = cmul(make_double2(R[mk], -R[n - mk]), hmk);
+    if (on) {
+      const int np = m / 2 + 1;
+      const double* R = (const double*)(b1 + (size_t)cl * LS);
+      double2* Z = b0 + (size_t)cl * LS;
+      for (int k = lane; k < np; k += TPL) {
+        const int mk = m - k;
+        double2 Xk, Xmk;
+        if (kind == K_PP) {
+          Xk = make_double2(R[k], (k > 0 && k < m) ? R[n - k] : 0.);
+          Xmk = make_double2(R[mk], (mk > 0 && mk < m) ? R[n - mk] : 0.);
+        } else {                                       // V_k = (a_k - i a_{n-k}) e^{+i pi k/(2n)}, a_n := 0
+          const double2 hk = cconj(__ldg(A.h4 + k)), hmk = cconj(__ldg(A.h4 + mk));
+          Xk = cmul(make_double2(R[k], k > 0 ? -R[n - k] : 0.), hk);
+          Xmk = cmul(make_double2(R[mk], -R[n - mk]), hmk);
+        }
+        const double2 Aa = cadd(Xk, cconj(Xmk));
+        const double2 Bb = cmul(csub(Xk, cconj(Xmk)), cconj(__ldg(A.wn + k)));
+        Z[k] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
+        if (k > 0 && mk != k) Z[mk] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
       }
-      const double2 Aa = cadd(Xk, cconj(Xmk));
-      const double2 Bb = cmul(csub(Xk, cconj(Xmk)), cconj(__ldg(A.wn + k)));
-      double2* Z = b0 + (size_t)l * LS;
-      Z[k] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
-      if (k > 0 && mk != k) Z[mk] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
     }
     __syncthreads();
   }
@@ -166,13 +178,17 @@ __global__ void __launch_bounds__(256) fft_lines_k(FftArgs A, int NL, int LS) {
   double2* src = b0;
   double2* dst = b1;
   int Ns = 1;
-  for (int s = 0; s < A.nfac; ++s) {
-    const int R = A.fac[s];
-    if (R == 4) stage<4>(src, dst, nl, LS, m, Ns, A.wm, inv);
-    else if (R == 2) stage<2>(src, dst, nl, LS, m, Ns, A.wm, inv);
-    else if (R == 3) stage<3>(src, dst, nl, LS, m, Ns, A.wm, inv);
-    else if (R == 5) stage<5>(src, dst, nl, LS, m, Ns, A.wm, inv);
-    else stage_any(R, src, dst, nl, LS, m, Ns, A.wm, inv);
+  for (int st = 0; st < A.nfac; ++st) {
+    const int R = A.fac[st];
+    if (on) {
+      const double2* sl = src + (size_t)cl * LS;
+      double2* dl = dst + (size_t)cl * LS;
+      if (R == 4) stage<4, TPL>(sl, dl, lane, m, Ns, A.wm, inv);
+      else if (R == 2) stage<2, TPL>(sl, dl, lane, m, Ns, A.wm, inv);
+      else if (R == 3) stage<3, TPL>(sl, dl, lane, m, Ns, A.wm, inv);
+      else if (R == 5) stage<5, TPL>(sl, dl, lane, m, Ns, A.wm, inv);
+      else stage_any<TPL>(R, sl, dl, lane, m, Ns, A.wm, inv);
+    }
     Ns *= R;
     __syncthreads();
     double2* t = src; src = dst; dst = t;
@@ -180,56 +196,56 @@ __global__ void __launch_bounds__(256) fft_lines_k(FftArgs A, int NL, int LS) {
   // result is in `src`; `dst` is free
   if (!inv) {
     // ---- forward post-stage: Z -> X (even/odd split) -> output ordering, written as reals into dst ------------------------
-    const int np = m / 2 + 1;
-    for (int idx = threadIdx.x; idx < nl * np; idx += blockDim.x) {
-      const int l = idx / np, k = idx - l * np, mk = m - k;
-      const double2* Z = src + (size_t)l * LS;
-      double* R = (double*)(dst + (size_t)l * LS);
-      const double2 Zk = Z[k], Zmk = cconj(Z[k == 0 ? 0 : mk]);
-      const double2 E = make_double2(0.5 * (Zk.x + Zmk.x), 0.5 * (Zk.y + Zmk.y));
-      const double2 D = csub(Zk, Zmk);
-      const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);          // (Zk - conj Zmk)/(2i)
-      const double2 T = cmul(__ldg(A.wn + k), O);
-      const double2 Xk = cadd(E, T), Xmk = cconj(csub(E, T));        // X[k], X[m-k]
-      if (kind == K_PP) {
-        R[k] = Xk.x;
-        if (k > 0 && k < m) R[n - k] = Xk.y;
-        R[mk] = Xmk.x;
-        if (mk > 0 && mk < m) R[n - mk] = Xmk.y;
-      } else {
-        const double2 Yk = cmul(__ldg(A.h4 + k), Xk), Ymk = cmul(__ldg(A.h4 + mk), Xmk);
-        if (kind == K_NN) {
-          R[k] = 2. * Yk.x;
-          if (k > 0) R[n - k] = -2. * Yk.y;
-          R[mk] = 2. * Ymk.x;
-          if (mk < n && mk > 0) R[n - mk] = -2. * Ymk.y;
-        } else {                                                     // reversed order for the DST
-          R[n - 1 - k] = 2. * Yk.x;
-          if (k > 0) R[k - 1] = -2. * Yk.y;
-          R[n - 1 - mk] = 2. * Ymk.x;
-          if (mk > 0) R[mk - 1] = -2. * Ymk.y;
+    if (on) {
+      const int np = m / 2 + 1;
+      const double2* Z = src + (size_t)cl * LS;
+      double* R = (double*)(dst + (size_t)cl * LS);
+      for (int k = lane; k < np; k += TPL) {
+        const int mk = m - k;
+        const double2 Zk = Z[k], Zmk = cconj(Z[k == 0 ? 0 : mk]);
+        const double2 E = make_double2(0.5 * (Zk.x + Zmk.x), 0.5 * (Zk.y + Zmk.y));
+        const double2 D = csub(Zk, Zmk);
+        const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);          // (Zk - conj Zmk)/(2i)
+        const double2 T = cmul(__ldg(A.wn + k), O);
+        const double2 Xk = cadd(E, T), Xmk = cconj(csub(E, T));        // X[k], X[m-k]
+        if (kind == K_PP) {
+          R[k] = Xk.x;
+          if (k > 0 && k < m) R[n - k] = Xk.y;
+          R[mk] = Xmk.x;
+          if (mk > 0 && mk < m) R[n - mk] = Xmk.y;
+        } else {
+          const double2 Yk = cmul(__ldg(A.h4 + k), Xk), Ymk = cmul(__ldg(A.h4 + mk), Xmk);
+          if (kind == K_NN) {
+            R[k] = 2. * Yk.x;
+            if (k > 0) R[n - k] = -2. * Yk.y;
+            R[mk] = 2. * Ymk.x;
+            if (mk < n && mk > 0) R[n - mk] = -2. * Ymk.y;
+          } else {                                                     // reversed order for the DST
+            R[n - 1 - k] = 2. * Yk.x;
+            if (k > 0) R[k - 1] = -2. * Yk.y;
+            R[n - 1 - mk] = 2. * Ymk.x;
+            if (mk > 0) R[mk - 1] = -2. * Ymk.y;
+          }
         }
       }
     }
     __syncthreads();
-    const int LSD = 2 * LS;
-    const double* Rb = (const double*)dst;
-    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-      int l, e;
-      if (DIR == 0) { l = idx / n; e = idx - l * n; } else { e = idx / nl; l = idx - e * nl; }
-      gout[(long)l * A.ol1 + (long)e * A.oes] = Rb[l * LSD + e] * A.scale;
+    if (gl < nl) {
+      const double* Rb = (const double*)dst + gl * LSD;
+      double* g = gout + (long)gl * A.ol1;
+      for (int e = ge0; e < n; e += gstep) g[(long)e * A.oes] = Rb[e] * A.scale;
     }
   } else {
     // ---- backward store: z_j -> x_2j, x_2j+1 with the inverse Makhoul permutation ------------------------------------------
-    const int LSD = 2 * LS;
-    const double* Zb = (const double*)src;
-    for (int idx = threadIdx.x; idx < nl * n; idx += blockDim.x) {
-      int l, e;
-      if (DIR == 0) { l = idx / n; e = idx - l * n; } else { e = idx / nl; l = idx - e * nl; }
-      const int q = fwd_slot(e, n, kind);
-      double v = Zb[l * LSD + q];
-      if (kind == K_DD && (e & 1)) v = -v;
-      gout[(long)l * A.ol1 + (long)e * A.oes] = v * A.scale;
+    if (gl < nl) {
+      const double* Zb = (const double*)src + gl * LSD;
+      double* g = gout + (long)gl * A.ol1;
+      for (int e = ge0; e < n; e += gstep) {
+        const int q = fwd_slot(e, n, kind);
+        double v = Zb[q];
+        if (kind == K_DD && (e & 1)) v = -v;
+        g[(long)e * A.oes] = v * A.scale;
+      }
     }
   }
 }
@@ -289,18 +305,25 @@ int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backw
   if (m == 1) A.nfac = 0;
   const int LS = m + 1;
   const size_t per_line = 2 * (size_t)LS * sizeof(double2);
-  int NL = dir == 0 ? 16 : 16;
-  while (NL > 1 && NL * per_line > 96 * 1024) NL >>= 1;
+  int NL = 8;
+  while (NL > 2 && NL * per_line > 72 * 1024) NL >>= 1;
   if (NL * per_line > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "transform length %d exceeds the shared-memory line buffer", n);
   const size_t sh = NL * per_line;
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[dir]) {
-    cudaFuncSetAttribute(dir == 0 ? fft_lines_k<0> : fft_lines_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    attr_set[dir] = true;
+  static bool attr_set = false;
+  if (!attr_set) {
+    attr_set = true;
+    cudaFuncSetAttribute(fft_lines_k<0, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fft_lines_k<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fft_lines_k<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fft_lines_k<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fft_lines_k<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(fft_lines_k<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   }
   dim3 g(cdiv(A.nl1, NL), A.nl2);
-  if (dir == 0) fft_lines_k<0><<<g, 256, sh, ctx->stream>>>(A, NL, LS);
-  else fft_lines_k<1><<<g, 256, sh, ctx->stream>>>(A, NL, LS);
+#define GO(D_, N_) fft_lines_k<D_, N_><<<g, FT, sh, ctx->stream>>>(A, LS)
+  if (dir == 0) { if (NL == 8) GO(0, 8); else if (NL == 4) GO(0, 4); else GO(0, 2); }
+  else { if (NL == 8) GO(1, 8); else if (NL == 4) GO(1, 4); else GO(1, 2); }
+#undef GO
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }

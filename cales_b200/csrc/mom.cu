@@ -14,41 +14,70 @@
 #define PY (TY + 2)
 #define PLANE (PX * PY)
 
-// stage plane k of field f into sm (PX x PY incl. halo ring), cooperative
-__device__ __forceinline__ void load_plane(double* __restrict__ sm, const double* __restrict__ f, const Dims& d, int i0, int j0, int k) {
+// Per-thread staging descriptors: every thread moves the same (at most two) tile points of each plane, so
+// the tile-local index and the global offset are computed once, not per plane.
+struct Stage {
+  long g0, g1;      // global offsets (without the k term) of my two tile points, -1 if outside the array
+  int q0, q1;       // their positions in the PX x PY tile, -1 if none
+};
+
+__device__ __forceinline__ Stage make_stage(const Dims& d, int i0, int j0) {
+  Stage st;
   const int t = threadIdx.x + TX * threadIdx.y;
-  for (int q = t; q < PLANE; q += TX * TY) {
-    const int li = q % PX, lj = q / PX;
-    const int i = i0 + li - 1, j = j0 + lj - 1;   // global (0-based halo index) of tile origin is i0,j0 >= 1
-    double val = 0.;
-    if (i <= d.n1 + 1 && j <= d.n2 + 1) val = f[d.idx(i, j, k)];
-    sm[q] = val;
+  st.q0 = t;                                   // PLANE = 340 > 256 = TX*TY: first point always exists
+  st.q1 = t + TX * TY < PLANE ? t + TX * TY : -1;
+  {
+    const int li = st.q0 % PX, lj = st.q0 / PX;
+    const int i = i0 + li - 1, j = j0 + lj - 1;
+    st.g0 = (i <= d.n1 + 1 && j <= d.n2 + 1) ? (long)i + d.s1 * j : -1;
   }
+  if (st.q1 >= 0) {
+    const int li = st.q1 % PX, lj = st.q1 / PX;
+    const int i = i0 + li - 1, j = j0 + lj - 1;
+    st.g1 = (i <= d.n1 + 1 && j <= d.n2 + 1) ? (long)i + d.s1 * j : -1;
+  } else st.g1 = -1;
+  return st;
 }
 
 template <int MODE>  // 0 explicit, 1 _IMPDIFF, 2 _IMPDIFF + _IMPDIFF_1D
-__global__ void __launch_bounds__(TX* TY) mom_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci, const double* __restrict__ dzfi,
-                                                 double visc, const double* __restrict__ u, const double* __restrict__ v,
-                                                 const double* __restrict__ w, const double* __restrict__ s,
-                                                 double* __restrict__ dudt, double* __restrict__ dvdt, double* __restrict__ dwdt,
-                                                 double* __restrict__ dudtd, double* __restrict__ dvdtd, double* __restrict__ dwdtd, int kc) {
+__global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci, const double* __restrict__ dzfi,
+                                                    double visc, const double* __restrict__ u, const double* __restrict__ v,
+                                                    const double* __restrict__ w, const double* __restrict__ s,
+                                                    double* __restrict__ dudt, double* __restrict__ dvdt, double* __restrict__ dwdt,
+                                                    double* __restrict__ dudtd, double* __restrict__ dvdtd, double* __restrict__ dwdtd, int kc) {
   extern __shared__ double smem[];   // [4 fields][3 planes][PLANE]
   const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
   const double* fld[4] = {u, v, w, s};
-  // planes k0-1 and k0
-  for (int f = 0; f < 4; ++f) {
-    load_plane(smem + (f * 3 + 0) * PLANE, fld[f], d, i0, j0, k0 - 1);
-    load_plane(smem + (f * 3 + 1) * PLANE, fld[f], d, i0, j0, k0);
+  const Stage st = make_stage(d, i0, j0);
+  double r0[4], r1[4];                // register stage of the plane in flight
+#define FETCH(k_)                                                                      \
+  {                                                                                    \
+    const long ko = d.s2 * (long)(k_);                                                 \
+    _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                    \
+      r0[f] = st.g0 >= 0 ? fld[f][st.g0 + ko] : 0.;                                    \
+      r1[f] = st.g1 >= 0 ? fld[f][st.g1 + ko] : 0.;                                    \
+    }                                                                                  \
   }
+#define COMMIT(slot)                                                                   \
+  {                                                                                    \
+    _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                    \
+      smem[(f * 3 + (slot)) * PLANE + st.q0] = r0[f];                                  \
+      if (st.q1 >= 0) smem[(f * 3 + (slot)) * PLANE + st.q1] = r1[f];                  \
+    }                                                                                  \
+  }
+  FETCH(k0 - 1) COMMIT(0)
+  FETCH(k0) COMMIT(1)
+  FETCH(k0 + 1) COMMIT(2)
+  __syncthreads();
   int pm = 0, pc = 1, pp = 2;
   const bool active = i <= d.n1 && j <= d.n2;
   const int c = (threadIdx.x + 1) + PX * (threadIdx.y + 1);
   const long n12 = (long)d.n1 * d.n2;
   for (int k = k0; k <= k1; ++k) {
-    for (int f = 0; f < 4; ++f) load_plane(smem + (f * 3 + pp) * PLANE, fld[f], d, i0, j0, k + 1);
-    __syncthreads();
+    const bool more = k < k1;
+    if (more) FETCH(k + 2)            // in flight while plane k is computed (k+2 <= n3+1)
     if (active) {
       const double* um = smem + (0 * 3 + pm) * PLANE; const double* uc = smem + (0 * 3 + pc) * PLANE; const double* up = smem + (0 * 3 + pp) * PLANE;
       const double* vm = smem + (1 * 3 + pm) * PLANE; const double* vc = smem + (1 * 3 + pc) * PLANE; const double* vp = smem + (1 * 3 + pp) * PLANE;
@@ -171,9 +200,13 @@ __global__ void __launch_bounds__(TX* TY) mom_k(Dims d, double dxi, double dyi, 
         dudtd[o] = dudtd_z_s; dvdtd[o] = dvdtd_z_s; dwdtd[o] = dwdtd_z_s;
       }
     }
+    __syncthreads();                 // everyone is done reading plane k-1 (slot pm)
+    if (more) COMMIT(pm)
     __syncthreads();
     const int tmp = pm; pm = pc; pc = pp; pp = tmp;
   }
+#undef FETCH
+#undef COMMIT
 }
 
 static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, const double* dzci, const double* dzfi, double visc,

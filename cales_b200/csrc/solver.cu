@@ -26,8 +26,21 @@ int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 // 3-D scratch array, solver_gpu.f90:166-231) the backward sweep recomputes it per tile from per-tile
 // checkpoints held in shared memory -- identical arithmetic, hence bit-identical results, and the solve
 // moves 32 B/cell (48 periodic) instead of 48 (88).
-#define TZ 16
-#define GT 128
+#define TZ 8
+#define GT 64
+
+// tile helpers: the loads of the NEXT tile are issued before the dependent chain of the current one runs
+#define LOAD_TILE(dst, t, nlev)                                                              \
+  {                                                                                          \
+    const int l0_ = (t) * TZ;                                                                \
+    _Pragma("unroll") for (int q = 0; q < TZ; ++q) if (l0_ + q < (nlev)) dst[q] = pp[(long)(l0_ + q) * sz]; \
+  }
+#define STORE_TILE(src, t, nlev)                                                             \
+  {                                                                                          \
+    const int l0_ = (t) * TZ;                                                                \
+    _Pragma("unroll") for (int q = 0; q < TZ; ++q) if (l0_ + q < (nlev)) pp[(long)(l0_ + q) * sz] = src[q]; \
+  }
+#define COPY_TILE(dst, src) { _Pragma("unroll") for (int q = 0; q < TZ; ++q) dst[q] = src[q]; }
 
 template <int LAM>
 __global__ void __launch_bounds__(GT) gaussel_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
@@ -39,17 +52,17 @@ __global__ void __launch_bounds__(GT) gaussel_k(int nxy, int n, long sz, const d
   double* pp = p + col;
   const int ntile = (n + TZ - 1) / TZ;
   double dl = 0., pl = 0.;
+  double r[TZ], rn[TZ];
   // forward elimination
+  LOAD_TILE(r, 0, n)
   for (int t = 0; t < ntile; ++t) {
-    const int l0 = t * TZ, m = min(TZ, n - l0);
-    double r[TZ];
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    const int l0 = t * TZ;
+    if (t + 1 < ntile) LOAD_TILE(rn, t + 1, n)
     ck[t * GT + threadIdx.x] = dl;
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < n) {
         double z;
         if (l == 0) { z = 1. / (b[0] + lam + EPS); pl = r[q] * z; }
         else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dl + EPS); pl = (r[q] - al * pl) * z; }
@@ -57,20 +70,20 @@ __global__ void __launch_bounds__(GT) gaussel_k(int nxy, int n, long sz, const d
         r[q] = pl;
       }
     }
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) pp[(long)(l0 + q) * sz] = r[q];
+    STORE_TILE(r, t, n)
+    COPY_TILE(r, rn)
   }
   // backward substitution: p(l) = p(l) - d(l)*p(l+1), l = n-2..0 ; pl holds p(n-1)
+  LOAD_TILE(r, ntile - 1, n)
   for (int t = ntile - 1; t >= 0; --t) {
-    const int l0 = t * TZ, m = min(TZ, n - l0);
-    double r[TZ], d[TZ];
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    const int l0 = t * TZ;
+    double d[TZ];
+    if (t > 0) LOAD_TILE(rn, t - 1, n)
     double dd = ck[t * GT + threadIdx.x];
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < n) {
         const double z = l == 0 ? 1. / (b[0] + lam + EPS) : 1. / ((b[l] + lam) - a[l] * dd + EPS);
         dd = c[l] * z;
         d[q] = dd;
@@ -78,13 +91,13 @@ __global__ void __launch_bounds__(GT) gaussel_k(int nxy, int n, long sz, const d
     }
 #pragma unroll
     for (int q = TZ - 1; q >= 0; --q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < n) {
         if (l < n - 1) { pl = r[q] - d[q] * pl; r[q] = pl; } else pl = r[q];
       }
     }
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m && l0 + q < n - 1) pp[(long)(l0 + q) * sz] = r[q];
+    STORE_TILE(r, t, n)
+    COPY_TILE(r, rn)
   }
 }
 
@@ -104,17 +117,17 @@ __global__ void __launch_bounds__(GT) gaussel_periodic_k(int nxy, int n, long sz
   double* ckd = ck;
   double* ck2 = ck + (size_t)ntile * GT;
   double dl = 0., p1l = 0., p2l = 0.;
+  double r[TZ], rn[TZ];
+  LOAD_TILE(r, 0, nm)
   for (int t = 0; t < ntile; ++t) {                    // forward elimination of both systems
-    const int l0 = t * TZ, m = min(TZ, nm - l0);
-    double r[TZ];
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    const int l0 = t * TZ;
+    if (t + 1 < ntile) LOAD_TILE(rn, t + 1, nm)
     ckd[t * GT + threadIdx.x] = dl;
     ck2[t * GT + threadIdx.x] = p2l;
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < nm) {
         double r2 = 0.;
         if (l == 0) r2 = -a[0];
         if (l == nm - 1) r2 = -c[nm - 1];
@@ -125,20 +138,21 @@ __global__ void __launch_bounds__(GT) gaussel_periodic_k(int nxy, int n, long sz
         r[q] = p1l;
       }
     }
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) pp[(long)(l0 + q) * sz] = r[q];
+    STORE_TILE(r, t, nm)
+    COPY_TILE(r, rn)
   }
   const double p1n = p1l, p2n = p2l;                   // p1(n-1), p2(n-1): unchanged by the back substitution
+  const double plast = pp[(long)(n - 1) * sz];
+  LOAD_TILE(r, ntile - 1, nm)
   for (int t = ntile - 1; t >= 0; --t) {               // backward substitution of both systems
-    const int l0 = t * TZ, m = min(TZ, nm - l0);
-    double r[TZ], d[TZ], f2[TZ];
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    const int l0 = t * TZ;
+    double d[TZ], f2[TZ];
+    if (t > 0) LOAD_TILE(rn, t - 1, nm)
     double dd = ckd[t * GT + threadIdx.x], g2 = ck2[t * GT + threadIdx.x];
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < nm) {
         double r2 = 0.;
         if (l == 0) r2 = -a[0];
         if (l == nm - 1) r2 = -c[nm - 1];
@@ -151,29 +165,28 @@ __global__ void __launch_bounds__(GT) gaussel_periodic_k(int nxy, int n, long sz
     }
 #pragma unroll
     for (int q = TZ - 1; q >= 0; --q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < nm) {
         if (l < nm - 1) { p1l = r[q] - d[q] * p1l; p2l = f2[q] - d[q] * p2l; r[q] = p1l; } else { p1l = r[q]; p2l = f2[q]; }
       }
     }
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m && l0 + q < nm - 1) pp[(long)(l0 + q) * sz] = r[q];
+    STORE_TILE(r, t, nm)
+    COPY_TILE(r, rn)
   }
   // p1l = p1(1), p2l = p2(1)                                                     solver.f90:142-144
-  const double pn = (pp[(long)(n - 1) * sz] - c[n - 1] * p1l - a[n - 1] * p1n) /
-                    ((b[n - 1] + lam) + c[n - 1] * p2l + a[n - 1] * p2n + EPS);
+  const double pn = (plast - c[n - 1] * p1l - a[n - 1] * p1n) / ((b[n - 1] + lam) + c[n - 1] * p2l + a[n - 1] * p2n + EPS);
   pp[(long)(n - 1) * sz] = pn;
   p2l = 0.;
+  LOAD_TILE(r, ntile - 1, nm)
   for (int t = ntile - 1; t >= 0; --t) {               // p(1:n-1) = p1 + p2*p(n): p2 recomputed once more
-    const int l0 = t * TZ, m = min(TZ, nm - l0);
-    double r[TZ], d[TZ], f2[TZ];
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) r[q] = pp[(long)(l0 + q) * sz];
+    const int l0 = t * TZ;
+    double d[TZ], f2[TZ];
+    if (t > 0) LOAD_TILE(rn, t - 1, nm)
     double dd = ckd[t * GT + threadIdx.x], g2 = ck2[t * GT + threadIdx.x];
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < nm) {
         double r2 = 0.;
         if (l == 0) r2 = -a[0];
         if (l == nm - 1) r2 = -c[nm - 1];
@@ -186,14 +199,14 @@ __global__ void __launch_bounds__(GT) gaussel_periodic_k(int nxy, int n, long sz
     }
 #pragma unroll
     for (int q = TZ - 1; q >= 0; --q) {
-      if (q < m) {
-        const int l = l0 + q;
+      const int l = l0 + q;
+      if (l < nm) {
         if (l < nm - 1) p2l = f2[q] - d[q] * p2l; else p2l = f2[q];
         r[q] = r[q] + p2l * pn;
       }
     }
-#pragma unroll
-    for (int q = 0; q < TZ; ++q) if (q < m) pp[(long)(l0 + q) * sz] = r[q];
+    STORE_TILE(r, t, nm)
+    COPY_TILE(r, rn)
   }
 }
 

@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcales_b200.so")
+# CALES_B200_FMAD=1 selects the contraction-enabled build (make FMAD=true); the default is the parity build (-fmad=false)
+LIB_PATH = os.path.join(_HERE, "libcales_b200_fma.so" if os.environ.get("CALES_B200_FMAD") == "1" else "libcales_b200.so")
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
