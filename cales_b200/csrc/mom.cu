@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(BX* BY) rk_update_k(Dims d, double f1, double 
   const long n12 = (long)d.n1 * d.n2;
   long o = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k0 - 1);
   double pc = p[c];
+#pragma unroll 4
   for (int k = k0; k <= k1; ++k, c += d.s2, o += n12) {
     const double pk = p[c + d.s2];
     double un = u[c] + f1 * du[o] + f2 * duo[o] + f12 * (bfx - dxi * (p[c + 1] - pc));

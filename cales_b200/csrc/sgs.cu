@@ -24,12 +24,80 @@ static inline int pick_kc(int ni, int nj, int nk) {
   return kc;
 }
 
+// ---- Smagorinsky + van Driest (sgs.f90:98-152), fused into the strain-rate kernel ---------------------------------
+struct SmagArgs {
+  double is_wall[6];
+  double dl0, dl1, l2, dxi, dyi, visc;
+  int any_wall;
+  const double* zc; const double* dzci0;      // zc(0:n3+1), dzci(0:n3+1)
+  const double* delk;                         // (dl(1)*dl(2)*dzf(k))**(1/3), precomputed per k
+  const double *u, *v, *w;                    // the UN-extrapolated velocity (wall shear, sgs.f90:117-143)
+  double* visct;
+};
+
+// del(k) = (dl(1)*dl(2)*dzf(k))**(1/3)   (sgs.f90:149)
+__global__ void smag_del_k(int n3, double dl0, double dl1, const double* __restrict__ dzf, double* __restrict__ delk) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= n3 + 1) delk[k] = pow(dl0 * dl1 * dzf[k], 1. / 3.);
+}
+
+__device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, int i, int j, int k) {
+  const double* __restrict__ u = A.u; const double* __restrict__ v = A.v; const double* __restrict__ w = A.w;
+  const int n1 = d.n1, n2 = d.n2, n3 = d.n3;
+  double dw[6];
+  dw[0] = A.dl0 * (i - 0.5); dw[1] = A.dl0 * (n1 - i + 0.5);
+  dw[2] = A.dl1 * (j - 0.5); dw[3] = A.dl1 * (n2 - j + 0.5);
+  dw[4] = A.zc[k]; dw[5] = A.l2 - A.zc[k];
+  int loc = 0;
+  double dw_min = BIG;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    dw[q] = dw[q] * A.is_wall[q] + BIG * (1. - A.is_wall[q]);
+    if (q == 0 || dw[q] < dw_min) { dw_min = dw[q]; loc = q; }     // minloc: first minimum
+  }
+  double t1, t2, tauw_s;
+#define U(ii, jj, kk) u[d.idx(ii, jj, kk)]
+#define V(ii, jj, kk) v[d.idx(ii, jj, kk)]
+#define W(ii, jj, kk) w[d.idx(ii, jj, kk)]
+  if (loc == 0) {
+    t1 = V(1, j, k) - V(0, j, k) + V(1, j - 1, k) - V(0, j - 1, k);
+    t2 = W(1, j, k) - W(0, j, k) + W(1, j, k - 1) - W(0, j, k - 1);
+    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
+  } else if (loc == 1) {
+    t1 = V(n1, j, k) - V(n1 + 1, j, k) + V(n1, j - 1, k) - V(n1 + 1, j - 1, k);
+    t2 = W(n1, j, k) - W(n1 + 1, j, k) + W(n1, j, k - 1) - W(n1 + 1, j, k - 1);
+    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
+  } else if (loc == 2) {
+    t1 = U(i, 1, k) - U(i, 0, k) + U(i - 1, 1, k) - U(i - 1, 0, k);
+    t2 = W(i, 1, k) - W(i, 0, k) + W(i, 1, k - 1) - W(i, 0, k - 1);
+    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
+  } else if (loc == 3) {
+    t1 = U(i, n2, k) - U(i, n2 + 1, k) + U(i - 1, n2, k) - U(i - 1, n2 + 1, k);
+    t2 = W(i, n2, k) - W(i, n2 + 1, k) + W(i, n2, k - 1) - W(i, n2 + 1, k - 1);
+    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
+  } else if (loc == 4) {
+    t1 = U(i, j, 1) - U(i, j, 0) + U(i - 1, j, 1) - U(i - 1, j, 0);
+    t2 = V(i, j, 1) - V(i, j, 0) + V(i, j - 1, 1) - V(i, j - 1, 0);
+    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dzci0[0];
+  } else {
+    t1 = U(i, j, n3) - U(i, j, n3 + 1) + U(i - 1, j, n3) - U(i - 1, j, n3 + 1);
+    t2 = V(i, j, n3) - V(i, j, n3 + 1) + V(i, j - 1, n3) - V(i, j - 1, n3 + 1);
+    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dzci0[n3];
+  }
+#undef U
+#undef V
+#undef W
+  tauw_s = 0.5 * A.visc * tauw_s;
+  const double dw_plus = dw_min * sqrt(tauw_s) * (1. / A.visc);
+  return 1. - exp(-dw_plus / 25.);
+}
+
 // ---- strain rate (sgs.f90:1019-1110) -----------------------------------------------------------------------------
-template <int SIJ>
+template <int SIJ, int SMAG>
 __global__ void __launch_bounds__(BX* BY) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
                                                     const double* __restrict__ dzfi, const double* __restrict__ u,
                                                     const double* __restrict__ v, const double* __restrict__ w,
-                                                    double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc) {
+                                                    double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc, SmagArgs A) {
   const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
   if (i > d.n1 || j > d.n2) return;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
@@ -53,7 +121,11 @@ __global__ void __launch_bounds__(BX* BY) strain_k(Dims d, double dxi, double dy
     const double s23 = .125 * ((v_ccp - v_ccc) * dzci_k + (w_cpc - w_ccc) * dyi + (v_ccc - v_ccm) * dzci_km + (w_cpm - w_ccm) * dyi +
                                (v_cmp - v_cmc) * dzci_k + (w_ccc - w_cmc) * dyi + (v_cmc - v_cmm) * dzci_km + (w_ccm - w_cmm) * dyi);
     const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
-    s0[c] = s;
+    if (SMAG) {                                          // visct = (c_smag*del*fd)**2*s0   (sgs.f90:150)
+      const double fd = A.any_wall ? van_driest(d, A, i, j, k) : 1.;
+      const double t = CSMAG * A.delk[k] * fd;
+      A.visct[c] = t * t * s;
+    } else s0[c] = s;
     if (SIJ) {
       sij.p[0][c] = s11; sij.p[1][c] = s22; sij.p[2][c] = s33; sij.p[3][c] = s12; sij.p[4][c] = s13; sij.p[5][c] = s23;
       if (s0copy) s0copy[c] = s;
@@ -68,8 +140,9 @@ static int strain_launch(cales_ctx* ctx, const int n[3], const double dli[3], co
   dim3 g(cdiv(n[0], BX), cdiv(n[1], BY), cdiv(n[2], kc)), b(BX, BY);
   Ptr6 P;
   for (int m = 0; m < 6; ++m) P.p[m] = sij ? sij[m] : nullptr;
-  if (sij) strain_k<1><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, s0copy, kc);
-  else strain_k<0><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, nullptr, kc);
+  SmagArgs none{};
+  if (sij) strain_k<1, 0><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, s0copy, kc, none);
+  else strain_k<0, 0><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, nullptr, kc, none);
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
@@ -172,80 +245,6 @@ static int extrap_launch(cales_ctx* ctx, const int n[3], const int is_bound[6], 
     KERNEL_CHECK(ctx);
   }
   return CALES_OK;
-}
-
-// ---- Smagorinsky + van Driest (sgs.f90:98-152) -------------------------------------------------------------------------
-struct SmagArgs {
-  double is_wall[6];
-  double dl0, dl1, l2, dxi, dyi, visc;
-  int any_wall;
-};
-
-__global__ void __launch_bounds__(BX* BY) smag_k(Dims d, SmagArgs A, const double* __restrict__ zc, const double* __restrict__ dzf,
-                                                  const double* __restrict__ dzci, const double* __restrict__ u,
-                                                  const double* __restrict__ v, const double* __restrict__ w,
-                                                  const double* __restrict__ s0, double* __restrict__ visct, int kc) {
-  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
-  if (i > d.n1 || j > d.n2) return;
-  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
-  const double visci = 1. / A.visc;
-  const double one_third = 1. / 3.;
-  const int n1 = d.n1, n2 = d.n2, n3 = d.n3;
-  for (int k = k0; k <= k1; ++k) {
-    double fd = 1.;
-    if (A.any_wall) {
-      double dw[6];
-      dw[0] = A.dl0 * (i - 0.5); dw[1] = A.dl0 * (n1 - i + 0.5);
-      dw[2] = A.dl1 * (j - 0.5); dw[3] = A.dl1 * (n2 - j + 0.5);
-      dw[4] = zc[k]; dw[5] = A.l2 - zc[k];
-      int loc = 0;
-      double dw_min = BIG;
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        dw[q] = dw[q] * A.is_wall[q] + BIG * (1. - A.is_wall[q]);
-        if (q == 0 || dw[q] < dw_min) { dw_min = dw[q]; loc = q; }     // minloc: first minimum
-      }
-      double t1, t2, tauw_s;
-#define U(ii, jj, kk) u[d.idx(ii, jj, kk)]
-#define V(ii, jj, kk) v[d.idx(ii, jj, kk)]
-#define W(ii, jj, kk) w[d.idx(ii, jj, kk)]
-      if (loc == 0) {
-        t1 = V(1, j, k) - V(0, j, k) + V(1, j - 1, k) - V(0, j - 1, k);
-        t2 = W(1, j, k) - W(0, j, k) + W(1, j, k - 1) - W(0, j, k - 1);
-        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
-      } else if (loc == 1) {
-        t1 = V(n1, j, k) - V(n1 + 1, j, k) + V(n1, j - 1, k) - V(n1 + 1, j - 1, k);
-        t2 = W(n1, j, k) - W(n1 + 1, j, k) + W(n1, j, k - 1) - W(n1 + 1, j, k - 1);
-        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
-      } else if (loc == 2) {
-        t1 = U(i, 1, k) - U(i, 0, k) + U(i - 1, 1, k) - U(i - 1, 0, k);
-        t2 = W(i, 1, k) - W(i, 0, k) + W(i, 1, k - 1) - W(i, 0, k - 1);
-        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
-      } else if (loc == 3) {
-        t1 = U(i, n2, k) - U(i, n2 + 1, k) + U(i - 1, n2, k) - U(i - 1, n2 + 1, k);
-        t2 = W(i, n2, k) - W(i, n2 + 1, k) + W(i, n2, k - 1) - W(i, n2 + 1, k - 1);
-        tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
-      } else if (loc == 4) {
-        t1 = U(i, j, 1) - U(i, j, 0) + U(i - 1, j, 1) - U(i - 1, j, 0);
-        t2 = V(i, j, 1) - V(i, j, 0) + V(i, j - 1, 1) - V(i, j - 1, 0);
-        tauw_s = sqrt(t1 * t1 + t2 * t2) * dzci[0];
-      } else {
-        t1 = U(i, j, n3) - U(i, j, n3 + 1) + U(i - 1, j, n3) - U(i - 1, j, n3 + 1);
-        t2 = V(i, j, n3) - V(i, j, n3 + 1) + V(i, j - 1, n3) - V(i, j - 1, n3 + 1);
-        tauw_s = sqrt(t1 * t1 + t2 * t2) * dzci[n3];
-      }
-#undef U
-#undef V
-#undef W
-      tauw_s = 0.5 * A.visc * tauw_s;
-      const double dw_plus = dw_min * sqrt(tauw_s) * visci;
-      fd = 1. - exp(-dw_plus / 25.);
-    }
-    const double del = pow(A.dl0 * A.dl1 * dzf[k], one_third);
-    const double t = CSMAG * del * fd;
-    const long c = d.idx(i, j, k);
-    visct[c] = t * t * s0[c];
-  }
 }
 
 // ---- dsmag building blocks ------------------------------------------------------------------------------------------------
@@ -372,8 +371,6 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
   const long nflat = d.size();
   const int gflat = 148 * 8;
   if (!strcmp(sgstype, "smag")) {
-    double* s0 = (double*)cales_scratch(ctx, "sgs_s0", fb, true);
-    if (!s0) return CALES_ERR_NOMEM;
     const double *us = u, *vs = v, *ws = w;
     if (any_wm) {                                            // sgs.f90:84-90: copies only matter where extrapolate acts
       double* wk[3];
@@ -384,7 +381,10 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
       if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces3, 3, 1, nullptr, lwm))) return rc;
       us = wk[0]; vs = wk[1]; ws = wk[2];
     }
-    if ((rc = strain_launch(ctx, n, dli, dzci, dzfi, us, vs, ws, s0, nullptr, nullptr))) return rc;
+    double* delk = (double*)cales_scratch(ctx, "sgs_delk", (size_t)(n[2] + 2) * sizeof(double));
+    if (!delk) return CALES_ERR_NOMEM;
+    smag_del_k<<<cdiv(n[2] + 2, 128), 128, 0, ctx->stream>>>(n[2], dl[0], dl[1], dzf, delk);
+    KERNEL_CHECK(ctx);
     SmagArgs A;
     A.any_wall = 0;
     for (int idir = 0; idir < 3; ++idir)
@@ -394,7 +394,9 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
         A.any_wall |= wall;
       }
     A.dl0 = dl[0]; A.dl1 = dl[1]; A.l2 = l[2]; A.dxi = dli[0]; A.dyi = dli[1]; A.visc = visc;
-    smag_k<<<g, b, 0, ctx->stream>>>(d, A, zc, dzf, dzci, u, v, w, s0, visct, kc);
+    A.zc = zc; A.dzci0 = dzci; A.delk = delk; A.u = u; A.v = v; A.w = w; A.visct = visct;
+    Ptr6 P{};
+    strain_k<0, 1><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kc, A);
     KERNEL_CHECK(ctx);
     return CALES_OK;
   }

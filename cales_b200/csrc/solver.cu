@@ -29,74 +29,88 @@ int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 #define TZ 8
 #define GT 64
 
-// tile helpers: the loads of the NEXT tile are issued before the dependent chain of the current one runs
-#define LOAD_TILE(dst, t, nlev)                                                              \
+// The recurrences are written branch-free so that every level costs one reciprocal and a handful of DFMA-pipe
+// operations: with d(0)=p(0)=0 the first level needs no special case ((b+lam) - a*0 + eps is exact), with
+// p(n+1):=0 neither does the last level of the back substitution, and the right-hand side of the second
+// periodic system is a (mostly zero) table.  Coefficients a,b,c live in shared memory.
+#define LOAD_TILE(dst, t, nlev, FULL)                                                        \
   {                                                                                          \
-    const int l0_ = (t) * TZ;                                                                \
-    _Pragma("unroll") for (int q = 0; q < TZ; ++q) if (l0_ + q < (nlev)) dst[q] = pp[(long)(l0_ + q) * sz]; \
+    const double* pt_ = pp + (long)(t) * TZ * sz;                                            \
+    _Pragma("unroll") for (int q = 0; q < TZ; ++q) if (FULL || (t) * TZ + q < (nlev)) dst[q] = pt_[q * sz]; \
   }
-#define STORE_TILE(src, t, nlev)                                                             \
+#define STORE_TILE(src, t, nlev, FULL)                                                       \
   {                                                                                          \
-    const int l0_ = (t) * TZ;                                                                \
-    _Pragma("unroll") for (int q = 0; q < TZ; ++q) if (l0_ + q < (nlev)) pp[(long)(l0_ + q) * sz] = src[q]; \
+    double* pt_ = pp + (long)(t) * TZ * sz;                                                  \
+    _Pragma("unroll") for (int q = 0; q < TZ; ++q) if (FULL || (t) * TZ + q < (nlev)) pt_[q * sz] = src[q]; \
   }
 #define COPY_TILE(dst, src) { _Pragma("unroll") for (int q = 0; q < TZ; ++q) dst[q] = src[q]; }
+#define PIVOT(l) const double al = sa[l]; const double z = __drcp_rn((sb[l] + lam) - al * dl + EPS); dl = sc[l] * z;
 
 template <int LAM>
 __global__ void __launch_bounds__(GT) gaussel_k(int nxy, int n, long sz, const double* __restrict__ a, const double* __restrict__ b,
                                                  const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ p) {
-  extern __shared__ double ck[];                       // checkpoints [ntile][GT]: d at the level before the tile
+  extern __shared__ double sh[];
+  const int ntile = (n + TZ - 1) / TZ, nfull = n / TZ;
+  double* sa = sh; double* sb = sa + n; double* sc = sb + n;
+  double* ck = sc + n;                                 // checkpoints [ntile][GT]: d at the level before the tile
+  for (int l = threadIdx.x; l < n; l += GT) { sa[l] = a[l]; sb[l] = b[l]; sc[l] = c[l]; }
+  __syncthreads();
   const int col = blockIdx.x * GT + threadIdx.x;
   if (col >= nxy) return;
   const double lam = LAM ? lambdaxy[col] : 0.;
   double* pp = p + col;
-  const int ntile = (n + TZ - 1) / TZ;
   double dl = 0., pl = 0.;
   double r[TZ], rn[TZ];
-  // forward elimination
-  LOAD_TILE(r, 0, n)
-  for (int t = 0; t < ntile; ++t) {
-    const int l0 = t * TZ;
-    if (t + 1 < ntile) LOAD_TILE(rn, t + 1, n)
+  // ---- forward elimination (solver.f90:165-173)
+  if (nfull > 0) LOAD_TILE(r, 0, n, true) else LOAD_TILE(r, 0, n, false)
+  for (int t = 0; t < nfull; ++t) {
+    if (t + 1 < nfull) LOAD_TILE(rn, t + 1, n, true) else if (t + 1 < ntile) LOAD_TILE(rn, t + 1, n, false)
     ck[t * GT + threadIdx.x] = dl;
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      const int l = l0 + q;
-      if (l < n) {
-        double z;
-        if (l == 0) { z = 1. / (b[0] + lam + EPS); pl = r[q] * z; }
-        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dl + EPS); pl = (r[q] - al * pl) * z; }
-        dl = c[l] * z;
-        r[q] = pl;
-      }
+      const int l = t * TZ + q;
+      const double dprev = dl;
+      PIVOT(l)
+      (void)dprev;
+      pl = (r[q] - al * pl) * z;
+      r[q] = pl;
     }
-    STORE_TILE(r, t, n)
+    STORE_TILE(r, t, n, true)
     COPY_TILE(r, rn)
   }
-  // backward substitution: p(l) = p(l) - d(l)*p(l+1), l = n-2..0 ; pl holds p(n-1)
-  LOAD_TILE(r, ntile - 1, n)
-  for (int t = ntile - 1; t >= 0; --t) {
-    const int l0 = t * TZ;
-    double d[TZ];
-    if (t > 0) LOAD_TILE(rn, t - 1, n)
-    double dd = ck[t * GT + threadIdx.x];
+  if (nfull < ntile) {
+    const int t = nfull;
+    ck[t * GT + threadIdx.x] = dl;
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      const int l = l0 + q;
-      if (l < n) {
-        const double z = l == 0 ? 1. / (b[0] + lam + EPS) : 1. / ((b[l] + lam) - a[l] * dd + EPS);
-        dd = c[l] * z;
-        d[q] = dd;
-      }
+      const int l = t * TZ + q;
+      if (l < n) { PIVOT(l) pl = (r[q] - al * pl) * z; r[q] = pl; }
     }
+    STORE_TILE(r, t, n, false)
+  }
+  // ---- backward substitution (solver.f90:176-178): p(l) = p(l) - d(l)*p(l+1) with p(n+1) := 0
+  pl = 0.;
+  if (nfull < ntile) {
+    const int t = nfull;
+    double d[TZ];
+    LOAD_TILE(r, t, n, false)
+    dl = ck[t * GT + threadIdx.x];
 #pragma unroll
-    for (int q = TZ - 1; q >= 0; --q) {
-      const int l = l0 + q;
-      if (l < n) {
-        if (l < n - 1) { pl = r[q] - d[q] * pl; r[q] = pl; } else pl = r[q];
-      }
-    }
-    STORE_TILE(r, t, n)
+    for (int q = 0; q < TZ; ++q) { const int l = t * TZ + q; if (l < n) { PIVOT(l) (void)z; d[q] = dl; } }
+#pragma unroll
+    for (int q = TZ - 1; q >= 0; --q) { const int l = t * TZ + q; if (l < n) { pl = r[q] - d[q] * pl; r[q] = pl; } }
+    STORE_TILE(r, t, n, false)
+  }
+  if (nfull > 0) LOAD_TILE(r, nfull - 1, n, true)
+  for (int t = nfull - 1; t >= 0; --t) {
+    double d[TZ];
+    if (t > 0) LOAD_TILE(rn, t - 1, n, true)
+    dl = ck[t * GT + threadIdx.x];
+#pragma unroll
+    for (int q = 0; q < TZ; ++q) { const int l = t * TZ + q; PIVOT(l) (void)z; d[q] = dl; }
+#pragma unroll
+    for (int q = TZ - 1; q >= 0; --q) { pl = r[q] - d[q] * pl; r[q] = pl; }
+    STORE_TILE(r, t, n, true)
     COPY_TILE(r, rn)
   }
 }
@@ -107,105 +121,89 @@ template <int LAM>
 __global__ void __launch_bounds__(GT) gaussel_periodic_k(int nxy, int n, long sz, const double* __restrict__ a,
                                                           const double* __restrict__ b, const double* __restrict__ c,
                                                           const double* __restrict__ lambdaxy, double* __restrict__ p) {
-  extern __shared__ double ck[];                       // [2][ntile][GT]: d and forward-p2 before each tile
+  extern __shared__ double sh[];
+  const int nm = n - 1;
+  const int ntile = (nm + TZ - 1) / TZ, nfull = nm / TZ;
+  double* sa = sh; double* sb = sa + n; double* sc = sb + n; double* s2 = sc + n;
+  double* ckd = s2 + n;                                // [2][ntile][GT]: d and forward-p2 before each tile
+  double* ck2 = ckd + (size_t)ntile * GT;
+  for (int l = threadIdx.x; l < n; l += GT) { sa[l] = a[l]; sb[l] = b[l]; sc[l] = c[l]; s2[l] = 0.; }
+  __syncthreads();
+  if (threadIdx.x == 0) { s2[0] = -a[0]; s2[nm - 1] = -c[nm - 1]; }   // p2(1) = -a(1); p2(n-1) = -c(n-1) (in that order)
+  __syncthreads();
   const int col = blockIdx.x * GT + threadIdx.x;
   if (col >= nxy) return;
   const double lam = LAM ? lambdaxy[col] : 0.;
   double* pp = p + col;
-  const int nm = n - 1;
-  const int ntile = (nm + TZ - 1) / TZ;
-  double* ckd = ck;
-  double* ck2 = ck + (size_t)ntile * GT;
   double dl = 0., p1l = 0., p2l = 0.;
   double r[TZ], rn[TZ];
-  LOAD_TILE(r, 0, nm)
-  for (int t = 0; t < ntile; ++t) {                    // forward elimination of both systems
-    const int l0 = t * TZ;
-    if (t + 1 < ntile) LOAD_TILE(rn, t + 1, nm)
+  // ---- forward elimination of both systems
+  if (nfull > 0) LOAD_TILE(r, 0, nm, true) else LOAD_TILE(r, 0, nm, false)
+  for (int t = 0; t < ntile; ++t) {
+    const bool full = t < nfull;
+    if (t + 1 < nfull) LOAD_TILE(rn, t + 1, nm, true) else if (t + 1 < ntile) LOAD_TILE(rn, t + 1, nm, false)
     ckd[t * GT + threadIdx.x] = dl;
     ck2[t * GT + threadIdx.x] = p2l;
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      const int l = l0 + q;
-      if (l < nm) {
-        double r2 = 0.;
-        if (l == 0) r2 = -a[0];
-        if (l == nm - 1) r2 = -c[nm - 1];
-        double z;
-        if (l == 0) { z = 1. / (b[0] + lam + EPS); p1l = r[q] * z; p2l = r2 * z; }
-        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dl + EPS); p1l = (r[q] - al * p1l) * z; p2l = (r2 - al * p2l) * z; }
-        dl = c[l] * z;
+      const int l = t * TZ + q;
+      if (full || l < nm) {
+        PIVOT(l)
+        p1l = (r[q] - al * p1l) * z;
+        p2l = (s2[l] - al * p2l) * z;
         r[q] = p1l;
       }
     }
-    STORE_TILE(r, t, nm)
+    if (full) STORE_TILE(r, t, nm, true) else STORE_TILE(r, t, nm, false)
     COPY_TILE(r, rn)
   }
   const double p1n = p1l, p2n = p2l;                   // p1(n-1), p2(n-1): unchanged by the back substitution
   const double plast = pp[(long)(n - 1) * sz];
-  LOAD_TILE(r, ntile - 1, nm)
-  for (int t = ntile - 1; t >= 0; --t) {               // backward substitution of both systems
-    const int l0 = t * TZ;
+  // ---- backward substitution of both systems (p(n) := 0 makes the last level uniform)
+  p1l = 0.; p2l = 0.;
+  if (ntile - 1 < nfull) LOAD_TILE(r, ntile - 1, nm, true) else LOAD_TILE(r, ntile - 1, nm, false)
+  for (int t = ntile - 1; t >= 0; --t) {
+    const bool full = t < nfull;
     double d[TZ], f2[TZ];
-    if (t > 0) LOAD_TILE(rn, t - 1, nm)
-    double dd = ckd[t * GT + threadIdx.x], g2 = ck2[t * GT + threadIdx.x];
+    if (t > 0) LOAD_TILE(rn, t - 1, nm, true)
+    dl = ckd[t * GT + threadIdx.x];
+    double g2 = ck2[t * GT + threadIdx.x];
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      const int l = l0 + q;
-      if (l < nm) {
-        double r2 = 0.;
-        if (l == 0) r2 = -a[0];
-        if (l == nm - 1) r2 = -c[nm - 1];
-        double z;
-        if (l == 0) { z = 1. / (b[0] + lam + EPS); g2 = r2 * z; }
-        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dd + EPS); g2 = (r2 - al * g2) * z; }
-        dd = c[l] * z;
-        d[q] = dd; f2[q] = g2;
-      }
+      const int l = t * TZ + q;
+      if (full || l < nm) { PIVOT(l) g2 = (s2[l] - al * g2) * z; d[q] = dl; f2[q] = g2; }
     }
 #pragma unroll
     for (int q = TZ - 1; q >= 0; --q) {
-      const int l = l0 + q;
-      if (l < nm) {
-        if (l < nm - 1) { p1l = r[q] - d[q] * p1l; p2l = f2[q] - d[q] * p2l; r[q] = p1l; } else { p1l = r[q]; p2l = f2[q]; }
-      }
+      const int l = t * TZ + q;
+      if (full || l < nm) { p1l = r[q] - d[q] * p1l; p2l = f2[q] - d[q] * p2l; r[q] = p1l; }
     }
-    STORE_TILE(r, t, nm)
+    if (full) STORE_TILE(r, t, nm, true) else STORE_TILE(r, t, nm, false)
     COPY_TILE(r, rn)
   }
   // p1l = p1(1), p2l = p2(1)                                                     solver.f90:142-144
-  const double pn = (plast - c[n - 1] * p1l - a[n - 1] * p1n) / ((b[n - 1] + lam) + c[n - 1] * p2l + a[n - 1] * p2n + EPS);
+  const double pn = (plast - sc[n - 1] * p1l - sa[n - 1] * p1n) / ((sb[n - 1] + lam) + sc[n - 1] * p2l + sa[n - 1] * p2n + EPS);
   pp[(long)(n - 1) * sz] = pn;
+  // ---- p(1:n-1) = p1 + p2*p(n): p2 recomputed once more
   p2l = 0.;
-  LOAD_TILE(r, ntile - 1, nm)
-  for (int t = ntile - 1; t >= 0; --t) {               // p(1:n-1) = p1 + p2*p(n): p2 recomputed once more
-    const int l0 = t * TZ;
+  if (ntile - 1 < nfull) LOAD_TILE(r, ntile - 1, nm, true) else LOAD_TILE(r, ntile - 1, nm, false)
+  for (int t = ntile - 1; t >= 0; --t) {
+    const bool full = t < nfull;
     double d[TZ], f2[TZ];
-    if (t > 0) LOAD_TILE(rn, t - 1, nm)
-    double dd = ckd[t * GT + threadIdx.x], g2 = ck2[t * GT + threadIdx.x];
+    if (t > 0) LOAD_TILE(rn, t - 1, nm, true)
+    dl = ckd[t * GT + threadIdx.x];
+    double g2 = ck2[t * GT + threadIdx.x];
 #pragma unroll
     for (int q = 0; q < TZ; ++q) {
-      const int l = l0 + q;
-      if (l < nm) {
-        double r2 = 0.;
-        if (l == 0) r2 = -a[0];
-        if (l == nm - 1) r2 = -c[nm - 1];
-        double z;
-        if (l == 0) { z = 1. / (b[0] + lam + EPS); g2 = r2 * z; }
-        else { const double al = a[l]; z = 1. / ((b[l] + lam) - al * dd + EPS); g2 = (r2 - al * g2) * z; }
-        dd = c[l] * z;
-        d[q] = dd; f2[q] = g2;
-      }
+      const int l = t * TZ + q;
+      if (full || l < nm) { PIVOT(l) g2 = (s2[l] - al * g2) * z; d[q] = dl; f2[q] = g2; }
     }
 #pragma unroll
     for (int q = TZ - 1; q >= 0; --q) {
-      const int l = l0 + q;
-      if (l < nm) {
-        if (l < nm - 1) p2l = f2[q] - d[q] * p2l; else p2l = f2[q];
-        r[q] = r[q] + p2l * pn;
-      }
+      const int l = t * TZ + q;
+      if (full || l < nm) { p2l = f2[q] - d[q] * p2l; r[q] = r[q] + p2l * pn; }
     }
-    STORE_TILE(r, t, nm)
+    if (full) STORE_TILE(r, t, nm, true) else STORE_TILE(r, t, nm, false)
     COPY_TILE(r, rn)
   }
 }
@@ -216,7 +214,7 @@ int k_gaussel(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, cons
   const int nxy = nx * ny;
   if (periodic && n < 3) return cales_fail(ctx, CALES_ERR_INVALID, "periodic tridiagonal solve needs n >= 3");
   const int ntile = ((periodic ? n - 1 : n) + TZ - 1) / TZ;
-  const size_t sh = (size_t)ntile * GT * sizeof(double) * (periodic ? 2 : 1);
+  const size_t sh = ((size_t)ntile * GT * (periodic ? 2 : 1) + (size_t)n * (periodic ? 4 : 3)) * sizeof(double);
   if (sh > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "tridiagonal system of %d points exceeds the checkpoint buffer", n);
   dim3 g(cdiv(nxy, GT));
   static bool attr = false;

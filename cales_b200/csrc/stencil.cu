@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(BX* BY) fillps_k(Dims d, double dxi, double dy
   const double dtidxi = dti * dxi, dtidyi = dti * dyi;
   long c = d.idx(i, j, k0);
   double wm = w[c - d.s2];
+#pragma unroll 4
   for (int k = k0; k <= k1; ++k, c += d.s2) {
     const double wc = w[c];
     p[c] = ((wc - wm) * dti * dzfi[k] + (v[c] - v[c - d.s1]) * dtidyi + (u[c] - u[c - 1]) * dtidxi);
@@ -57,6 +58,7 @@ __global__ void __launch_bounds__(BX* BY) correc_k(Dims d, double factori, doubl
   const int k0 = blockIdx.z * kc, k1 = min(k0 + kc - 1, d.n3 + 1);
   long c = d.idx(i, j, k0);
   double pc = p[c];
+#pragma unroll 4
   for (int k = k0; k <= k1; ++k, c += d.s2) {
     const double pk = k <= d.n3 ? p[c + d.s2] : 0.0;
     if (i <= d.n1) u[c] = u[c] - factori * (p[c + 1] - pc);
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(BX* BY) updatep_k(Dims d, double dxi, double d
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
   long c = d.idx(i, j, k0);
   if (MODE == 0) {
+#pragma unroll 4
     for (int k = k0; k <= k1; ++k, c += d.s2) p[c] = p[c] + pp[c];
   } else {
     double pm = pp[c - d.s2], pc = pp[c];
