@@ -12,6 +12,7 @@
 // x-lines are contiguous; y-lines are handled as [NL consecutive x] x [all y] tiles so global access
 // stays coalesced without any transpose pass.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -250,6 +251,9 @@ __global__ void __launch_bounds__(FT) fft_lines_k(FftArgs A, int LS) {
   }
 }
 
+int k_fftb_pass(cales_ctx* ctx, int dir, int kind, int backward, int n, int nl1, int nl2, const double* in, long ies, long il1, long il2,
+                double* out, long oes, long ol1, long ol2, double scale, const FftTables* T);
+
 // ---- host side -------------------------------------------------------------------------------------------------------
 FftTables* k_tables(cales_ctx* ctx, int n) {
   auto it = ctx->tables.find(n);
@@ -290,6 +294,17 @@ int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backw
   if (n < 2 || (n & 1)) return cales_fail(ctx, CALES_ERR_INVALID, "transform length %d: only even lengths are implemented", n);
   FftTables* T = k_tables(ctx, n);
   if (!T) return CALES_ERR_NOMEM;
+  {
+    // fast path: register-blocked batched kernel (fftb.cu) for power-of-two lengths
+    static const bool old_only = getenv("CALES_FFT_GENERIC") != nullptr;
+    if (!old_only) {
+      int rc;
+      if (dir == 0) rc = k_fftb_pass(ctx, 0, kind, backward, n, n2, n3, in, 1, ip1, ip2, out, 1, op1, op2, scale, T);
+      else rc = k_fftb_pass(ctx, 1, kind, backward, n, n1, n3, in, ip1, 1, ip2, out, op1, 1, op2, scale, T);
+      if (rc < 0) return -rc;
+      if (rc == 1) return CALES_OK;
+    }
+  }
   FftArgs A;
   A.in = in; A.out = out; A.n = n; A.kind = kind; A.backward = backward; A.scale = scale;
   const int m = n / 2;

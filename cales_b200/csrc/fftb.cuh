@@ -1,0 +1,390 @@
+// Register-blocked batched real transforms (power-of-two lengths): the fast path of the solver's x/y passes.
+// Same transforms and conventions as fft.cu (R2HC/HC2R, REDFT10/01, RODFT10/01 of src/fft.f90:192-245, FFTW
+// definitions, unnormalised), different machine mapping:
+//   * lanes run ACROSS lines (NL = 16 neighbouring lines per CTA), threadIdx.y = t walks along the transform, so every
+//     shared-memory access of the butterflies is a contiguous 16 x 16 B row (conflict-free by construction) and every
+//     index, twiddle address and branch is warp-uniform;
+//   * the transform length, the radix schedule, the direction and the transform family are template parameters, so
+//     all Stockham positions and twiddle indices fold to shifts and immediates;
+//   * each thread keeps E = 8 or 16 complex points in registers and performs radix-16/8/4/2 butterflies on them;
+//     stages exchange data through ONE in-place shared buffer (read -> sync -> butterfly -> write -> sync); stage
+//     twiddles come from a shared-memory copy of the table (warp-uniform broadcast reads);
+//   * y-lines (stride = row pitch): the NL lines of a CTA are NL consecutive x, so the first stage loads straight
+//     from global memory (128 B rows) and the even/odd split / Makhoul post-stage stores straight to global memory:
+//     one read + one write of the array, 4 shared-memory passes;
+//   * x-lines (contiguous): the tile is staged through the same buffer with a transposing, coalesced copy
+//     (pitch NL+1 keeps it conflict-free).
+#pragma once
+#include "common.cuh"
+
+enum { KB_PP = 0, KB_NN = 1, KB_DD = 2 };
+
+struct FftBArgs {
+  const double* in; double* out;
+  long ies, il1, il2, oes, ol1, ol2;
+  int nl1, nl2, dd;        // lines along l1 / l2; dd: DST flavour of the Makhoul family
+  double scale;
+  const double2 *wm, *wn, *h4;
+};
+
+#define NLB 16
+
+namespace fb {
+__device__ __forceinline__ double2 mul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ double2 add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 conj(double2 a) { return make_double2(a.x, -a.y); }
+template <bool INV> __device__ __forceinline__ double2 muli(double2 a) { return INV ? make_double2(-a.y, a.x) : make_double2(a.y, -a.x); }
+
+__device__ __forceinline__ void dft2(double2& a, double2& b) { const double2 t = a; a = add(t, b); b = sub(t, b); }
+template <bool INV> __device__ __forceinline__ void dft4(double2& a0, double2& a1, double2& a2, double2& a3) {
+  const double2 t0 = add(a0, a2), t1 = sub(a0, a2), t2 = add(a1, a3), t3 = muli<INV>(sub(a1, a3));
+  a0 = add(t0, t2); a1 = add(t1, t3); a2 = sub(t0, t2); a3 = sub(t1, t3);
+}
+#define FB_RH 0.70710678118654752440
+#define FB_C1 0.92387953251128675613
+#define FB_S1 0.38268343236508977173
+// o * exp(-+ i pi K/8)
+template <bool INV, int K> __device__ __forceinline__ double2 mw16(double2 o) {
+  if (K == 0) return o;
+  if (K == 4) return muli<INV>(o);
+  if (K == 2) return INV ? make_double2(FB_RH * (o.x - o.y), FB_RH * (o.x + o.y)) : make_double2(FB_RH * (o.x + o.y), FB_RH * (o.y - o.x));
+  if (K == 6) return INV ? make_double2(FB_RH * (-o.x - o.y), FB_RH * (o.x - o.y)) : make_double2(FB_RH * (o.y - o.x), FB_RH * (-o.x - o.y));
+  constexpr double c = K == 1 ? FB_C1 : K == 3 ? FB_S1 : -FB_C1;                 // K = 1, 3, 9
+  constexpr double s0 = K == 1 ? FB_S1 : K == 3 ? FB_C1 : -FB_S1;
+  constexpr double s = INV ? -s0 : s0;                                           // forward: c - i s
+  return make_double2(o.x * c + o.y * s, o.y * c - o.x * s);
+}
+template <bool INV> __device__ __forceinline__ void dft8(double2 (&v)[8]) {
+  dft4<INV>(v[0], v[2], v[4], v[6]);
+  dft4<INV>(v[1], v[3], v[5], v[7]);
+  const double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  const double2 o0 = v[1], o1 = mw16<INV, 2>(v[3]), o2 = muli<INV>(v[5]), o3 = mw16<INV, 6>(v[7]);
+  v[0] = add(e0, o0); v[4] = sub(e0, o0);
+  v[1] = add(e1, o1); v[5] = sub(e1, o1);
+  v[2] = add(e2, o2); v[6] = sub(e2, o2);
+  v[3] = add(e3, o3); v[7] = sub(e3, o3);
+}
+template <bool INV> __device__ __forceinline__ void dft16(double2 (&v)[16]) {
+  // a = 4 a1 + a0: 4-point DFTs over a1 for each a0, twiddle w16^(a0 p), 4-point DFTs over a0 for each p
+#pragma unroll
+  for (int a0 = 0; a0 < 4; ++a0) dft4<INV>(v[a0], v[4 + a0], v[8 + a0], v[12 + a0]);     // Y_{a0}(p) in v[4p + a0]
+  v[5] = mw16<INV, 1>(v[5]); v[6] = mw16<INV, 2>(v[6]); v[7] = mw16<INV, 3>(v[7]);
+  v[9] = mw16<INV, 2>(v[9]); v[10] = mw16<INV, 4>(v[10]); v[11] = mw16<INV, 6>(v[11]);
+  v[13] = mw16<INV, 3>(v[13]); v[14] = mw16<INV, 6>(v[14]); v[15] = mw16<INV, 9>(v[15]);
+#pragma unroll
+  for (int p = 0; p < 4; ++p) dft4<INV>(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);  // X_{p + 4r} in v[4p + r]
+  double2 o[16];
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[p + 4 * r] = v[4 * p + r];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) v[q] = o[q];
+}
+template <int R, bool INV> __device__ __forceinline__ void dftR(double2 (&v)[R]) {
+  if constexpr (R == 2) dft2(v[0], v[1]);
+  else if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+  else if constexpr (R == 8) dft8<INV>(v);
+  else dft16<INV>(v);
+}
+
+// One Stockham stage of radix R (Ns = product of the previous radices) on the E register points of thread t (point e
+// sits at complex index t + T e): butterfly b handles j = t + b T with inputs j + a M/R = x[b + a E/R]; output q goes
+// to position (j - k) R + k + q Ns, k = j mod Ns.  sw: stage twiddles exp(-2 pi i t / M) in shared memory.
+template <int M, int E, int R, int Ns, bool INV>
+__device__ __forceinline__ void stage(double2 (&x)[E], int (&pos)[E], int t, const double2* __restrict__ sw) {
+  constexpr int NB = E / R, T = M / E, tstep = M / (Ns * R);
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const int j = t + b * T;
+    const int k = j & (Ns - 1);
+    double2 v[R];
+#pragma unroll
+    for (int a = 0; a < R; ++a) v[a] = x[b + a * NB];
+    if (Ns > 1) {
+      const int ts = k * tstep;
+#pragma unroll
+      for (int a = 1; a < R; ++a) {
+        double2 w = sw[a * ts];
+        if (INV) w.y = -w.y;
+        v[a] = mul(v[a], w);
+      }
+    }
+    dftR<R, INV>(v);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int q = 0; q < R; ++q) { x[b + q * NB] = v[q]; pos[b + q * NB] = base + q * Ns; }
+  }
+}
+
+// Makhoul: line element that holds sample vi of the permuted sequence v (v_j = x_2j, v_{n-1-j} = x_{2j+1})
+template <int MK> __device__ __forceinline__ int src_of(int vi, int n) {
+  if (!MK) return vi;
+  return vi < (n >> 1) ? 2 * vi : 2 * (n - 1 - vi) + 1;
+}
+template <int MK> __device__ __forceinline__ int slot_of(int e, int n) {       // inverse of src_of
+  if (!MK) return e;
+  return (e & 1) ? n - 1 - (e >> 1) : (e >> 1);
+}
+}  // namespace fb
+
+// M complex points per line (n = 2M reals), E points per thread, XD: x-lines (staged) / y-lines (direct),
+// INV: backward transform, MK: Makhoul family (DCT/DST) instead of the periodic real FFT.
+template <int M, int E, int XD, bool INV, int MK>
+__global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
+  using namespace fb;
+  extern __shared__ double2 S[];
+  constexpr int NLP = XD ? NLB + 1 : NLB;
+  constexpr int n = 2 * M, T = M / E, NT = NLB * T;
+  double2* sw = S + M * NLP;                  // stage twiddles, M entries
+  const int l = threadIdx.x, t = threadIdx.y;
+  const int L0 = blockIdx.x * NLB;
+  const int nl = min(NLB, A.nl1 - L0);
+  const bool on = l < nl;
+  const bool dd = MK && A.dd;
+  const double* gin = A.in + (long)blockIdx.y * A.il2 + (long)L0 * A.il1;
+  double* gout = A.out + (long)blockIdx.y * A.ol2 + (long)L0 * A.ol1;
+  const int tid = l + NLB * t;
+  double* Sd = (double*)S;
+#define RS(s_, l_) ((((s_) >> 1) * NLP + (l_)) * 2 + ((s_) & 1))     // real slot s of line l in the double view
+  double2 x[E];
+  int pos[E];
+  const double* gl = gin + (long)l * A.il1;     // my line (y-mapping)
+  double* go = gout + (long)l * A.ol1;
+
+  for (int q = tid; q < M; q += NT) sw[q] = __ldg(A.wm + q);
+
+  if (XD) {
+    // ---- coalesced, transposing load: thread (line ln, pair c), c fastest; for the forward Makhoul family the pair is
+    // (v_2c, v_2c+1) gathered from the line, for backward transforms the raw spectrum is copied pair by pair
+#pragma unroll
+    for (int it = 0; it < E; ++it) {
+      const int idx = tid + it * NT;
+      const int ln = idx / M, c = idx % M;
+      const double* g = gin + (long)ln * A.il1;
+      double a = 0., b = 0.;
+      if (ln < nl) {
+        if (!INV) {
+          const int e0 = src_of<MK>(2 * c, n), e1 = src_of<MK>(2 * c + 1, n);
+          a = g[e0]; b = g[e1];
+          if (dd) { if (e0 & 1) a = -a; if (e1 & 1) b = -b; }
+        } else {
+          const int e0 = dd ? n - 1 - 2 * c : 2 * c, e1 = dd ? n - 2 - 2 * c : 2 * c + 1;
+          a = g[e0]; b = g[e1];
+        }
+      }
+      S[c * NLP + ln] = make_double2(a, b);
+    }
+  }
+  __syncthreads();
+
+  if (!INV) {
+    // ---- forward: first-stage operands
+    if (XD) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) x[e] = S[(t + T * e) * NLP + l];
+      __syncthreads();
+    } else {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int c = t + T * e;
+        int e0, e1;
+        if (!MK) { e0 = 2 * c; e1 = 2 * c + 1; }
+        else if (e < E / 2) { e0 = 4 * c; e1 = 4 * c + 2; }               // c < M/2  <=>  e < E/2
+        else { e0 = 2 * n - 1 - 4 * c; e1 = 2 * n - 3 - 4 * c; }
+        double a = 0., b = 0.;
+        if (on) { a = gl[(long)e0 * A.ies]; b = gl[(long)e1 * A.ies]; }
+        if (MK && e >= E / 2 && dd) { a = -a; b = -b; }                  // odd line elements change sign for the DST
+        x[e] = make_double2(a, b);
+      }
+    }
+  } else {
+    // ---- backward pre-stage: half spectrum -> packed complex Z
+    double2 zk[E / 2 + 1], zmk[E / 2 + 1];
+#pragma unroll
+    for (int b = 0; b <= E / 2; ++b) {
+      const int k = t + T * b, mk = M - k;
+      zk[b] = zmk[b] = make_double2(0., 0.);
+      if (b == E / 2 && t > 0) continue;          // k = M/2 belongs to t = 0
+      double rk, rnk, rmk, rnmk;                  // R[k], R[n-k], R[mk], R[n-mk]
+      const int snk = k > 0 ? n - k : 0, snmk = n - mk;
+      if (XD) {
+        rk = Sd[RS(k, l)]; rnk = Sd[RS(snk, l)]; rmk = Sd[RS(mk, l)]; rnmk = Sd[RS(snmk, l)];
+      } else {
+        rk = rnk = rmk = rnmk = 0.;
+        if (on) {
+#define GI(s_) gl[(long)(dd ? n - 1 - (s_) : (s_)) * A.ies]
+          rk = GI(k); rnk = GI(snk); rmk = GI(mk); rnmk = GI(snmk);
+#undef GI
+        }
+      }
+      double2 Xk, Xmk;
+      if (!MK) {
+        Xk = make_double2(rk, (k > 0 && k < M) ? rnk : 0.);
+        Xmk = make_double2(rmk, (mk > 0 && mk < M) ? rnmk : 0.);
+      } else {
+        const double2 hk = conj(__ldg(A.h4 + k)), hmk = conj(__ldg(A.h4 + mk));
+        Xk = mul(make_double2(rk, k > 0 ? -rnk : 0.), hk);
+        Xmk = mul(make_double2(rmk, -rnmk), hmk);
+      }
+      const double2 Aa = add(Xk, conj(Xmk));
+      const double2 Bb = mul(sub(Xk, conj(Xmk)), conj(__ldg(A.wn + k)));
+      zk[b] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
+      zmk[b] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
+    }
+    if (XD) __syncthreads();          // everyone has read the raw spectrum before Z overwrites it
+#pragma unroll
+    for (int b = 0; b <= E / 2; ++b) {
+      const int k = t + T * b, mk = M - k;
+      if (b == E / 2 && t > 0) continue;
+      S[k * NLP + l] = zk[b];
+      if (k > 0 && mk != k) S[mk * NLP + l] = zmk[b];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < E; ++e) x[e] = S[(t + T * e) * NLP + l];
+    __syncthreads();
+  }
+
+  // ---- complex FFT of length M: Stockham stages on registers, in-place exchange through S.  Radix schedule: E, E, ...,
+  // then the remaining power of two.
+  constexpr int R0 = M >= E ? E : M;
+  constexpr int M1 = M / R0, R1 = M1 >= E ? E : M1;
+  constexpr int M2 = M1 / R1, R2 = M2 >= E ? E : M2;
+  constexpr int M3 = M2 / R2;
+  static_assert(M3 == 1, "at most three stages");
+#define EXCHANGE(last_)                                                        \
+  {                                                                            \
+    if (!((last_) && INV && !XD)) {                                            \
+      _Pragma("unroll") for (int e = 0; e < E; ++e) S[pos[e] * NLP + l] = x[e]; \
+      __syncthreads();                                                         \
+      if (!(last_)) {                                                          \
+        _Pragma("unroll") for (int e = 0; e < E; ++e) x[e] = S[(t + T * e) * NLP + l]; \
+        __syncthreads();                                                       \
+      }                                                                        \
+    }                                                                          \
+  }
+  stage<M, E, R0, 1, INV>(x, pos, t, sw);
+  EXCHANGE(M1 == 1)
+  if constexpr (M1 > 1) {
+    stage<M, E, R1, R0, INV>(x, pos, t, sw);
+    EXCHANGE(M2 == 1)
+  }
+  if constexpr (M2 > 1) {
+    stage<M, E, R2, R0 * R1, INV>(x, pos, t, sw);
+    EXCHANGE(true)
+  }
+#undef EXCHANGE
+
+  if (!INV) {
+    // ---- forward post-stage: even/odd split (+ Makhoul twiddles), output ordering
+    double2 zk[E / 2 + 1], zmk[E / 2 + 1];
+#pragma unroll
+    for (int b = 0; b <= E / 2; ++b) {
+      const int k = t + T * b;
+      if (b == E / 2 && t > 0) continue;
+      zk[b] = S[k * NLP + l];
+      zmk[b] = S[(k == 0 ? 0 : M - k) * NLP + l];
+    }
+    if (XD) __syncthreads();
+#pragma unroll
+    for (int b = 0; b <= E / 2; ++b) {
+      const int k = t + T * b, mk = M - k;
+      if (b == E / 2 && t > 0) continue;
+      const double2 Zk = zk[b], Zmk = conj(zmk[b]);
+      const double2 Ev = make_double2(0.5 * (Zk.x + Zmk.x), 0.5 * (Zk.y + Zmk.y));
+      const double2 D = sub(Zk, Zmk);
+      const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);
+      const double2 Tw = mul(__ldg(A.wn + k), O);
+      const double2 Xk = add(Ev, Tw), Xmk = conj(sub(Ev, Tw));
+      int i0, i1, i2, i3;            // output slots of the four reals (-1: none)
+      double r0, r1, r2, r3;
+      if (!MK) {
+        i0 = k; r0 = Xk.x;
+        i1 = (k > 0 && k < M) ? n - k : -1; r1 = Xk.y;
+        i2 = mk; r2 = Xmk.x;
+        i3 = (mk > 0 && mk < M) ? n - mk : -1; r3 = Xmk.y;
+      } else {
+        const double2 Yk = mul(__ldg(A.h4 + k), Xk), Ymk = mul(__ldg(A.h4 + mk), Xmk);
+        r0 = 2. * Yk.x; r1 = -2. * Yk.y; r2 = 2. * Ymk.x; r3 = -2. * Ymk.y;
+        if (!dd) { i0 = k; i1 = k > 0 ? n - k : -1; i2 = mk; i3 = n - mk; }
+        else { i0 = n - 1 - k; i1 = k > 0 ? k - 1 : -1; i2 = n - 1 - mk; i3 = mk - 1; }
+      }
+      if (XD) {
+        Sd[RS(i0, l)] = r0; if (i1 >= 0) Sd[RS(i1, l)] = r1;
+        Sd[RS(i2, l)] = r2; if (i3 >= 0) Sd[RS(i3, l)] = r3;
+      } else if (on) {
+        go[(long)i0 * A.oes] = r0 * A.scale; if (i1 >= 0) go[(long)i1 * A.oes] = r1 * A.scale;
+        go[(long)i2 * A.oes] = r2 * A.scale; if (i3 >= 0) go[(long)i3 * A.oes] = r3 * A.scale;
+      }
+    }
+    if (XD) {
+      __syncthreads();
+#pragma unroll
+      for (int it = 0; it < E; ++it) {
+        const int idx = tid + it * NT;
+        const int ln = idx / M, c = idx % M;
+        const double2 v = S[c * NLP + ln];
+        if (ln < nl) { double* g = gout + (long)ln * A.ol1 + 2 * c; g[0] = v.x * A.scale; g[1] = v.y * A.scale; }
+      }
+    }
+  } else {
+    // ---- backward store: z_c = (v_2c, v_2c+1), x = inverse Makhoul permutation of v
+    if (XD) {
+#pragma unroll
+      for (int it = 0; it < E; ++it) {
+        const int idx = tid + it * NT;
+        const int ln = idx / M, c = idx % M;
+        const int e0 = 2 * c, e1 = 2 * c + 1;
+        double a = Sd[RS(slot_of<MK>(e0, n), ln)], b = Sd[RS(slot_of<MK>(e1, n), ln)];
+        if (dd) b = -b;
+        if (ln < nl) { double* g = gout + (long)ln * A.ol1 + e0; g[0] = a * A.scale; g[1] = b * A.scale; }
+      }
+    } else if (on) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int c = pos[e];
+        const int e0 = src_of<MK>(2 * c, n), e1 = src_of<MK>(2 * c + 1, n);
+        double a = x[e].x, b = x[e].y;
+        if (dd) { if (e0 & 1) a = -a; if (e1 & 1) b = -b; }
+        go[(long)e0 * A.oes] = a * A.scale;
+        go[(long)e1 * A.oes] = b * A.scale;
+      }
+    }
+  }
+#undef RS
+}
+
+template <int M, int E, int XD>
+static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int backward) {
+  constexpr int NLP = XD ? NLB + 1 : NLB;
+  const size_t sh = ((size_t)M * NLP + M) * sizeof(double2);
+  dim3 g(cdiv(A.nl1, NLB), A.nl2), b(NLB, M / E);
+#define FB_GO(INV_, MK_)                                                                                           \
+  {                                                                                                                \
+    static bool attr = false;                                                                                      \
+    if (!attr) { attr = true; cudaFuncSetAttribute(fftb_k<M, E, XD, INV_, MK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); } \
+    fftb_k<M, E, XD, INV_, MK_><<<g, b, sh, ctx->stream>>>(A);                                                      \
+  }
+  const int mk = kind != KB_PP;
+  if (!backward) { if (mk) FB_GO(false, 1) else FB_GO(false, 0) }
+  else { if (mk) FB_GO(true, 1) else FB_GO(true, 0) }
+#undef FB_GO
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) return -cales_fail(ctx, CALES_ERR_CUDA, "fftb_k launch failed");
+  return 1;
+}
+
+template <int XD>
+static inline int fftb_dispatch(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward) {
+  switch (n) {
+    case 32: return fftb_launch<16, 8, XD>(ctx, A, kind, backward);
+    case 64: return fftb_launch<32, 8, XD>(ctx, A, kind, backward);
+    case 128: return fftb_launch<64, 8, XD>(ctx, A, kind, backward);
+    case 256: return fftb_launch<128, 8, XD>(ctx, A, kind, backward);
+    case 512: return fftb_launch<256, 16, XD>(ctx, A, kind, backward);
+    case 1024: return fftb_launch<512, 16, XD>(ctx, A, kind, backward);
+    default: return 0;
+  }
+}

@@ -1,0 +1,18 @@
+// y-lines (strided; lanes across neighbouring x) instantiations of the register-blocked batched transforms, see fftb.cuh
+#include "fftb.cuh"
+
+int k_fftb_x(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward);
+int k_fftb_y(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward) { return fftb_dispatch<0>(ctx, n, A, kind, backward); }
+
+// returns 1 if handled, 0 if this length is not covered by the fast path (caller falls back), <0 on error
+int k_fftb_pass(cales_ctx* ctx, int dir, int kind, int backward, int n, int nl1, int nl2, const double* in, long ies, long il1, long il2,
+                double* out, long oes, long ol1, long ol2, double scale, const FftTables* T) {
+  if (n < 32 || n > 1024 || (n & (n - 1))) return 0;
+  if (dir == 0 && (ies != 1 || oes != 1)) return 0;
+  const int m = n / 2;
+  FftBArgs A;
+  A.in = in; A.out = out; A.ies = ies; A.il1 = il1; A.il2 = il2; A.oes = oes; A.ol1 = ol1; A.ol2 = ol2;
+  A.nl1 = nl1; A.nl2 = nl2; A.dd = kind == KB_DD; A.scale = scale;
+  A.wm = T->w; A.wn = T->w + m; A.h4 = T->h;
+  return dir == 0 ? k_fftb_x(ctx, n, A, kind, backward) : k_fftb_y(ctx, n, A, kind, backward);
+}
