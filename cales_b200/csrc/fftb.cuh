@@ -12,8 +12,8 @@
 //   * y-lines (stride = row pitch): the NL lines of a CTA are NL consecutive x, so the first stage loads straight
 //     from global memory (128 B rows) and the even/odd split / Makhoul post-stage stores straight to global memory:
 //     one read + one write of the array, 4 shared-memory passes;
-//   * x-lines (contiguous): the tile is staged through the same buffer with a transposing, coalesced copy
-//     (pitch NL+1 keeps it conflict-free).
+//   * x-lines (contiguous): the phases that touch global memory use a second thread mapping (lanes ALONG the line,
+//     coalesced) and the shared buffer is XOR-swizzled so both mappings are conflict-free: same traffic as y-lines.
 #pragma once
 #include "common.cuh"
 
@@ -129,95 +129,61 @@ template <int MK> __device__ __forceinline__ int slot_of(int e, int n) {       /
 }
 }  // namespace fb
 
-// M complex points per line (n = 2M reals), E points per thread, XD: x-lines (staged) / y-lines (direct),
-// INV: backward transform, MK: Makhoul family (DCT/DST) instead of the periodic real FFT.
+// M complex points per line (n = 2M reals), E points per thread, XD: x-lines / y-lines, INV: backward transform,
+// MK: Makhoul family (DCT/DST) instead of the periodic real FFT.
+// Two thread mappings are used.  "Standard" (ls, ts): lanes across the NL lines, ts along the transform -- the
+// butterfly stages in the middle.  "Global" (lx, tx): the mapping of every phase that touches global memory (first
+// forward stage, forward post-stage, backward pre-stage, last backward stage).  For y-lines the two coincide (the NL
+// lines are NL consecutive x, so lanes across lines ARE coalesced); for x-lines lanes run along the line (tx fastest)
+// so that global accesses are coalesced, and the shared buffer is XOR-swizzled so that both mappings are conflict-free.
 template <int M, int E, int XD, bool INV, int MK>
 __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
   using namespace fb;
   extern __shared__ double2 S[];
-  constexpr int NLP = XD ? NLB + 1 : NLB;
   constexpr int n = 2 * M, T = M / E, NT = NLB * T;
-  double2* sw = S + M * NLP;                  // stage twiddles, M entries
-  const int l = threadIdx.x, t = threadIdx.y;
+  double2* sw = S + M * NLB;                  // stage twiddles, M entries
+  const int ls = threadIdx.x, ts = threadIdx.y;
+  const int tid = ls + NLB * ts;
+  const int lx = XD ? tid / T : ls, tx = XD ? tid % T : ts;
   const int L0 = blockIdx.x * NLB;
   const int nl = min(NLB, A.nl1 - L0);
-  const bool on = l < nl;
+  const bool on = lx < nl;
   const bool dd = MK && A.dd;
-  const double* gin = A.in + (long)blockIdx.y * A.il2 + (long)L0 * A.il1;
-  double* gout = A.out + (long)blockIdx.y * A.ol2 + (long)L0 * A.ol1;
-  const int tid = l + NLB * t;
-  double* Sd = (double*)S;
-#define RS(s_, l_) ((((s_) >> 1) * NLP + (l_)) * 2 + ((s_) & 1))     // real slot s of line l in the double view
+  const double* gl = A.in + (long)blockIdx.y * A.il2 + (long)(L0 + lx) * A.il1;
+  double* go = A.out + (long)blockIdx.y * A.ol2 + (long)(L0 + lx) * A.ol1;
+  const long ies = XD ? 1 : A.ies, oes = XD ? 1 : A.oes;
+#define SI(p_, l_) (XD ? (p_) * NLB + ((l_) ^ (((p_) ^ ((p_) >> 3) ^ ((p_) >> 4)) & (NLB - 1))) : (p_) * NLB + (l_))
   double2 x[E];
   int pos[E];
-  const double* gl = gin + (long)l * A.il1;     // my line (y-mapping)
-  double* go = gout + (long)l * A.ol1;
 
   for (int q = tid; q < M; q += NT) sw[q] = __ldg(A.wm + q);
 
-  if (XD) {
-    // ---- coalesced, transposing load: thread (line ln, pair c), c fastest; for the forward Makhoul family the pair is
-    // (v_2c, v_2c+1) gathered from the line, for backward transforms the raw spectrum is copied pair by pair
-#pragma unroll
-    for (int it = 0; it < E; ++it) {
-      const int idx = tid + it * NT;
-      const int ln = idx / M, c = idx % M;
-      const double* g = gin + (long)ln * A.il1;
-      double a = 0., b = 0.;
-      if (ln < nl) {
-        if (!INV) {
-          const int e0 = src_of<MK>(2 * c, n), e1 = src_of<MK>(2 * c + 1, n);
-          a = g[e0]; b = g[e1];
-          if (dd) { if (e0 & 1) a = -a; if (e1 & 1) b = -b; }
-        } else {
-          const int e0 = dd ? n - 1 - 2 * c : 2 * c, e1 = dd ? n - 2 - 2 * c : 2 * c + 1;
-          a = g[e0]; b = g[e1];
-        }
-      }
-      S[c * NLP + ln] = make_double2(a, b);
-    }
-  }
-  __syncthreads();
-
   if (!INV) {
-    // ---- forward: first-stage operands
-    if (XD) {
+    // ---- forward: first-stage operands straight from global memory
 #pragma unroll
-      for (int e = 0; e < E; ++e) x[e] = S[(t + T * e) * NLP + l];
-      __syncthreads();
-    } else {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int c = t + T * e;
-        int e0, e1;
-        if (!MK) { e0 = 2 * c; e1 = 2 * c + 1; }
-        else if (e < E / 2) { e0 = 4 * c; e1 = 4 * c + 2; }               // c < M/2  <=>  e < E/2
-        else { e0 = 2 * n - 1 - 4 * c; e1 = 2 * n - 3 - 4 * c; }
-        double a = 0., b = 0.;
-        if (on) { a = gl[(long)e0 * A.ies]; b = gl[(long)e1 * A.ies]; }
-        if (MK && e >= E / 2 && dd) { a = -a; b = -b; }                  // odd line elements change sign for the DST
-        x[e] = make_double2(a, b);
-      }
+    for (int e = 0; e < E; ++e) {
+      const int c = tx + T * e;
+      int e0, e1;
+      if (!MK) { e0 = 2 * c; e1 = 2 * c + 1; }
+      else if (e < E / 2) { e0 = 4 * c; e1 = 4 * c + 2; }               // c < M/2  <=>  e < E/2
+      else { e0 = 2 * n - 1 - 4 * c; e1 = 2 * n - 3 - 4 * c; }
+      double a = 0., b = 0.;
+      if (on) { a = gl[(long)e0 * ies]; b = gl[(long)e1 * ies]; }
+      if (MK && e >= E / 2 && dd) { a = -a; b = -b; }                  // odd line elements change sign for the DST
+      x[e] = make_double2(a, b);
     }
   } else {
-    // ---- backward pre-stage: half spectrum -> packed complex Z
-    double2 zk[E / 2 + 1], zmk[E / 2 + 1];
+    // ---- backward pre-stage: half spectrum (global) -> packed complex Z (shared)
 #pragma unroll
     for (int b = 0; b <= E / 2; ++b) {
-      const int k = t + T * b, mk = M - k;
-      zk[b] = zmk[b] = make_double2(0., 0.);
-      if (b == E / 2 && t > 0) continue;          // k = M/2 belongs to t = 0
-      double rk, rnk, rmk, rnmk;                  // R[k], R[n-k], R[mk], R[n-mk]
+      const int k = tx + T * b, mk = M - k;
+      if (b == E / 2 && tx > 0) continue;          // k = M/2 belongs to tx = 0
+      double rk = 0., rnk = 0., rmk = 0., rnmk = 0.;   // R[k], R[n-k], R[mk], R[n-mk]
       const int snk = k > 0 ? n - k : 0, snmk = n - mk;
-      if (XD) {
-        rk = Sd[RS(k, l)]; rnk = Sd[RS(snk, l)]; rmk = Sd[RS(mk, l)]; rnmk = Sd[RS(snmk, l)];
-      } else {
-        rk = rnk = rmk = rnmk = 0.;
-        if (on) {
-#define GI(s_) gl[(long)(dd ? n - 1 - (s_) : (s_)) * A.ies]
-          rk = GI(k); rnk = GI(snk); rmk = GI(mk); rnmk = GI(snmk);
+      if (on) {
+#define GI(s_) gl[(long)(dd ? n - 1 - (s_) : (s_)) * ies]
+        rk = GI(k); rnk = GI(snk); rmk = GI(mk); rnmk = GI(snmk);
 #undef GI
-        }
       }
       double2 Xk, Xmk;
       if (!MK) {
@@ -230,69 +196,58 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
       }
       const double2 Aa = add(Xk, conj(Xmk));
       const double2 Bb = mul(sub(Xk, conj(Xmk)), conj(__ldg(A.wn + k)));
-      zk[b] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
-      zmk[b] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
+      S[SI(k, lx)] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
+      if (k > 0 && mk != k) S[SI(mk, lx)] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
     }
-    if (XD) __syncthreads();          // everyone has read the raw spectrum before Z overwrites it
-#pragma unroll
-    for (int b = 0; b <= E / 2; ++b) {
-      const int k = t + T * b, mk = M - k;
-      if (b == E / 2 && t > 0) continue;
-      S[k * NLP + l] = zk[b];
-      if (k > 0 && mk != k) S[mk * NLP + l] = zmk[b];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int e = 0; e < E; ++e) x[e] = S[(t + T * e) * NLP + l];
     __syncthreads();
   }
 
   // ---- complex FFT of length M: Stockham stages on registers, in-place exchange through S.  Radix schedule: E, E, ...,
-  // then the remaining power of two.
+  // then the remaining power of two.  Forward: stage 0 runs in the global mapping; backward: the last stage does.
   constexpr int R0 = M >= E ? E : M;
   constexpr int M1 = M / R0, R1 = M1 >= E ? E : M1;
   constexpr int M2 = M1 / R1, R2 = M2 >= E ? E : M2;
   constexpr int M3 = M2 / R2;
-  static_assert(M3 == 1, "at most three stages");
-#define EXCHANGE(last_)                                                        \
-  {                                                                            \
-    if (!((last_) && INV && !XD)) {                                            \
-      _Pragma("unroll") for (int e = 0; e < E; ++e) S[pos[e] * NLP + l] = x[e]; \
-      __syncthreads();                                                         \
-      if (!(last_)) {                                                          \
-        _Pragma("unroll") for (int e = 0; e < E; ++e) x[e] = S[(t + T * e) * NLP + l]; \
-        __syncthreads();                                                       \
-      }                                                                        \
-    }                                                                          \
+  static_assert(M3 == 1 && M1 > 1, "two or three stages");
+  constexpr int NST = M2 > 1 ? 3 : 2;
+#define PUT(l_) { _Pragma("unroll") for (int e = 0; e < E; ++e) S[SI(pos[e], l_)] = x[e]; __syncthreads(); }
+#define GET(l_, t_) { _Pragma("unroll") for (int e = 0; e < E; ++e) x[e] = S[SI((t_) + T * e, l_)]; }
+  if (!INV) {
+    stage<M, E, R0, 1, INV>(x, pos, tx, sw);
+    PUT(lx)
+    GET(ls, ts) __syncthreads();
+    stage<M, E, R1, R0, INV>(x, pos, ts, sw);
+    PUT(ls)
+    if constexpr (NST == 3) {
+      GET(ls, ts) __syncthreads();
+      stage<M, E, R2, R0 * R1, INV>(x, pos, ts, sw);
+      PUT(ls)
+    }
+  } else {
+    GET(ls, ts) __syncthreads();
+    stage<M, E, R0, 1, INV>(x, pos, ts, sw);
+    PUT(ls)
+    if constexpr (NST == 3) {
+      GET(ls, ts) __syncthreads();
+      stage<M, E, R1, R0, INV>(x, pos, ts, sw);
+      PUT(ls)
+      GET(lx, tx)
+      stage<M, E, R2, R0 * R1, INV>(x, pos, tx, sw);
+    } else {
+      GET(lx, tx)
+      stage<M, E, R1, R0, INV>(x, pos, tx, sw);
+    }
   }
-  stage<M, E, R0, 1, INV>(x, pos, t, sw);
-  EXCHANGE(M1 == 1)
-  if constexpr (M1 > 1) {
-    stage<M, E, R1, R0, INV>(x, pos, t, sw);
-    EXCHANGE(M2 == 1)
-  }
-  if constexpr (M2 > 1) {
-    stage<M, E, R2, R0 * R1, INV>(x, pos, t, sw);
-    EXCHANGE(true)
-  }
-#undef EXCHANGE
+#undef PUT
+#undef GET
 
   if (!INV) {
-    // ---- forward post-stage: even/odd split (+ Makhoul twiddles), output ordering
-    double2 zk[E / 2 + 1], zmk[E / 2 + 1];
+    // ---- forward post-stage: even/odd split (+ Makhoul twiddles), output ordering, straight to global memory
 #pragma unroll
     for (int b = 0; b <= E / 2; ++b) {
-      const int k = t + T * b;
-      if (b == E / 2 && t > 0) continue;
-      zk[b] = S[k * NLP + l];
-      zmk[b] = S[(k == 0 ? 0 : M - k) * NLP + l];
-    }
-    if (XD) __syncthreads();
-#pragma unroll
-    for (int b = 0; b <= E / 2; ++b) {
-      const int k = t + T * b, mk = M - k;
-      if (b == E / 2 && t > 0) continue;
-      const double2 Zk = zk[b], Zmk = conj(zmk[b]);
+      const int k = tx + T * b, mk = M - k;
+      if (b == E / 2 && tx > 0) continue;
+      const double2 Zk = S[SI(k, lx)], Zmk = conj(S[SI(k == 0 ? 0 : mk, lx)]);
       const double2 Ev = make_double2(0.5 * (Zk.x + Zmk.x), 0.5 * (Zk.y + Zmk.y));
       const double2 D = sub(Zk, Zmk);
       const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);
@@ -311,55 +266,29 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
         if (!dd) { i0 = k; i1 = k > 0 ? n - k : -1; i2 = mk; i3 = n - mk; }
         else { i0 = n - 1 - k; i1 = k > 0 ? k - 1 : -1; i2 = n - 1 - mk; i3 = mk - 1; }
       }
-      if (XD) {
-        Sd[RS(i0, l)] = r0; if (i1 >= 0) Sd[RS(i1, l)] = r1;
-        Sd[RS(i2, l)] = r2; if (i3 >= 0) Sd[RS(i3, l)] = r3;
-      } else if (on) {
-        go[(long)i0 * A.oes] = r0 * A.scale; if (i1 >= 0) go[(long)i1 * A.oes] = r1 * A.scale;
-        go[(long)i2 * A.oes] = r2 * A.scale; if (i3 >= 0) go[(long)i3 * A.oes] = r3 * A.scale;
+      if (on) {
+        go[(long)i0 * oes] = r0 * A.scale; if (i1 >= 0) go[(long)i1 * oes] = r1 * A.scale;
+        go[(long)i2 * oes] = r2 * A.scale; if (i3 >= 0) go[(long)i3 * oes] = r3 * A.scale;
       }
     }
-    if (XD) {
-      __syncthreads();
-#pragma unroll
-      for (int it = 0; it < E; ++it) {
-        const int idx = tid + it * NT;
-        const int ln = idx / M, c = idx % M;
-        const double2 v = S[c * NLP + ln];
-        if (ln < nl) { double* g = gout + (long)ln * A.ol1 + 2 * c; g[0] = v.x * A.scale; g[1] = v.y * A.scale; }
-      }
-    }
-  } else {
+  } else if (on) {
     // ---- backward store: z_c = (v_2c, v_2c+1), x = inverse Makhoul permutation of v
-    if (XD) {
 #pragma unroll
-      for (int it = 0; it < E; ++it) {
-        const int idx = tid + it * NT;
-        const int ln = idx / M, c = idx % M;
-        const int e0 = 2 * c, e1 = 2 * c + 1;
-        double a = Sd[RS(slot_of<MK>(e0, n), ln)], b = Sd[RS(slot_of<MK>(e1, n), ln)];
-        if (dd) b = -b;
-        if (ln < nl) { double* g = gout + (long)ln * A.ol1 + e0; g[0] = a * A.scale; g[1] = b * A.scale; }
-      }
-    } else if (on) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const int c = pos[e];
-        const int e0 = src_of<MK>(2 * c, n), e1 = src_of<MK>(2 * c + 1, n);
-        double a = x[e].x, b = x[e].y;
-        if (dd) { if (e0 & 1) a = -a; if (e1 & 1) b = -b; }
-        go[(long)e0 * A.oes] = a * A.scale;
-        go[(long)e1 * A.oes] = b * A.scale;
-      }
+    for (int e = 0; e < E; ++e) {
+      const int c = pos[e];
+      const int e0 = src_of<MK>(2 * c, n), e1 = src_of<MK>(2 * c + 1, n);
+      double a = x[e].x, b = x[e].y;
+      if (dd) { if (e0 & 1) a = -a; if (e1 & 1) b = -b; }
+      go[(long)e0 * oes] = a * A.scale;
+      go[(long)e1 * oes] = b * A.scale;
     }
   }
-#undef RS
+#undef SI
 }
 
 template <int M, int E, int XD>
 static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int backward) {
-  constexpr int NLP = XD ? NLB + 1 : NLB;
-  const size_t sh = ((size_t)M * NLP + M) * sizeof(double2);
+  const size_t sh = ((size_t)M * NLB + M) * sizeof(double2);
   dim3 g(cdiv(A.nl1, NLB), A.nl2), b(NLB, M / E);
 #define FB_GO(INV_, MK_)                                                                                           \
   {                                                                                                                \
