@@ -136,11 +136,14 @@ extern "C" int cales_init(cales_ctx** out, const int ng[3], const int dims[2], i
   return CALES_OK;
 }
 
+void k_gaussel_tab_free(cales_ctx* ctx);
+
 extern "C" int cales_finalize(cales_ctx* ctx) {
   CHECK_CTX(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   comm_finalize(ctx);
+  k_gaussel_tab_free(ctx);
   for (auto& kv : ctx->scratch) cudaFree(kv.second.first);
   for (auto& kv : ctx->tables) { cudaFree(kv.second.w); cudaFree(kv.second.h); }
   cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->fdev);

@@ -1,0 +1,361 @@
+// Tridiagonal z-solves of the Poisson/Helmholtz solver with cached pivots.
+//   gaussel / gaussel_periodic / dgtsv_homebrewed   src/solver.f90:82-179
+// The pivot recurrence of dgtsv_homebrewed, z(l) = 1/(b(l)+lambda(i,j) - a(l) d(l-1) + eps), d(l) = c(l) z(l), does not
+// depend on the right-hand side, and neither does the second system p2 of the periodic solve.  Both are therefore
+// computed once per coefficient set -- by the SAME arithmetic, in the same order, as the reference -- and cached in
+// device tables; every later solve only runs the two right-hand-side recurrences (3 + 2 dependent fp64 operations per
+// level instead of a reciprocal chain), bit-identical to recomputing them.  Validity is checked ON THE DEVICE at every
+// call (the caller may rescale a,b,c,lambda between calls, main.f90:434-441): a small kernel compares the coefficient
+// arrays with the cached copies, and the table-build kernel that follows is a no-op unless something changed.  No host
+// synchronisation anywhere.
+//
+// Solve kernel: one warp per CTA, one thread per (i,j) column.  Right-hand side and pivots stream in through an
+// cp.async ring (GD levels ahead, thread-private slots: no barriers), the forward sweep leaves its result in shared
+// memory (the last S levels; earlier levels of very long columns spill to global memory), the backward sweep reads
+// it back from there and stores the solution: 8 B read + 8 B pivots + 8 B write per cell (+ 8 B for p2 when periodic).
+#include <algorithm>
+#include <cstdlib>
+
+#include "common.cuh"
+
+#define EPS 2.220446049250313e-16
+#define GC 32     // columns per CTA
+#define GU 8      // levels per cp.async group
+
+struct GaussTab {
+  double *Z = nullptr, *P2 = nullptr, *DEN = nullptr;   // [n][nxy] pivots, [n-1][nxy] periodic system, [nxy] denominator
+  double *ca = nullptr, *cb = nullptr, *cc = nullptr, *clam = nullptr;   // cached coefficient copies
+  unsigned* flag = nullptr;                             // generation of the last detected change
+  const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nxy = 0, n = 0, periodic = 0;
+  long last_use = 0;
+};
+
+static std::map<cales_ctx*, std::vector<GaussTab>> g_tabs;
+static long g_use = 0;
+
+__device__ __forceinline__ void cp8(double* dst_smem, const double* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- validation: flag := gen if any coefficient differs from the cached copy; cache := current --------------------------
+__global__ void gauss_validate_k(int n, int nxy, const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c,
+                                 const double* __restrict__ lam, double* ca, double* cb, double* cc, double* clam, unsigned* flag, unsigned gen) {
+  const long tot = 3L * n + nxy;
+  bool bad = false;
+  for (long q = blockIdx.x * (long)blockDim.x + threadIdx.x; q < tot; q += (long)gridDim.x * blockDim.x) {
+    const double* src; double* dst; long o;
+    if (q < n) { src = a; dst = ca; o = q; }
+    else if (q < 2L * n) { src = b; dst = cb; o = q - n; }
+    else if (q < 3L * n) { src = c; dst = cc; o = q - 2L * n; }
+    else { src = lam; dst = clam; o = q - 3L * n; }
+    const unsigned long long v = __double_as_longlong(src[o]), w = __double_as_longlong(dst[o]);
+    if (v != w) { bad = true; dst[o] = src[o]; }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicMax(flag, gen);
+}
+
+// ---- table build (runs only when the flag carries the current generation) ----------------------------------------------
+template <int PER>
+__global__ void __launch_bounds__(64) gauss_build_k(int nxy, int n, const double* __restrict__ a, const double* __restrict__ b,
+                                                     const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ Z,
+                                                     double* __restrict__ P2, double* __restrict__ DEN, const unsigned* flag, unsigned gen) {
+  if (*flag != gen) return;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nxy) return;
+  const int nlev = PER ? n - 1 : n;
+  const double lam = lambdaxy[col];
+  double dl = 0., g = 0.;
+  for (int l = 0; l < nlev; ++l) {
+    const double al = a[l];
+    const double z = __drcp_rn((b[l] + lam) - al * dl + EPS);
+    dl = c[l] * z;
+    Z[(long)l * nxy + col] = z;
+    if (PER) {
+      double s2 = 0.;
+      if (l == 0) s2 = -a[0];
+      if (l == nlev - 1) s2 = -c[nlev - 1];
+      g = (s2 - al * g) * z;
+      P2[(long)l * nxy + col] = g;
+    }
+  }
+  if (PER) {
+    const double p2n = g;                      // p2(n-1): unchanged by the back substitution
+    double g2 = 0.;
+    for (int l = nlev - 1; l >= 0; --l) {
+      const double d = c[l] * Z[(long)l * nxy + col];
+      g2 = P2[(long)l * nxy + col] - d * g2;
+      P2[(long)l * nxy + col] = g2;
+    }
+    DEN[col] = (b[n - 1] + lam) + c[n - 1] * g2 + a[n - 1] * p2n + EPS;      // solver.f90:143-144
+  }
+}
+
+// ---- solve ----------------------------------------------------------------------------------------------------------
+// nlev levels are swept (n, or n-1 when periodic).  Levels [spill, nlev) keep their forward result in shared memory
+// (S = nlev - spill slots), levels [0, spill) go through global memory (SP; spill is a multiple of GU).
+// Everything is organised in groups of GU consecutive levels = one cp.async group = one ring slot; the ring holds GNG
+// slots.  Slots and smem columns are thread-private, so the kernel needs no barrier after the coefficient load.
+template <bool FULL>
+__device__ __forceinline__ void g_issue(double* dst, const double* src, long stride, int nvalid) {
+#pragma unroll
+  for (int q = 0; q < GU; ++q)
+    if (FULL || q < nvalid) cp8(dst + q * GC, src + q * stride);
+}
+
+template <int PER, bool SP, int GNG>
+__global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, long sz, const double* __restrict__ a, const double* __restrict__ c,
+                                                     const double* __restrict__ Z, const double* __restrict__ P2, const double* __restrict__ DEN,
+                                                     double* __restrict__ p) {
+  extern __shared__ double sh[];
+  constexpr int GD = GU * GNG;
+  const int nlev = PER ? n - 1 : n;
+  const int S = nlev - spill;
+  double* sa = sh; double* sc = sa + n;
+  const int tid = threadIdx.x;
+  double* keep = sc + n + tid;                      // [S][GC], my column
+  double* zr = sc + n + (size_t)S * GC + tid;       // [GNG][GU][GC] pivots (or p2) in flight
+  double* pr = zr + GD * GC;                        // [GNG][GU][GC] spilled levels in flight (SP only)
+  for (int l = tid; l < n; l += GC) { sa[l] = a[l]; sc[l] = c[l]; }
+  __syncthreads();
+  const int col = blockIdx.x * GC + tid;
+  if (col >= nxy) return;
+  double* pp = p + col;
+  const double* zz = Z + col;
+  double plast = 0., den = 1.;
+  if (PER) { plast = pp[(long)(n - 1) * sz]; den = DEN[col]; }
+  const int ngrp = (nlev + GU - 1) / GU, nfull = nlev / GU, ntail = nlev - nfull * GU;
+  const long zst = nxy;
+  // ================= forward elimination: p'(l) = (p(l) - a(l) p'(l-1)) z(l) ======================================
+  // group g = levels g*GU .. g*GU+GU-1
+#define FWD_ISSUE(g_)                                                                                        \
+  {                                                                                                          \
+    const int gg = (g_);                                                                                     \
+    if (gg < ngrp) {                                                                                         \
+      const int l0 = gg * GU, slot = gg % GNG;                                                               \
+      double* pd = (!SP || l0 >= spill) ? keep + (size_t)(l0 - spill) * GC : pr + slot * (GU * GC);          \
+      if (gg < nfull) { g_issue<true>(zr + slot * (GU * GC), zz + l0 * zst, zst, GU); g_issue<true>(pd, pp + l0 * sz, sz, GU); } \
+      else { g_issue<false>(zr + slot * (GU * GC), zz + l0 * zst, zst, ntail); g_issue<false>(pd, pp + l0 * sz, sz, ntail); }    \
+    }                                                                                                        \
+    cp_commit();                                                                                             \
+  }
+#pragma unroll
+  for (int g = 0; g < GNG; ++g) FWD_ISSUE(g)
+  double pl = 0.;
+  for (int g = 0; g < ngrp; ++g) {
+    cp_wait<GNG - 1>();
+    const int l0 = g * GU, slot = g % GNG;
+    const bool kept = !SP || l0 >= spill;
+    const double* zs = zr + slot * (GU * GC);
+    double* ps = kept ? keep + (size_t)(l0 - spill) * GC : pr + slot * (GU * GC);
+    const double* as = sa + l0;
+    double r[GU], z[GU], aa[GU];
+    if (g < nfull) {
+#pragma unroll
+      for (int q = 0; q < GU; ++q) { z[q] = zs[q * GC]; r[q] = ps[q * GC]; aa[q] = as[q]; }
+#pragma unroll
+      for (int q = 0; q < GU; ++q) { pl = (r[q] - aa[q] * pl) * z[q]; r[q] = pl; }
+      if (kept) {
+#pragma unroll
+        for (int q = 0; q < GU; ++q) ps[q * GC] = r[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < GU; ++q) pp[(l0 + q) * sz] = r[q];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < GU; ++q)
+        if (q < ntail) {
+          pl = (ps[q * GC] - as[q] * pl) * zs[q * GC];
+          if (kept) ps[q * GC] = pl; else pp[(l0 + q) * sz] = pl;
+        }
+    }
+    FWD_ISSUE(g + GNG)
+  }
+  cp_wait<0>();
+  const double p1n = pl;                      // p1(n-1) of the periodic solve
+  // ================= backward substitution: p(l) = p'(l) - d(l) p(l+1), d(l) = c(l) z(l) =============================
+  // group g = levels hi-q, q = 0..GU-1, hi = nlev-1-g*GU; the last group may be partial (levels below 0 do not exist)
+#define BWD_ISSUE(g_)                                                                                        \
+  {                                                                                                          \
+    const int gg = (g_);                                                                                     \
+    if (gg < ngrp) {                                                                                         \
+      const int hi = nlev - 1 - gg * GU, slot = gg % GNG;                                                    \
+      if (gg < nfull) g_issue<true>(zr + slot * (GU * GC), zz + hi * zst, -zst, GU);                         \
+      else g_issue<false>(zr + slot * (GU * GC), zz + hi * zst, -zst, ntail);                                \
+      if (SP && hi - (GU - 1) < spill) {                                                                     \
+        _Pragma("unroll") for (int q = 0; q < GU; ++q)                                                       \
+          if (hi - q < spill && hi - q >= 0) cp8(pr + slot * (GU * GC) + q * GC, pp + (hi - q) * sz);        \
+      }                                                                                                      \
+    }                                                                                                        \
+    cp_commit();                                                                                             \
+  }
+#pragma unroll
+  for (int g = 0; g < GNG; ++g) BWD_ISSUE(g)
+  pl = 0.;
+  for (int g = 0; g < ngrp; ++g) {
+    cp_wait<GNG - 1>();
+    const int hi = nlev - 1 - g * GU, slot = g % GNG;
+    const double* zs = zr + slot * (GU * GC);
+    const double* prs = pr + slot * (GU * GC);
+    double* ks = keep + (long)(hi - spill) * GC;     // level hi-q at ks[-q*GC]
+    const double* cs = sc + hi;
+    if (g < nfull && (!SP || hi - (GU - 1) >= spill)) {
+      double r[GU], d[GU];
+#pragma unroll
+      for (int q = 0; q < GU; ++q) { d[q] = cs[-q] * zs[q * GC]; r[q] = ks[-q * GC]; }
+#pragma unroll
+      for (int q = 0; q < GU; ++q) { pl = r[q] - d[q] * pl; r[q] = pl; }
+      if (PER) {
+#pragma unroll
+        for (int q = 0; q < GU; ++q) ks[-q * GC] = r[q];
+      } else {
+#pragma unroll
+        for (int q = 0; q < GU; ++q) pp[(hi - q) * sz] = r[q];
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < GU; ++q) {
+        const int l = hi - q;
+        if (l >= 0) {
+          const bool kept = !SP || l >= spill;
+          const double d = cs[-q] * zs[q * GC];
+          pl = (kept ? ks[-q * GC] : prs[q * GC]) - d * pl;
+          if (PER && kept) ks[-q * GC] = pl; else pp[l * sz] = pl;
+        }
+      }
+    }
+    BWD_ISSUE(g + GNG)
+  }
+  cp_wait<0>();
+  if (!PER) return;
+  // ================= periodic closure (solver.f90:142-145): p(n) and p(1:n-1) = p1 + p2 p(n) ===========================
+  const double pn = (plast - sc[n - 1] * pl - sa[n - 1] * p1n) / den;
+  pp[(long)(n - 1) * sz] = pn;
+  const double* p2 = P2 + col;
+#define CMB_ISSUE(g_)                                                                                        \
+  {                                                                                                          \
+    const int gg = (g_);                                                                                     \
+    if (gg < ngrp) {                                                                                         \
+      const int l0 = gg * GU, slot = gg % GNG;                                                               \
+      if (gg < nfull) g_issue<true>(zr + slot * (GU * GC), p2 + l0 * zst, zst, GU);                          \
+      else g_issue<false>(zr + slot * (GU * GC), p2 + l0 * zst, zst, ntail);                                 \
+      if (SP && l0 < spill) g_issue<true>(pr + slot * (GU * GC), pp + l0 * sz, sz, GU);                      \
+    }                                                                                                        \
+    cp_commit();                                                                                             \
+  }
+#pragma unroll
+  for (int g = 0; g < GNG; ++g) CMB_ISSUE(g)
+  for (int g = 0; g < ngrp; ++g) {
+    cp_wait<GNG - 1>();
+    const int l0 = g * GU, slot = g % GNG;
+    const double* zs = zr + slot * (GU * GC);
+    const double* ps = (!SP || l0 >= spill) ? keep + (size_t)(l0 - spill) * GC : pr + slot * (GU * GC);
+    if (g < nfull) {
+      double r[GU];
+#pragma unroll
+      for (int q = 0; q < GU; ++q) r[q] = ps[q * GC] + zs[q * GC] * pn;
+#pragma unroll
+      for (int q = 0; q < GU; ++q) pp[(l0 + q) * sz] = r[q];
+    } else {
+#pragma unroll
+      for (int q = 0; q < GU; ++q)
+        if (q < ntail) pp[(l0 + q) * sz] = ps[q * GC] + zs[q * GC] * pn;
+    }
+    CMB_ISSUE(g + GNG)
+  }
+  cp_wait<0>();
+#undef FWD_ISSUE
+#undef BWD_ISSUE
+#undef CMB_ISSUE
+}
+
+static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const double* a, const double* b, const double* c, const double* lam) {
+  std::vector<GaussTab>& v = g_tabs[ctx];
+  for (auto& t : v)
+    if (t.nxy == nxy && t.n == n && t.periodic == periodic && t.key[0] == a && t.key[1] == b && t.key[2] == c && t.key[3] == lam) return &t;
+  GaussTab* t = nullptr;
+  if (v.size() < 8) { v.emplace_back(); t = &v.back(); }
+  else {
+    t = &v[0];
+    for (auto& u : v) if (u.last_use < t->last_use) t = &u;
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(t->Z); cudaFree(t->P2); cudaFree(t->DEN); cudaFree(t->ca); cudaFree(t->clam); cudaFree(t->flag);
+    *t = GaussTab();
+  }
+  const size_t cells = (size_t)nxy * n;
+  bool ok = cudaMalloc(&t->Z, cells * sizeof(double)) == cudaSuccess;
+  if (periodic) ok = ok && cudaMalloc(&t->P2, cells * sizeof(double)) == cudaSuccess && cudaMalloc(&t->DEN, nxy * sizeof(double)) == cudaSuccess;
+  ok = ok && cudaMalloc(&t->ca, 3 * (size_t)n * sizeof(double)) == cudaSuccess && cudaMalloc(&t->clam, nxy * sizeof(double)) == cudaSuccess &&
+       cudaMalloc(&t->flag, sizeof(unsigned)) == cudaSuccess;
+  if (!ok) { cales_fail(ctx, CALES_ERR_NOMEM, "tridiagonal pivot tables (%zu bytes) could not be allocated", cells * 8 * (periodic ? 2 : 1)); return nullptr; }
+  t->cb = t->ca + n; t->cc = t->cb + n;
+  // cached copies start as an all-ones bit pattern (a NaN no caller passes), so the first validation fails
+  cudaMemsetAsync(t->ca, 0xff, 3 * (size_t)n * sizeof(double), ctx->stream);
+  cudaMemsetAsync(t->clam, 0xff, nxy * sizeof(double), ctx->stream);
+  cudaMemsetAsync(t->flag, 0, sizeof(unsigned), ctx->stream);
+  t->nxy = nxy; t->n = n; t->periodic = periodic;
+  t->key[0] = a; t->key[1] = b; t->key[2] = c; t->key[3] = lam;
+  return t;
+}
+
+void k_gaussel_tab_free(cales_ctx* ctx) {
+  auto it = g_tabs.find(ctx);
+  if (it == g_tabs.end()) return;
+  for (auto& t : it->second) { cudaFree(t.Z); cudaFree(t.P2); cudaFree(t.DEN); cudaFree(t.ca); cudaFree(t.clam); cudaFree(t.flag); }
+  g_tabs.erase(it);
+}
+
+// returns 1 if handled, 0 if the caller should use the direct kernels, < 0 on error
+int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
+                  const double* lambdaxy, double* p) {
+  if (!lambdaxy) return 0;
+  const int nxy = nx * ny;
+  const int nlev = periodic ? n - 1 : n;
+  if (nlev < 1) return 0;
+  GaussTab* t = find_tab(ctx, nxy, n, periodic, a, b, c, lambdaxy);
+  if (!t) return -CALES_ERR_NOMEM;
+  t->last_use = ++g_use;
+  static unsigned gen = 0;
+  ++gen;
+  const long tot = 3L * n + nxy;
+  gauss_validate_k<<<(int)std::min<long>((tot + 255) / 256, 592), 256, 0, ctx->stream>>>(n, nxy, a, b, c, lambdaxy, t->ca, t->cb, t->cc, t->clam, t->flag, gen);
+  ctx->launches++;
+  if (periodic) gauss_build_k<1><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->flag, gen);
+  else gauss_build_k<0><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->flag, gen);
+  ctx->launches++;
+  // shared memory: coefficients + kept levels + the two rings; keep three CTAs per SM when the column is long
+  static const size_t budget = getenv("CALES_GAUSS_SMEM") ? (size_t)atol(getenv("CALES_GAUSS_SMEM")) : 76800;   // 3 CTAs per SM
+  static const int gng = getenv("CALES_GAUSS_GNG") ? atoi(getenv("CALES_GAUSS_GNG")) : 3;
+  const int GD = GU * gng;
+  size_t fixed = (2 * (size_t)n + GD * GC) * sizeof(double);
+  int S = nlev;
+  if (fixed + (size_t)S * GC * sizeof(double) > budget) {         // long columns: second ring + spill the early levels
+    fixed += GD * GC * sizeof(double);
+    S = budget > fixed ? (int)((budget - fixed) / (GC * sizeof(double))) : 0;
+  }
+  int spill = nlev - S;
+  if (spill > 0) { spill = std::min(nlev - nlev % GU, ((spill + GU - 1) / GU) * GU); S = nlev - spill; }   // whole groups spill
+  const size_t sh = fixed + (size_t)S * GC * sizeof(double);
+  const dim3 g(cdiv(nxy, GC));
+#define GS_GO(PER_, SP_, NG_)                                                                                         \
+  {                                                                                                                   \
+    static bool attr = false;                                                                                         \
+    if (!attr) { attr = true; cudaFuncSetAttribute(gauss_solve_k<PER_, SP_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); } \
+    gauss_solve_k<PER_, SP_, NG_><<<g, GC, sh, ctx->stream>>>(nxy, n, spill, sz, a, c, t->Z, t->P2, t->DEN, p);      \
+  }
+#define GS_NG(NG_)                                                                   \
+  {                                                                                  \
+    if (periodic) { if (spill) GS_GO(1, true, NG_) else GS_GO(1, false, NG_) }       \
+    else { if (spill) GS_GO(0, true, NG_) else GS_GO(0, false, NG_) }                \
+  }
+  if (gng == 3) GS_NG(3) else if (gng == 6) GS_NG(6) else if (gng == 12) GS_NG(12) else return -cales_fail(ctx, CALES_ERR_INVALID, "CALES_GAUSS_GNG must be 3, 6 or 12");
+#undef GS_NG
+#undef GS_GO
+  ctx->launches++;
+  if (cudaGetLastError() != cudaSuccess) return -cales_fail(ctx, CALES_ERR_CUDA, "gauss_solve_k launch failed");
+  return 1;
+}

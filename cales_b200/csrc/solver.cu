@@ -9,12 +9,15 @@
 // (pivot regularisation `+eps` included), and the backward x pass writes the haloed field scaled by
 // normfft: five sweeps, 16 B/cell each, no transposes and no copy-in/out passes.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 
 int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
                const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale);
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
+int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
+                  const double* lambdaxy, double* p);
 
 #define EPS 2.220446049250313e-16
 
@@ -213,6 +216,15 @@ int k_gaussel(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, cons
               const double* lambdaxy, double* p) {
   const int nxy = nx * ny;
   if (periodic && n < 3) return cales_fail(ctx, CALES_ERR_INVALID, "periodic tridiagonal solve needs n >= 3");
+  {
+    // fast path: cached pivots (gaussel_tab.cu); CALES_GAUSSEL_DIRECT=1 forces the recompute-everything kernels below
+    static const bool direct = getenv("CALES_GAUSSEL_DIRECT") != nullptr;
+    if (!direct) {
+      const int rc = k_gaussel_tab(ctx, nx, ny, n, sz, periodic, a, b, c, lambdaxy, p);
+      if (rc < 0) return -rc;
+      if (rc == 1) return CALES_OK;
+    }
+  }
   const int ntile = ((periodic ? n - 1 : n) + TZ - 1) / TZ;
   const size_t sh = ((size_t)ntile * GT * (periodic ? 2 : 1) + (size_t)n * (periodic ? 4 : 3)) * sizeof(double);
   if (sh > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "tridiagonal system of %d points exceeds the checkpoint buffer", n);
