@@ -77,6 +77,23 @@ void* cales_scratch(cales_ctx* ctx, const char* name, size_t bytes, bool zero_on
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// z-chunk of a marching kernel: `cols` CTAs per chunk, `resident` CTAs fit on the GPU at once (148 SMs x CTAs/SM),
+// every chunk re-reads `extra` planes (carried values / staging prologue).  Picks the chunk count that maximises
+// (fill of the last wave) x (useful planes / planes read), with at least `min_kc` levels per chunk.
+static inline int pick_chunk(long cols, int nk, int resident, int min_kc, int extra) {
+  int best = nk; double beste = -1.;
+  for (int chunks = 1; chunks <= nk; ++chunks) {
+    const int kc = (nk + chunks - 1) / chunks;
+    if (kc < min_kc && chunks > 1) break;
+    const long ctas = cols * ((nk + kc - 1) / kc);
+    const double waves = (double)ctas / resident;
+    const double fill = waves / (double)((ctas + resident - 1) / resident);
+    const double e = fill * kc / (double)(kc + extra) * (waves >= 3. ? 1. : 0.6 + 0.4 * waves / 3.);   // a few waves hide ramp-up/tail
+    if (e > beste + 1e-9) { beste = e; best = kc; }
+  }
+  return best;
+}
+
 // tables indexed ib + 2*idir
 __host__ __device__ inline int tb(int ib, int idir) { return ib + 2 * idir; }
 

@@ -214,8 +214,7 @@ static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, co
                       double* dwdt, double* dudtd, double* dvdtd, double* dwdtd) {
   Dims d(n);
   long cols = (long)cdiv(n[0], TX) * cdiv(n[1], TY);
-  int kc = n[2];
-  while (kc > 16 && cols * cdiv(n[2], kc) < 148 * 6) kc = (kc + 1) / 2;
+  const int kc = pick_chunk(cols, n[2], 148 * 2, 12, 2);
   dim3 g(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc)), b(TX, TY);
   const size_t sh = 12 * PLANE * sizeof(double);
   if (ctx->diffusion == CALES_DIFF_EXPLICIT)
@@ -240,7 +239,11 @@ extern "C" int cales_mom_xyz_ad(cales_ctx* ctx, const int n[3], double dxi, doub
 // ---- RK update (rk.f90:77-94) ---------------------------------------------------------------------------
 #define BX 64
 #define BY 4
-template <int IMP>
+// F2: factor2 != 0 (the first RK substep has rkpar(2) = 0: the old right-hand side is not read at all; adding
+// 0*dudtrko changes no bit of a finite sum).  Loads of RU consecutive levels are issued together before any store so
+// that each thread keeps ~10*RU independent requests in flight.
+#define RU 2
+template <int IMP, int F2>
 __global__ void __launch_bounds__(BX* BY) rk_update_k(Dims d, double f1, double f2, double f12, double dxi, double dyi,
                                                        const double* __restrict__ dzci, double bfx, double bfy, double bfz,
                                                        const double* __restrict__ p, const double* __restrict__ du,
@@ -253,15 +256,47 @@ __global__ void __launch_bounds__(BX* BY) rk_update_k(Dims d, double f1, double 
   if (i > d.n1 || j > d.n2) return;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
   long c = d.idx(i, j, k0);
-  const long n12 = (long)d.n1 * d.n2;
+  const long n12 = (long)d.n1 * d.n2, s1 = d.s1, s2 = d.s2;
   long o = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k0 - 1);
   double pc = p[c];
-#pragma unroll 4
-  for (int k = k0; k <= k1; ++k, c += d.s2, o += n12) {
-    const double pk = p[c + d.s2];
-    double un = u[c] + f1 * du[o] + f2 * duo[o] + f12 * (bfx - dxi * (p[c + 1] - pc));
-    double vn = v[c] + f1 * dv[o] + f2 * dvo[o] + f12 * (bfy - dyi * (p[c + d.s1] - pc));
-    double wn = w[c] + f1 * dw[o] + f2 * dwo[o] + f12 * (bfz - dzci[k] * (pk - pc));
+  int k = k0;
+  for (; k + RU - 1 <= k1; k += RU, c += RU * s2, o += RU * n12) {
+    double uu[RU], vv[RU], ww[RU], pk[RU], pi[RU], pj[RU], a[RU], b[RU], e[RU], ao[RU], bo[RU], eo[RU], ad[RU], bd[RU], ed[RU], dz[RU];
+#pragma unroll
+    for (int q = 0; q < RU; ++q) {
+      const long cq = c + q * s2, oq = o + q * n12;
+      uu[q] = u[cq]; vv[q] = v[cq]; ww[q] = w[cq];
+      pk[q] = p[cq + s2]; pi[q] = p[cq + 1]; pj[q] = p[cq + s1];
+      a[q] = du[oq]; b[q] = dv[oq]; e[q] = dw[oq];
+      if (F2) { ao[q] = duo[oq]; bo[q] = dvo[oq]; eo[q] = dwo[oq]; }
+      if (IMP) { ad[q] = dud[oq]; bd[q] = dvd[oq]; ed[q] = dwd[oq]; }
+      dz[q] = dzci[k + q];
+    }
+#pragma unroll
+    for (int q = 0; q < RU; ++q) {
+      const long cq = c + q * s2;
+      double un, vn, wn;
+      if (F2) {
+        un = uu[q] + f1 * a[q] + f2 * ao[q] + f12 * (bfx - dxi * (pi[q] - pc));
+        vn = vv[q] + f1 * b[q] + f2 * bo[q] + f12 * (bfy - dyi * (pj[q] - pc));
+        wn = ww[q] + f1 * e[q] + f2 * eo[q] + f12 * (bfz - dz[q] * (pk[q] - pc));
+      } else {
+        un = uu[q] + f1 * a[q] + f12 * (bfx - dxi * (pi[q] - pc));
+        vn = vv[q] + f1 * b[q] + f12 * (bfy - dyi * (pj[q] - pc));
+        wn = ww[q] + f1 * e[q] + f12 * (bfz - dz[q] * (pk[q] - pc));
+      }
+      if (IMP) { un = un + f12 * ad[q]; vn = vn + f12 * bd[q]; wn = wn + f12 * ed[q]; }
+      u[cq] = un; v[cq] = vn; w[cq] = wn;
+      pc = pk[q];
+    }
+  }
+  for (; k <= k1; ++k, c += s2, o += n12) {
+    const double pk = p[c + s2];
+    double un = u[c] + f1 * du[o], vn = v[c] + f1 * dv[o], wn = w[c] + f1 * dw[o];
+    if (F2) { un = un + f2 * duo[o]; vn = vn + f2 * dvo[o]; wn = wn + f2 * dwo[o]; }
+    un = un + f12 * (bfx - dxi * (p[c + 1] - pc));
+    vn = vn + f12 * (bfy - dyi * (p[c + s1] - pc));
+    wn = wn + f12 * (bfz - dzci[k] * (pk - pc));
     if (IMP) { un = un + f12 * dud[o]; vn = vn + f12 * dvd[o]; wn = wn + f12 * dwd[o]; }
     u[c] = un; v[c] = vn; w[c] = wn;
     pc = pk;
@@ -316,15 +351,13 @@ int k_rk_dev(cales_ctx* ctx, const double rkpar[2], const int n[3], const double
   if (rc) return rc;
   Dims d(n);
   long cols = (long)cdiv(n[0], BX) * cdiv(n[1], BY);
-  int kc = n[2];
-  while (kc > 8 && cols * cdiv(n[2], kc) < 148 * 8) kc = (kc + 1) / 2;
+  const int kc = pick_chunk(cols, n[2], 148 * 4, 8, 1);
   dim3 g(cdiv(n[0], BX), cdiv(n[1], BY), cdiv(n[2], kc)), b(BX, BY);
-  if (imp)
-    rk_update_k<1><<<g, b, 0, ctx->stream>>>(d, factor1, factor2, factor12, dli[0], dli[1], dzci, bforce[0], bforce[1], bforce[2], p,
-                                             nw[0], nw[1], nw[2], ol[0], ol[1], ol[2], r[6], r[7], r[8], u, v, w, kc);
-  else
-    rk_update_k<0><<<g, b, 0, ctx->stream>>>(d, factor1, factor2, factor12, dli[0], dli[1], dzci, bforce[0], bforce[1], bforce[2], p,
-                                             nw[0], nw[1], nw[2], ol[0], ol[1], ol[2], nullptr, nullptr, nullptr, u, v, w, kc);
+#define RKU(IMP_, F2_) rk_update_k<IMP_, F2_><<<g, b, 0, ctx->stream>>>(d, factor1, factor2, factor12, dli[0], dli[1], dzci, bforce[0], bforce[1], \
+                                                                         bforce[2], p, nw[0], nw[1], nw[2], ol[0], ol[1], ol[2], r[6], r[7], r[8], u, v, w, kc)
+  if (imp) { if (factor2 != 0.) RKU(1, 1); else RKU(1, 0); }
+  else { if (factor2 != 0.) RKU(0, 1); else RKU(0, 0); }
+#undef RKU
   KERNEL_CHECK(ctx);
   ctx->rk_swap ^= 1;                                 // rk.f90:98-100
   // cmpt_bulk_forcing (rk.f90:197-222)

@@ -18,10 +18,7 @@ struct Ptr6 { double* p[6]; };
 struct CPtr6 { const double* p[6]; };
 
 static inline int pick_kc(int ni, int nj, int nk) {
-  long cols = (long)cdiv(ni, BX) * cdiv(nj, BY);
-  int kc = nk;
-  while (kc > 8 && cols * cdiv(nk, kc) < 148 * 8) kc = (kc + 1) / 2;
-  return kc;
+  return pick_chunk((long)cdiv(ni, BX) * cdiv(nj, BY), nk, 148 * 5, 8, 2);
 }
 
 // ---- Smagorinsky + van Driest (sgs.f90:98-152), fused into the strain-rate kernel ---------------------------------
@@ -94,7 +91,7 @@ __device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, i
 
 // ---- strain rate (sgs.f90:1019-1110) -----------------------------------------------------------------------------
 template <int SIJ, int SMAG>
-__global__ void __launch_bounds__(BX* BY) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
+__global__ void __launch_bounds__(BX* BY, 3) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
                                                     const double* __restrict__ dzfi, const double* __restrict__ u,
                                                     const double* __restrict__ v, const double* __restrict__ w,
                                                     double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc, SmagArgs A) {
@@ -103,13 +100,15 @@ __global__ void __launch_bounds__(BX* BY) strain_k(Dims d, double dxi, double dy
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
   const long s1 = d.s1, s2 = d.s2;
   long c = d.idx(i, j, k0);
+  // z-march with register rotation: the k-1 values are the previous k values and the k values at (i-1..i, j) / (i, j-1..j)
+  // are the previous k+1 values, so a step loads 17 new values instead of 30 (all but three of them L1 hits)
+  double u_mcm = u[c - 1 - s2], u_ccm = u[c - s2], u_mcc = u[c - 1], u_ccc = u[c];
+  double v_cmm = v[c - s1 - s2], v_ccm = v[c - s2], v_cmc = v[c - s1], v_ccc = v[c];
+  double w_cmm = w[c - s1 - s2], w_mcm = w[c - 1 - s2], w_ccm = w[c - s2], w_pcm = w[c + 1 - s2], w_cpm = w[c + s1 - s2];
   for (int k = k0; k <= k1; ++k, c += s2) {
-    const double u_mcm = u[c - 1 - s2], u_ccm = u[c - s2], u_mmc = u[c - 1 - s1], u_cmc = u[c - s1], u_mcc = u[c - 1], u_ccc = u[c],
-                 u_mpc = u[c - 1 + s1], u_cpc = u[c + s1], u_mcp = u[c - 1 + s2], u_ccp = u[c + s2];
-    const double v_cmm = v[c - s1 - s2], v_ccm = v[c - s2], v_mmc = v[c - 1 - s1], v_cmc = v[c - s1], v_pmc = v[c + 1 - s1],
-                 v_mcc = v[c - 1], v_ccc = v[c], v_pcc = v[c + 1], v_cmp = v[c - s1 + s2], v_ccp = v[c + s2];
-    const double w_cmm = w[c - s1 - s2], w_mcm = w[c - 1 - s2], w_ccm = w[c - s2], w_pcm = w[c + 1 - s2], w_cpm = w[c + s1 - s2],
-                 w_cmc = w[c - s1], w_mcc = w[c - 1], w_ccc = w[c], w_pcc = w[c + 1], w_cpc = w[c + s1];
+    const double u_mmc = u[c - 1 - s1], u_cmc = u[c - s1], u_mpc = u[c - 1 + s1], u_cpc = u[c + s1], u_mcp = u[c - 1 + s2], u_ccp = u[c + s2];
+    const double v_mmc = v[c - 1 - s1], v_pmc = v[c + 1 - s1], v_mcc = v[c - 1], v_pcc = v[c + 1], v_cmp = v[c - s1 + s2], v_ccp = v[c + s2];
+    const double w_cmc = w[c - s1], w_mcc = w[c - 1], w_ccc = w[c], w_pcc = w[c + 1], w_cpc = w[c + s1];
     const double dzci_k = dzci[k], dzci_km = dzci[k - 1];
     const double s11 = (u_ccc - u_mcc) * dxi;
     const double s22 = (v_ccc - v_cmc) * dyi;
@@ -130,6 +129,9 @@ __global__ void __launch_bounds__(BX* BY) strain_k(Dims d, double dxi, double dy
       sij.p[0][c] = s11; sij.p[1][c] = s22; sij.p[2][c] = s33; sij.p[3][c] = s12; sij.p[4][c] = s13; sij.p[5][c] = s23;
       if (s0copy) s0copy[c] = s;
     }
+    u_mcm = u_mcc; u_ccm = u_ccc; u_mcc = u_mcp; u_ccc = u_ccp;
+    v_cmm = v_cmc; v_ccm = v_ccc; v_cmc = v_cmp; v_ccc = v_ccp;
+    w_cmm = w_cmc; w_mcm = w_mcc; w_ccm = w_ccc; w_pcm = w_pcc; w_cpm = w_cpc;
   }
 }
 

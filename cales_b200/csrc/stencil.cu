@@ -16,10 +16,7 @@ static inline dim3 grid_for(int ni, int nj, int nk, int kchunk) { return dim3(cd
 
 // choose a z-chunk so that the grid has a few waves of CTAs on 148 SMs
 static inline int pick_kchunk(int ni, int nj, int nk) {
-  long cols = (long)cdiv(ni, BX) * cdiv(nj, BY);
-  int kc = nk;
-  while (kc > 8 && cols * cdiv(nk, kc) < 148 * 8) kc = (kc + 1) / 2;
-  return kc;
+  return pick_chunk((long)cdiv(ni, BX) * cdiv(nj, BY), nk, 148 * 8, 8, 1);
 }
 
 __global__ void __launch_bounds__(BX* BY) fillps_k(Dims d, double dxi, double dyi, const double* __restrict__ dzfi, double dti,
@@ -49,20 +46,45 @@ extern "C" int cales_fillps(cales_ctx* ctx, const int n[3], const double dli[3],
   return CALES_OK;
 }
 
-// correc: u over i=0:n1, j=0:n2+1, k=0:n3+1; v over i=0:n1+1, j=0:n2, k=0:n3+1; w over k=0:n3 (ghost rows included)
-__global__ void __launch_bounds__(BX* BY) correc_k(Dims d, double factori, double factorj, double dt, const double* __restrict__ dzci,
-                                                    const double* __restrict__ p, double* __restrict__ u,
-                                                    double* __restrict__ v, double* __restrict__ w, int kc) {
-  const int i = blockIdx.x * BX + threadIdx.x, j = blockIdx.y * BY + threadIdx.y;
-  if (i > d.n1 + 1 || j > d.n2 + 1) return;
-  const int k0 = blockIdx.z * kc, k1 = min(k0 + kc - 1, d.n3 + 1);
-  long c = d.idx(i, j, k0);
+// correc: u over i=0:n1, j=0:n2+1, k=0:n3+1; v over i=0:n1+1, j=0:n2, k=0:n3+1; w over k=0:n3 (ghost rows included).
+// The update covers whole haloed planes, so threads are laid over the linear plane index q = i + (n1+2) j (no partial
+// tiles, perfectly coalesced); CU levels are loaded together before any store.
+#define CU 2
+__global__ void __launch_bounds__(256) correc_k(Dims d, double factori, double factorj, double dt, const double* __restrict__ dzci,
+                                                const double* __restrict__ p, double* __restrict__ u,
+                                                double* __restrict__ v, double* __restrict__ w, int kc) {
+  const long q = blockIdx.x * 256L + threadIdx.x;
+  if (q >= d.s2) return;
+  const int j = (int)(q / d.s1), i = (int)(q - j * d.s1);
+  const bool du = i <= d.n1, dv = j <= d.n2;
+  const int k0 = blockIdx.y * kc, k1 = min(k0 + kc - 1, d.n3 + 1);
+  const long s1 = d.s1, s2 = d.s2;
+  long c = q + s2 * k0;
+  // p(i+1), p(j+1) of the last ghost row/plane are never used; keep the addresses inside the array
+  const long oi = du ? 1 : 0, oj = dv ? s1 : 0;
   double pc = p[c];
-#pragma unroll 4
-  for (int k = k0; k <= k1; ++k, c += d.s2) {
-    const double pk = k <= d.n3 ? p[c + d.s2] : 0.0;
-    if (i <= d.n1) u[c] = u[c] - factori * (p[c + 1] - pc);
-    if (j <= d.n2) v[c] = v[c] - factorj * (p[c + d.s1] - pc);
+  int k = k0;
+  for (; k + CU - 1 <= k1 && k + CU - 1 <= d.n3; k += CU, c += CU * s2) {
+    double pk[CU], pi[CU], pj[CU], uu[CU], vv[CU], ww[CU], dz[CU];
+#pragma unroll
+    for (int r = 0; r < CU; ++r) {
+      const long cr = c + r * s2;
+      pk[r] = p[cr + s2]; pi[r] = p[cr + oi]; pj[r] = p[cr + oj];
+      uu[r] = u[cr]; vv[r] = v[cr]; ww[r] = w[cr]; dz[r] = dzci[k + r];
+    }
+#pragma unroll
+    for (int r = 0; r < CU; ++r) {
+      const long cr = c + r * s2;
+      if (du) u[cr] = uu[r] - factori * (pi[r] - pc);
+      if (dv) v[cr] = vv[r] - factorj * (pj[r] - pc);
+      w[cr] = ww[r] - dt * dz[r] * (pk[r] - pc);
+      pc = pk[r];
+    }
+  }
+  for (; k <= k1; ++k, c += s2) {
+    const double pk = k <= d.n3 ? p[c + s2] : 0.0;
+    if (du) u[c] = u[c] - factori * (p[c + oi] - pc);
+    if (dv) v[c] = v[c] - factorj * (p[c + oj] - pc);
     if (k <= d.n3) w[c] = w[c] - dt * dzci[k] * (pk - pc);
     pc = pk;
   }
@@ -72,8 +94,9 @@ extern "C" int cales_correc(cales_ctx* ctx, const int n[3], const double dli[3],
                             const double* p, double* u, double* v, double* w) {
   CHECK_CTX(ctx);
   Dims d(n);
-  const int kc = pick_kchunk(n[0] + 2, n[1] + 2, n[2] + 2);
-  correc_k<<<grid_for(n[0] + 2, n[1] + 2, n[2] + 2, kc), dim3(BX, BY), 0, ctx->stream>>>(d, dt * dli[0], dt * dli[1], dt, dzci, p, u, v, w, kc);
+  const int cols = cdiv(d.s2, 256);
+  const int kc = pick_chunk(cols, n[2] + 2, 148 * 8, 8, 1);
+  correc_k<<<dim3(cols, cdiv(n[2] + 2, kc)), 256, 0, ctx->stream>>>(d, dt * dli[0], dt * dli[1], dt, dzci, p, u, v, w, kc);
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
