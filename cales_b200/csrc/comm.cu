@@ -7,6 +7,8 @@
 // message per neighbour (the reference sends one message per field and direction).
 #include <nccl.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 // NCCL is bound at run time (dlopen) and only when nranks > 1: a host process that already carries an NCCL
@@ -18,6 +20,7 @@ struct NcclApi {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -33,7 +36,7 @@ static int nccl_load(cales_ctx* ctx) {
   if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!h) return cales_fail(ctx, CALES_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
 #define SYM(name) *(void**)(&g_nccl.name) = dlsym(h, "nccl" #name); if (!g_nccl.name) return cales_fail(ctx, CALES_ERR_NCCL, "libnccl lacks nccl" #name)
-  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
+  SYM(GetUniqueId); SYM(CommInitRank); SYM(CommDestroy); SYM(AllReduce); SYM(AllGather); SYM(Send); SYM(Recv); SYM(GroupStart); SYM(GroupEnd); SYM(GetErrorString);
 #undef SYM
   g_nccl.h = h;
   return CALES_OK;
@@ -69,6 +72,13 @@ int comm_init(cales_ctx* ctx, const char* uid) {
 }
 
 void comm_finalize(cales_ctx* ctx) {
+  if (ctx->nccl && !ctx->peerbufs.empty()) { k_barrier(ctx); cudaStreamSynchronize(ctx->stream); }   // nobody still stores into my buffers
+  for (auto& kv : ctx->peerbufs) {
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && kv.second.ptr[r]) cudaIpcCloseMemHandle(kv.second.ptr[r]);
+    cudaFree(kv.second.local);
+  }
+  ctx->peerbufs.clear();
   if (ctx->nccl) { g_nccl.CommDestroy((ncclComm_t)ctx->nccl); ctx->nccl = nullptr; }
 }
 
@@ -81,6 +91,80 @@ int k_allreduce_sum(cales_ctx* ctx, double* dev, int count) {
 int k_allreduce_minmax(cales_ctx* ctx, double* dev, int count, int is_max) {
   if (ctx->nranks == 1) return CALES_OK;
   NCCL_TRY(ctx, g_nccl.AllReduce(dev, dev, count, ncclDouble, is_max ? ncclMax : ncclMin, (ncclComm_t)ctx->nccl, ctx->stream));
+  return CALES_OK;
+}
+
+// ---- peer memory (CUDA IPC over NVLink / NVSwitch) --------------------------------------------------------------
+// Every rank allocates the buffer, publishes its IPC handle with one ncclAllGather and maps the handles of all other
+// ranks, so kernels can store straight into a peer's pencil (the transposes below, and the fused transform/solve
+// kernels of the distributed solver).  CALES_NO_P2P=1 keeps the NCCL send/recv path.
+PeerBuf* k_peer_buffer(cales_ctx* ctx, const char* name, size_t bytes) {
+  if (ctx->nranks == 1 || !ctx->nccl || ctx->nranks > CALES_MAX_RANKS) return nullptr;
+  if (ctx->p2p == -1) ctx->p2p = getenv("CALES_NO_P2P") ? 0 : 1;
+  if (ctx->p2p == 0) return nullptr;
+  auto it = ctx->peerbufs.find(name);
+  if (it != ctx->peerbufs.end() && it->second.bytes >= bytes) return &it->second;
+  if (it != ctx->peerbufs.end()) {                      // grow: unmap, free, re-create (collective: all ranks take this branch together)
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ctx->nranks; ++r)
+      if (r != ctx->rank && it->second.ptr[r]) cudaIpcCloseMemHandle(it->second.ptr[r]);
+    k_barrier(ctx); cudaStreamSynchronize(ctx->stream);
+    cudaFree(it->second.local);
+    ctx->peerbufs.erase(it);
+  }
+  PeerBuf pb;
+  pb.bytes = bytes;
+  if (cudaMalloc(&pb.local, bytes) != cudaSuccess) { cales_fail(ctx, CALES_ERR_NOMEM, "cudaMalloc(%zu) for peer buffer '%s' failed", bytes, name); return nullptr; }
+  cudaIpcMemHandle_t mine;
+  const int n = ctx->nranks;
+  bool ok = cudaIpcGetMemHandle(&mine, pb.local) == cudaSuccess;
+  // exchange {ok flag, handle} records
+  const size_t rec = 128;
+  static_assert(sizeof(cudaIpcMemHandle_t) + 8 <= 128, "ipc record");
+  std::vector<char> h(rec * n, 0);
+  char* dsend = nullptr; char* drecv = nullptr;
+  cudaMalloc(&dsend, rec); cudaMalloc(&drecv, rec * n);
+  char mrec[128] = {0};
+  mrec[0] = ok ? 1 : 0;
+  memcpy(mrec + 8, &mine, sizeof mine);
+  cudaMemcpyAsync(dsend, mrec, rec, cudaMemcpyHostToDevice, ctx->stream);
+  const bool sent = g_nccl.AllGather(dsend, drecv, rec, ncclChar, (ncclComm_t)ctx->nccl, ctx->stream) == ncclSuccess;
+  cudaMemcpyAsync(h.data(), drecv, rec * n, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(dsend); cudaFree(drecv);
+  bool all = sent;
+  for (int r = 0; r < n; ++r) all = all && h[rec * r] == 1;
+  if (all) {
+    for (int r = 0; r < n && all; ++r) {
+      if (r == ctx->rank) { pb.ptr[r] = pb.local; continue; }
+      cudaIpcMemHandle_t hd;
+      memcpy(&hd, h.data() + rec * r + 8, sizeof hd);
+      if (cudaIpcOpenMemHandle(&pb.ptr[r], hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) all = false;
+    }
+  }
+  // every rank must reach the same verdict: sum of failures
+  double fail = all ? 0. : 1.;
+  if (!ctx->bar) cudaMalloc(&ctx->bar, sizeof(double));
+  cudaMemcpyAsync(ctx->bar, &fail, sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+  g_nccl.AllReduce(ctx->bar, ctx->bar, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream);
+  cudaMemcpyAsync(&fail, ctx->bar, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  cudaGetLastError();
+  if (fail != 0.) {
+    for (int r = 0; r < n; ++r) if (r != ctx->rank && pb.ptr[r]) cudaIpcCloseMemHandle(pb.ptr[r]);
+    cudaFree(pb.local);
+    ctx->p2p = 0;
+    fprintf(stderr, "cales_b200: CUDA IPC peer mapping unavailable on rank %d; using NCCL send/recv transposes\n", ctx->rank);
+    return nullptr;
+  }
+  ctx->peerbufs[name] = pb;
+  return &ctx->peerbufs[name];
+}
+
+int k_barrier(cales_ctx* ctx) {
+  if (ctx->nranks == 1) return CALES_OK;
+  if (!ctx->bar) { CUDA_TRY(ctx, cudaMalloc(&ctx->bar, sizeof(double))); CUDA_TRY(ctx, cudaMemsetAsync(ctx->bar, 0, sizeof(double), ctx->stream)); }
+  NCCL_TRY(ctx, g_nccl.AllReduce(ctx->bar, ctx->bar, 1, ncclDouble, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
   return CALES_OK;
 }
 
@@ -183,7 +267,7 @@ extern "C" int cales_updthalo(cales_ctx* ctx, const int n[3], const int nb[6], d
 // grid; pencil B is complete along `be` and split along `al`.  Rank q receives my sub-box al in range_al(q);
 // I receive from q the sub-box be in range_be(q).  One pack launch builds all peer slabs, one NCCL group moves
 // them over NVLink (the self slab never leaves the device), one unpack launch scatters them.
-struct Seg { long soff, doff; int b0, b1, b2; long ss1, ss2, ds1, ds2; };
+struct Seg { long soff, doff; int b0, b1, b2; long ss1, ss2, ds1, ds2; double* dptr; };
 struct SegList { Seg s[16]; int n; };
 
 __global__ void __launch_bounds__(256) boxcopy_k(const double* __restrict__ src, double* __restrict__ dst, SegList L) {
@@ -193,7 +277,7 @@ __global__ void __launch_bounds__(256) boxcopy_k(const double* __restrict__ src,
   const long rows = (long)g.b1 * g.b2;
   for (long r = blockIdx.y * 4 + threadIdx.y; r < rows; r += (long)gridDim.y * 4) {
     const int j = (int)(r % g.b1), k = (int)(r / g.b1);
-    dst[g.doff + i + j * g.ds1 + k * g.ds2] = src[g.soff + i + j * g.ss1 + k * g.ss2];
+    (g.dptr ? g.dptr : dst)[g.doff + i + j * g.ds1 + k * g.ds2] = src[g.soff + i + j * g.ss1 + k * g.ss2];
   }
 }
 
@@ -259,6 +343,7 @@ int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {
   for (int q = 0; q < P; ++q) {
     const int* sb = sendbox + 6 * q; const int* rb = recvbox + 6 * q;
     Seg& g = pk.s[q];
+    g.dptr = nullptr; up.s[q].dptr = nullptr;
     g.b0 = sb[3]; g.b1 = sb[4]; g.b2 = sb[5];
     g.soff = sb[0] + sb[1] * As1 + sb[2] * As2; g.ss1 = As1; g.ss2 = As2;
     g.doff = so; g.ds1 = sb[3]; g.ds2 = (long)sb[3] * sb[4];
@@ -282,6 +367,40 @@ int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {
   // the self slab never leaves the device
   CUDA_TRY(ctx, cudaMemcpyAsync(rbuf + roff[me], sbuf + soff[me], scnt[me] * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   return boxcopy(ctx, rbuf, dst, up);
+}
+
+// Peer-memory transpose: ONE kernel reads my pencil and stores every sub-box straight into the destination pencil of
+// its owner (local or over NVLink) in its final layout -- no pack, no unpack, no staging buffers -- followed by a
+// stream-ordered barrier.  dst must be a peer buffer (k_peer_buffer); the caller guarantees by the barrier discipline
+// of the solver that no rank still reads it.
+int k_transpose_p2p(cales_ctx* ctx, int which, const double* src, PeerBuf* dst) {
+  int P, peers[16], sendbox[96], recvbox[96], A[3], B[3];
+  const bool colcomm = (which == 0 || which == 3);
+  if ((colcomm ? ctx->dims[0] : ctx->dims[1]) > 16) return cales_fail(ctx, CALES_ERR_INVALID, "transpose: at most 16 ranks per row/column supported");
+  if (cales_transpose_plan(ctx->ng, ctx->dims, ctx->rank, which, &P, peers, sendbox, recvbox, A, B)) return cales_fail(ctx, CALES_ERR_INVALID, "transpose plan failed");
+  const int me = colcomm ? ctx->coord[0] : ctx->coord[1];
+  const int axB = which == 0 ? 2 : which == 1 ? 3 : which == 2 ? 2 : 1;
+  const int be = which == 0 ? 1 : which == 1 ? 2 : which == 2 ? 1 : 0;
+  std::vector<int> bst(P), ben(P), bsz(P);
+  cales_distribute(ctx->ng[be], P, bst.data(), ben.data(), bsz.data());
+  SegList L; L.n = P;
+  const long As1 = A[0], As2 = (long)A[0] * A[1];
+  for (int q = 0; q < P; ++q) {
+    const int* sb = sendbox + 6 * q;
+    int lo[3], hi[3], Bq[3];
+    cales_pencil(ctx->ng, ctx->dims, peers[q], axB, lo, hi, Bq);          // shape of the destination pencil on rank q
+    Seg& g = L.s[q];
+    g.b0 = sb[3]; g.b1 = sb[4]; g.b2 = sb[5];
+    g.soff = sb[0] + sb[1] * As1 + sb[2] * As2; g.ss1 = As1; g.ss2 = As2;
+    int off[3] = {0, 0, 0};
+    off[be] = bst[me] - 1;                                               // my slab of the re-assembled direction
+    g.ds1 = Bq[0]; g.ds2 = (long)Bq[0] * Bq[1];
+    g.doff = off[0] + off[1] * g.ds1 + off[2] * g.ds2;
+    g.dptr = (double*)dst->ptr[peers[q]];
+  }
+  int rc;
+  if ((rc = boxcopy(ctx, src, nullptr, L))) return rc;
+  return k_barrier(ctx);
 }
 
 extern "C" int cales_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {

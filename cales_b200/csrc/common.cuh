@@ -33,6 +33,13 @@ struct FftTables {   // twiddle tables per transform length, device resident
   double2* h = nullptr;   // exp(-  pi i k / (2 n)),  k = 0..n-1   (Makhoul DCT twiddles)
 };
 
+#define CALES_MAX_RANKS 64
+struct PeerBuf {              // a buffer every rank allocated and mapped into every other rank (CUDA IPC over NVLink)
+  void* local = nullptr;
+  void* ptr[CALES_MAX_RANKS] = {nullptr};   // indexed by global rank; ptr[rank] == local
+  size_t bytes = 0;
+};
+
 struct cales_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -46,6 +53,9 @@ struct cales_ctx {
   // comms (comm.cu)
   void* nccl = nullptr;                 // ncclComm_t
   cudaStream_t comm_stream = nullptr;
+  std::map<std::string, PeerBuf> peerbufs;
+  int p2p = -1;                         // -1 untested, 0 unavailable (NCCL send/recv transposes), 1 peer memory mapped
+  double* bar = nullptr;                // barrier token
   // scratch owned by the callee (the reference's `save`d allocatables and module buffers)
   std::map<std::string, std::pair<void*, size_t>> scratch;
   double* red = nullptr;                // device reduction slots
@@ -104,5 +114,7 @@ int k_boundp(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_boun
 int k_boundp_multi(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_bound* bcp, const int nb[6],
                    const int is_bound[6], const double dl[3], const double* dzc, double* const* ps, int np);
 int k_allreduce_sum(cales_ctx* ctx, double* dev, int count);
+PeerBuf* k_peer_buffer(cales_ctx* ctx, const char* name, size_t bytes);   // collective; nullptr if peer mapping is unavailable
+int k_barrier(cales_ctx* ctx);                                              // stream-ordered barrier over all ranks
 int k_allreduce_minmax(cales_ctx* ctx, double* dev, int count, int is_max);
 FftTables* k_tables(cales_ctx* ctx, int n);

@@ -146,7 +146,7 @@ extern "C" int cales_finalize(cales_ctx* ctx) {
   k_gaussel_tab_free(ctx);
   for (auto& kv : ctx->scratch) cudaFree(kv.second.first);
   for (auto& kv : ctx->tables) { cudaFree(kv.second.w); cudaFree(kv.second.h); }
-  cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->fdev);
+  cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->fdev); cudaFree(ctx->bar);
   delete ctx;
   return CALES_OK;
 }

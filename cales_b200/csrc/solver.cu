@@ -16,6 +16,7 @@
 int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
                const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale);
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
+int k_transpose_p2p(cales_ctx* ctx, int which, const double* src, PeerBuf* dst);
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
                   const double* lambdaxy, double* p);
 
@@ -362,14 +363,31 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   const int* xs = ctx->xsz; const int* ys = ctx->ysz; const int* zs = ctx->zsz;
   const size_t bx = (size_t)xs[0] * xs[1] * xs[2], by = (size_t)ys[0] * ys[1] * ys[2], bz = (size_t)zs[0] * zs[1] * zs[2];
   size_t bmax = bx > by ? bx : by; bmax = bmax > bz ? bmax : bz;
-  double* w0 = (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
-  double* w1 = (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
+  // the largest pencil over ALL ranks bounds the peer buffers (uneven splits)
+  {
+    size_t m = 0;
+    for (int r = 0; r < ctx->nranks; ++r)
+      for (int ax = 1; ax <= 3; ++ax) {
+        int lo[3], hi[3], sz[3];
+        cales_pencil(ctx->ng, ctx->dims, r, ax, lo, hi, sz);
+        const size_t v = (size_t)sz[0] * sz[1] * sz[2];
+        if (v > m) m = v;
+      }
+    bmax = m;
+  }
+  PeerBuf* pb0 = k_peer_buffer(ctx, "solver_wk", bmax * sizeof(double));
+  PeerBuf* pb1 = pb0 ? k_peer_buffer(ctx, "solver_wk1", bmax * sizeof(double)) : nullptr;
+  const bool p2p = pb0 && pb1;
+  double* w0 = p2p ? (double*)pb0->local : (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
+  double* w1 = p2p ? (double*)pb1->local : (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
   if (!w0 || !w1) return CALES_ERR_NOMEM;
   double *cur = w0, *oth = w1, *t_;
-#define TRANSPOSE(which, P)                                      \
-  if ((P) > 1) {                                                 \
-    if ((rc = k_transpose(ctx, which, cur, oth))) return rc;     \
-    t_ = cur; cur = oth; oth = t_;                               \
+  PeerBuf *pcur = pb0, *poth = pb1, *pt_;
+#define TRANSPOSE(which, P)                                                                       \
+  if ((P) > 1) {                                                                                  \
+    if ((rc = p2p ? k_transpose_p2p(ctx, which, cur, poth) : k_transpose(ctx, which, cur, oth))) return rc; \
+    t_ = cur; cur = oth; oth = t_;                                                                \
+    pt_ = pcur; pcur = poth; poth = pt_;                                                          \
   }
   if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, cur, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
   TRANSPOSE(0, ctx->dims[0])                                                            // x -> y
