@@ -5,6 +5,9 @@
 // Ghost-fill ORDER is semantics (whole-plane array syntax incl. ghost rows, x then y then z, after
 // all halo exchanges): one launch per direction fills both faces of every field of the call, so a
 // bounduvw is 3 halo rounds + 3 fills (+ wall model) instead of ~20 tiny launches.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 #define MAXT 12
@@ -84,6 +87,151 @@ static void add_task(BcBatch& b, double* p, const double* bc, char ctype, int ib
 }
 
 static const double* plane_of(const cales_bound* b, int idir) { return idir == 0 ? b->x : idir == 1 ? b->y : b->z; }
+
+// ---- fused ghost fill ------------------------------------------------------------------------------------------
+// The reference fills ghosts by a fixed SEQUENCE of whole-plane operations (periodic self-copies of the halo phase in
+// y, z, then set_bc in x, y, z; bound.f90:42-100,175-199), each of which reads cells the previous ones wrote -- that is
+// how edges and corners get their values.  Every operation maps a ghost index of ONE direction to an interior index of
+// that direction (copy / 2 bc - p / -+dr bc + p / constant bc), so the final value of any shell cell is the original
+// value of one interior cell pushed through at most three such maps, applied in sequence order.  One launch evaluates
+// that chain for every shell cell of every field: same arithmetic, same order, bit-identical -- instead of one launch
+// per direction and phase.  (Not expressible this way: the face-centred Neumann top face, which reads a cell its own
+// operation overwrites; the host keeps the per-direction launches for it.)
+#define FG_MAXF 8
+enum { FG_NONE = 0, FG_P = 1, FG_DC = 2, FG_DF = 3, FG_NC = 4, FG_NF = 5 };
+struct FgRule { signed char kind[2]; int dri[2]; const double* bc; const double* drp; double drv; };
+struct FgStep { int dir; FgRule r[FG_MAXF]; };
+struct FgArgs { int ns, nf; double* p[FG_MAXF]; FgStep s[6]; };
+
+__device__ __forceinline__ bool fg_eval(const FgArgs& A, const Dims& d, int f, int i, int j, int k, double& out) {
+  int idx[3] = {i, j, k};
+  const int nn[3] = {d.n1, d.n2, d.n3};
+  int nops = 0, opk[3];
+  double opc[3];
+  bool konst = false;
+  double cval = 0.;
+  for (int s = A.ns - 1; s >= 0; --s) {
+    const int dir = A.s[s].dir;
+    const FgRule& R = A.s[s].r[f];
+    const int q = idx[dir], n = nn[dir];
+    int ib;
+    if (q == 0) ib = 0; else if (q == n + 1 || q == n) ib = 1; else continue;
+    const int kind = R.kind[ib];
+    if (kind == FG_NONE || (q == n && kind != FG_DF)) continue;
+    if (kind == FG_P) { idx[dir] = q == 0 ? n : 1; continue; }              // plain copy: no arithmetic
+    if (kind == FG_DF && q == n + 1) { idx[dir] = n - 1; continue; }        // P(n+1) = P(n-1)
+    const int a = dir == 0 ? idx[1] : idx[0], c = dir == 2 ? idx[1] : idx[2];
+    const int m1 = dir == 0 ? d.n2 + 2 : d.n1 + 2, m2 = dir == 2 ? d.n2 + 2 : d.n3 + 2;
+    const double bcv = R.bc[a + (long)m1 * (c + (long)m2 * ib)];
+    if (kind == FG_DF) { konst = true; cval = bcv; break; }                 // P(0) = bc, P(n) = bc
+    const double dr = R.drp ? R.drp[R.dri[ib]] : R.drv;
+    opk[nops] = kind;
+    opc[nops] = kind == FG_DC ? 2. * bcv : (ib == 0 ? -dr * bcv : dr * bcv);
+    ++nops;
+    idx[dir] = ib == 0 ? 1 : n;
+  }
+  if (!konst && nops == 0 && idx[0] == i && idx[1] == j && idx[2] == k) return false;   // nothing writes this cell
+  double v = konst ? cval : A.p[f][d.idx(idx[0], idx[1], idx[2])];
+  for (int o = nops - 1; o >= 0; --o) v = opk[o] == FG_DC ? opc[o] + (-1.) * v : opc[o] + v;
+  out = v;
+  return true;
+}
+
+// slab 2: k in {0, n3, n3+1}, all (i,j); slab 1: j in {0, n2, n2+1}, k in 1..n3-1, all i; slab 0: i in {0, n1, n1+1},
+// j in 1..n2-1, k in 1..n3-1: every shell cell exactly once.
+__global__ void __launch_bounds__(256) fused_fill_k(Dims d, FgArgs A) {
+  const long t = blockIdx.x * 256L + threadIdx.x;
+  const int slab = blockIdx.y;
+  int i, j, k;
+  if (slab == 2) {
+    if (t >= 3 * d.s2) return;
+    const int kq = (int)(t / d.s2); const long r = t - kq * d.s2;
+    j = (int)(r / d.s1); i = (int)(r - j * d.s1);
+    k = kq == 0 ? 0 : d.n3 - 1 + kq;
+  } else if (slab == 1) {
+    const long per = (long)d.s1 * 3;
+    if (t >= per * (d.n3 - 1)) return;
+    const int kk = (int)(t / per); const long r = t - kk * per;
+    const int jq = (int)(r / d.s1); i = (int)(r - jq * d.s1);
+    j = jq == 0 ? 0 : d.n2 - 1 + jq; k = kk + 1;
+  } else {
+    const long per = 3L * (d.n2 - 1);
+    if (t >= per * (d.n3 - 1)) return;
+    const int kk = (int)(t / per); const long r = t - kk * per;
+    const int jj = (int)(r / 3); const int iq = (int)(r - jj * 3);
+    i = iq == 0 ? 0 : d.n1 - 1 + iq; j = jj + 1; k = kk + 1;
+  }
+  const long c = d.idx(i, j, k);
+  for (int f = 0; f < A.nf; ++f) {
+    double v;
+    if (fg_eval(A, d, f, i, j, k, v)) A.p[f][c] = v;
+  }
+}
+
+// Ghost fill of `nf` fields: halo phase (exchange with real neighbours, periodic self-copies) followed by the set_bc
+// batches of the three directions.  Everything after the last direction that needs communication is one launch.
+static int run_batch(cales_ctx* ctx, const Dims& d, BcBatch& b);
+static int ghost_fill(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nf, BcBatch* batches /*[3]*/) {
+  Dims d(n);
+  int rc;
+  static const bool nofuse = getenv("CALES_NO_FUSED_FILL") != nullptr;
+  int self_mask = 0, comm_mask = 0, last_comm = -1;
+  for (int idir = 0; idir < 3; ++idir) {
+    if (idir + 1 == ctx->ipencil) continue;
+    const int nb0 = nb[tb(0, idir)], nb1 = nb[tb(1, idir)];
+    if (nb0 < 0 && nb1 < 0) continue;
+    if (nb0 == ctx->rank && nb1 == ctx->rank) self_mask |= 1 << idir;
+    else { comm_mask |= 1 << idir; last_comm = idir; }
+  }
+  bool ok = !nofuse && nf <= FG_MAXF && n[0] >= 2 && n[1] >= 2 && n[2] >= 2;
+  for (int b = 0; b < 3 && ok; ++b)
+    for (int q = 0; q < batches[b].nt; ++q) {
+      const BcTask& t = batches[b].t[q];
+      if (t.ctype == 'N' && !t.centered && t.ibound == 1) ok = false;
+      bool known = false;
+      for (int f = 0; f < nf; ++f) known |= fields[f] == t.p;
+      if (!known) ok = false;
+    }
+  if (!ok) {
+    if ((rc = k_halo_exchange(ctx, n, nb, fields, nf))) return rc;
+    for (int b = 0; b < 3; ++b) if ((rc = run_batch(ctx, d, batches[b]))) return rc;
+    return CALES_OK;
+  }
+  // halo phase up to and including the last communicating direction: as before
+  int early = 0;
+  for (int idir = 0; idir <= last_comm; ++idir) early |= 1 << idir;
+  if (early && (rc = k_halo_exchange_dirs(ctx, n, nb, fields, nf, early))) return rc;
+  FgArgs A;
+  memset(&A, 0, sizeof A);
+  A.nf = nf;
+  for (int f = 0; f < nf; ++f) A.p[f] = fields[f];
+  for (int idir = last_comm + 1; idir < 3; ++idir)
+    if (self_mask & (1 << idir)) {
+      FgStep& S = A.s[A.ns++];
+      S.dir = idir;
+      for (int f = 0; f < nf; ++f) S.r[f].kind[0] = S.r[f].kind[1] = FG_P;
+    }
+  for (int b = 0; b < 3; ++b) {
+    if (batches[b].nt == 0) continue;
+    FgStep& S = A.s[A.ns++];
+    S.dir = batches[b].idir;
+    for (int q = 0; q < batches[b].nt; ++q) {
+      const BcTask& t = batches[b].t[q];
+      int f = 0;
+      while (fields[f] != t.p) ++f;
+      FgRule& R = S.r[f];
+      R.bc = t.bc; R.drp = t.drp; R.drv = t.drv;
+      if (t.ctype == 'P') { R.kind[0] = R.kind[1] = FG_P; continue; }
+      R.kind[t.ibound] = t.ctype == 'D' ? (t.centered ? FG_DC : FG_DF) : (t.centered ? FG_NC : FG_NF);
+      R.dri[t.ibound] = t.dri;
+    }
+  }
+  if (A.ns == 0) return CALES_OK;
+  const long cnt = std::max(std::max(3 * d.s2, 3L * d.s1 * (n[2] - 1)), 3L * (n[1] - 1) * (n[2] - 1));
+  fused_fill_k<<<dim3(cdiv(cnt, 256), 3), 256, 0, ctx->stream>>>(d, A);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
 
 // ---- wall model (wmodel.f90) --------------------------------------------------------------------------------
 struct WmFace {
@@ -236,11 +384,11 @@ extern "C" int cales_bounduvw(cales_ctx* ctx, const char cbc[18], const int n[3]
   double* vel[3] = {u, v, w};
   const cales_bound* bcs[3] = {bcu, bcv, bcw};
   const cales_bound* mags[3] = {bcu_mag, bcv_mag, bcw_mag};
-  int rc = k_halo_exchange(ctx, n, nb, vel, 3);             // bound.f90:42-52
-  if (rc) return rc;
+  int rc;
+  BcBatch bb[3];
 #define CBC(ib, idir, ivel) cbc[(ib) + 2 * (idir) + 6 * (ivel)]
   for (int idir = 0; idir < 3; ++idir) {                    // bound.f90:56-100
-    BcBatch b; b.idir = idir; b.nt = 0;
+    BcBatch& b = bb[idir]; b.idir = idir; b.nt = 0;
     const bool impose_norm_bc = (!is_correc) || (CBC(0, idir, idir) == 'P' && CBC(1, idir, idir) == 'P');
     for (int ib = 0; ib < 2; ++ib) {
       if (!is_bound[tb(ib, idir)]) continue;
@@ -251,8 +399,8 @@ extern "C" int cales_bounduvw(cales_ctx* ctx, const char cbc[18], const int n[3]
         for (int c = 0; c < 3; ++c)
           if (c != idir) add_task(b, vel[c], plane_of(bcs[c], idir), CBC(ib, idir, c), ib, 1, dl[idir < 2 ? idir : 0], idir == 2 ? dzc : nullptr, kk);
     }
-    if ((rc = run_batch(ctx, d, b))) return rc;
   }
+  if ((rc = ghost_fill(ctx, n, nb, vel, 3, bb))) return rc;   // halo exchange (bound.f90:42-52) + the three set_bc rounds
   bool any_wm = false;
   for (int q = 0; q < 6; ++q) any_wm |= (is_bound[q] && lwm[q] != 0);
   if (!any_wm) return CALES_OK;
@@ -292,8 +440,19 @@ extern "C" int cales_bounduvw(cales_ctx* ctx, const char cbc[18], const int n[3]
 int k_boundp_multi(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_bound* bcp, const int nb[6],
                    const int is_bound[6], const double dl[3], const double* dzc, double* const* ps, int np) {
   Dims d(n);
-  int rc = k_halo_exchange(ctx, n, nb, ps, np);             // bound.f90:175-180
-  if (rc) return rc;
+  int rc;
+  if (np <= MAXT / 2) {
+    BcBatch bb[3];
+    for (int idir = 0; idir < 3; ++idir) {                  // bound.f90:181-199
+      BcBatch& b = bb[idir]; b.idir = idir; b.nt = 0;
+      for (int f = 0; f < np; ++f)
+        for (int ib = 0; ib < 2; ++ib)
+          if (is_bound[tb(ib, idir)])
+            add_task(b, ps[f], plane_of(bcp, idir), cbc[tb(ib, idir)], ib, 1, dl[idir < 2 ? idir : 0], idir == 2 ? dzc : nullptr, ib == 0 ? 0 : n[2]);
+    }
+    return ghost_fill(ctx, n, nb, ps, np, bb);
+  }
+  if ((rc = k_halo_exchange(ctx, n, nb, ps, np))) return rc;             // bound.f90:175-180
   for (int idir = 0; idir < 3; ++idir) {                    // bound.f90:181-199
     for (int f0 = 0; f0 < np; f0 += MAXT / 2) {
       BcBatch b; b.idir = idir; b.nt = 0;

@@ -212,7 +212,13 @@ __global__ void __launch_bounds__(256) halo_unpack_k(Dims d, int idir, FieldList
   if (has_hi) p[face_idx(d, idir, n + 1, a, c)] = buf[(fl.nf + f) * m + a + (long)m1 * c];
 }
 
+int k_halo_exchange_dirs(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields, int dirmask);
+
 int k_halo_exchange(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields) {
+  return k_halo_exchange_dirs(ctx, n, nb, fields, nfields, 7);
+}
+
+int k_halo_exchange_dirs(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields, int dirmask) {
   Dims d(n);
   for (int f0 = 0; f0 < nfields; f0 += 12) {
     FieldList fl;
@@ -220,6 +226,7 @@ int k_halo_exchange(cales_ctx* ctx, const int n[3], const int nb[6], double* con
     for (int f = 0; f < fl.nf; ++f) fl.p[f] = fields[f0 + f];
     for (int idir = 0; idir < 3; ++idir) {
       if (idir + 1 == ctx->ipencil) continue;                 // bound.f90:634
+      if (!(dirmask & (1 << idir))) continue;
       const int nb0 = nb[tb(0, idir)], nb1 = nb[tb(1, idir)];
       if (nb0 < 0 && nb1 < 0) continue;
       const int m1 = idir == 0 ? n[1] + 2 : n[0] + 2, m2 = idir == 2 ? n[1] + 2 : n[2] + 2;

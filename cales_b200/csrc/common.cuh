@@ -109,6 +109,7 @@ __host__ __device__ inline int tb(int ib, int idir) { return ib + 2 * idir; }
 
 // internal device-level entry points shared between translation units (no host sync)
 int k_halo_exchange(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields);
+int k_halo_exchange_dirs(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields, int dirmask);
 int k_boundp(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_bound* bcp, const int nb[6],
              const int is_bound[6], const double dl[3], const double* dzc, double* p);
 int k_boundp_multi(cales_ctx* ctx, const char cbc[6], const int n[3], const cales_bound* bcp, const int nb[6],
