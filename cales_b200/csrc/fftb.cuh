@@ -25,6 +25,12 @@ struct FftBArgs {
   int nl1, nl2, dd;        // lines along l1 / l2; dd: DST flavour of the Makhoul family
   double scale;
   const double2 *wm, *wn, *h4;
+  // peer-fused y -> z transpose (forward y-lines only): the spectral line is scattered straight into the Z-pencils of
+  // the ranks owning each slab of ky (local or over NVLink); element (x, ky, z) of rank r lives at
+  // pbase[r] + x + nx (ky - pys[r]) + nx pny[r] (zoff + z_local)
+  int np, zoff, nx;
+  double* pbase[8];
+  int pys[9], pny[8];
 };
 
 #define NLB 16
@@ -136,7 +142,7 @@ template <int MK> __device__ __forceinline__ int slot_of(int e, int n) {       /
 // forward stage, forward post-stage, backward pre-stage, last backward stage).  For y-lines the two coincide (the NL
 // lines are NL consecutive x, so lanes across lines ARE coalesced); for x-lines lanes run along the line (tx fastest)
 // so that global accesses are coalesced, and the shared buffer is XOR-swizzled so that both mappings are conflict-free.
-template <int M, int E, int XD, bool INV, int MK>
+template <int M, int E, int XD, bool INV, int MK, bool PEER = false>
 __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
   using namespace fb;
   extern __shared__ double2 S[];
@@ -157,6 +163,9 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
   int pos[E];
 
   for (int q = tid; q < M; q += NT) sw[q] = __ldg(A.wm + q);
+  double** sbase = (double**)(sw + M);        // PEER: per-rank row bases for this CTA's (x-tile, z)
+  if (PEER && tid < A.np)
+    sbase[tid] = A.pbase[tid] + L0 + (long)A.nx * A.pny[tid] * (A.zoff + (int)blockIdx.y) - (long)A.nx * A.pys[tid];
 
   if (!INV) {
     // ---- forward: first-stage operands straight from global memory
@@ -267,8 +276,20 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
         else { i0 = n - 1 - k; i1 = k > 0 ? k - 1 : -1; i2 = n - 1 - mk; i3 = mk - 1; }
       }
       if (on) {
-        go[(long)i0 * oes] = r0 * A.scale; if (i1 >= 0) go[(long)i1 * oes] = r1 * A.scale;
-        go[(long)i2 * oes] = r2 * A.scale; if (i3 >= 0) go[(long)i3 * oes] = r3 * A.scale;
+        if (PEER) {
+#define FB_PUT(iq_, rq_)                                                          \
+  {                                                                               \
+    int rr = 0;                                                                   \
+    for (int q = 1; q < A.np; ++q) rr += (iq_) >= A.pys[q];                        \
+    sbase[rr][lx + (long)A.nx * (iq_)] = (rq_) * A.scale;                          \
+  }
+          FB_PUT(i0, r0) if (i1 >= 0) FB_PUT(i1, r1)
+          FB_PUT(i2, r2) if (i3 >= 0) FB_PUT(i3, r3)
+#undef FB_PUT
+        } else {
+          go[(long)i0 * oes] = r0 * A.scale; if (i1 >= 0) go[(long)i1 * oes] = r1 * A.scale;
+          go[(long)i2 * oes] = r2 * A.scale; if (i3 >= 0) go[(long)i3 * oes] = r3 * A.scale;
+        }
       }
     }
   } else if (on) {
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
 
 template <int M, int E, int XD>
 static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int backward) {
-  const size_t sh = ((size_t)M * NLB + M) * sizeof(double2);
+  const size_t sh = ((size_t)M * NLB + M) * sizeof(double2) + 8 * sizeof(double*);
   dim3 g(cdiv(A.nl1, NLB), A.nl2), b(NLB, M / E);
 #define FB_GO(INV_, MK_)                                                                                           \
   {                                                                                                                \
@@ -297,7 +318,16 @@ static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int b
     fftb_k<M, E, XD, INV_, MK_><<<g, b, sh, ctx->stream>>>(A);                                                      \
   }
   const int mk = kind != KB_PP;
-  if (!backward) { if (mk) FB_GO(false, 1) else FB_GO(false, 0) }
+  if (XD == 0 && A.np > 0 && !backward) {
+#define FB_GOP(MK_)                                                                                                \
+  {                                                                                                                \
+    static bool attr = false;                                                                                      \
+    if (!attr) { attr = true; cudaFuncSetAttribute(fftb_k<M, E, 0, false, MK_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); } \
+    fftb_k<M, E, 0, false, MK_, true><<<g, b, sh, ctx->stream>>>(A);                                                \
+  }
+    if (mk) FB_GOP(1) else FB_GOP(0)
+#undef FB_GOP
+  } else if (!backward) { if (mk) FB_GO(false, 1) else FB_GO(false, 0) }
   else { if (mk) FB_GO(true, 1) else FB_GO(true, 0) }
 #undef FB_GO
   ctx->launches++;

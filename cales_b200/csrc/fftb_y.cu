@@ -1,10 +1,17 @@
 // y-lines (strided; lanes across neighbouring x) instantiations of the register-blocked batched transforms, see fftb.cuh
+#include <cstdlib>
+
 #include "fftb.cuh"
 
 int k_fftb_x(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward);
 int k_fftb_y(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward) { return fftb_dispatch<0>(ctx, n, A, kind, backward); }
 
+bool k_fftb_supported(int n) { return n >= 32 && n <= 1024 && !(n & (n - 1)) && getenv("CALES_FFT_GENERIC") == nullptr; }
+
 // returns 1 if handled, 0 if this length is not covered by the fast path (caller falls back), <0 on error
+struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };
+const FftPeerOut* g_fft_peer_out = nullptr;    // set by the distributed solver around the forward y pass (solver.cu)
+
 int k_fftb_pass(cales_ctx* ctx, int dir, int kind, int backward, int n, int nl1, int nl2, const double* in, long ies, long il1, long il2,
                 double* out, long oes, long ol1, long ol2, double scale, const FftTables* T) {
   if (n < 32 || n > 1024 || (n & (n - 1))) return 0;
@@ -14,5 +21,12 @@ int k_fftb_pass(cales_ctx* ctx, int dir, int kind, int backward, int n, int nl1,
   A.in = in; A.out = out; A.ies = ies; A.il1 = il1; A.il2 = il2; A.oes = oes; A.ol1 = ol1; A.ol2 = ol2;
   A.nl1 = nl1; A.nl2 = nl2; A.dd = kind == KB_DD; A.scale = scale;
   A.wm = T->w; A.wn = T->w + m; A.h4 = T->h;
+  A.np = 0; A.zoff = 0; A.nx = 0;
+  if (g_fft_peer_out && dir == 1 && !backward) {
+    const FftPeerOut& P = *g_fft_peer_out;
+    A.np = P.np; A.zoff = P.zoff; A.nx = P.nx;
+    for (int q = 0; q < P.np; ++q) { A.pbase[q] = P.pbase[q]; A.pys[q] = P.pys[q]; A.pny[q] = P.pny[q]; }
+    A.pys[P.np] = P.pys[P.np];
+  }
   return dir == 0 ? k_fftb_x(ctx, n, A, kind, backward) : k_fftb_y(ctx, n, A, kind, backward);
 }

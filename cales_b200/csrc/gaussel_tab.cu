@@ -106,10 +106,15 @@ __device__ __forceinline__ void g_issue(double* dst, const double* src, long str
     if (FULL || q < nvalid) cp8(dst + q * GC, src + q * stride);
 }
 
-template <int PER, bool SP, int GNG>
+// Peer-fused z -> y transpose: the solution of level l (global z) of my columns goes straight into the Y-pencil of the
+// rank that owns z = l: pbase[r] + (col + coff) + plane (l - pzs[r]).
+struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };
+const GPeer* g_gauss_peer_out = nullptr;       // set by the distributed solver around the z solve (solver.cu)
+
+template <int PER, bool SP, int GNG, bool PEER>
 __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, long sz, const double* __restrict__ a, const double* __restrict__ c,
                                                      const double* __restrict__ Z, const double* __restrict__ P2, const double* __restrict__ DEN,
-                                                     double* __restrict__ p) {
+                                                     double* __restrict__ p, GPeer G) {
   extern __shared__ double sh[];
   constexpr int GD = GU * GNG;
   const int nlev = PER ? n - 1 : n;
@@ -125,6 +130,15 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
   if (col >= nxy) return;
   double* pp = p + col;
   const double* zz = Z + col;
+  const long colo = col + G.coff;
+#define GSTORE(l_, v_)                                                                        \
+  {                                                                                           \
+    if (PEER) {                                                                               \
+      int rr_ = 0;                                                                            \
+      for (int q_ = 1; q_ < G.np; ++q_) rr_ += (l_) >= G.pzs[q_];                             \
+      G.pbase[rr_][colo + G.plane * ((l_) - G.pzs[rr_])] = (v_);                              \
+    } else pp[(long)(l_) * sz] = (v_);                                                        \
+  }
   double plast = 0., den = 1.;
   if (PER) { plast = pp[(long)(n - 1) * sz]; den = DEN[col]; }
   const int ngrp = (nlev + GU - 1) / GU, nfull = nlev / GU, ntail = nlev - nfull * GU;
@@ -214,7 +228,7 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
         for (int q = 0; q < GU; ++q) ks[-q * GC] = r[q];
       } else {
 #pragma unroll
-        for (int q = 0; q < GU; ++q) pp[(hi - q) * sz] = r[q];
+        for (int q = 0; q < GU; ++q) GSTORE(hi - q, r[q])
       }
     } else {
 #pragma unroll
@@ -224,7 +238,7 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
           const bool kept = !SP || l >= spill;
           const double d = cs[-q] * zs[q * GC];
           pl = (kept ? ks[-q * GC] : prs[q * GC]) - d * pl;
-          if (PER && kept) ks[-q * GC] = pl; else pp[l * sz] = pl;
+          if (PER && kept) ks[-q * GC] = pl; else if (PER) pp[l * sz] = pl; else GSTORE(l, pl)
         }
       }
     }
@@ -234,7 +248,7 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
   if (!PER) return;
   // ================= periodic closure (solver.f90:142-145): p(n) and p(1:n-1) = p1 + p2 p(n) ===========================
   const double pn = (plast - sc[n - 1] * pl - sa[n - 1] * p1n) / den;
-  pp[(long)(n - 1) * sz] = pn;
+  GSTORE(n - 1, pn)
   const double* p2 = P2 + col;
 #define CMB_ISSUE(g_)                                                                                        \
   {                                                                                                          \
@@ -259,11 +273,11 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
 #pragma unroll
       for (int q = 0; q < GU; ++q) r[q] = ps[q * GC] + zs[q * GC] * pn;
 #pragma unroll
-      for (int q = 0; q < GU; ++q) pp[(l0 + q) * sz] = r[q];
+      for (int q = 0; q < GU; ++q) GSTORE(l0 + q, r[q])
     } else {
 #pragma unroll
       for (int q = 0; q < GU; ++q)
-        if (q < ntail) pp[(l0 + q) * sz] = ps[q * GC] + zs[q * GC] * pn;
+        if (q < ntail) GSTORE(l0 + q, ps[q * GC] + zs[q * GC] * pn)
     }
     CMB_ISSUE(g + GNG)
   }
@@ -271,6 +285,7 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
 #undef FWD_ISSUE
 #undef BWD_ISSUE
 #undef CMB_ISSUE
+#undef GSTORE
 }
 
 static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const double* a, const double* b, const double* c, const double* lam) {
@@ -341,11 +356,20 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   if (spill > 0) { spill = std::min(nlev - nlev % GU, ((spill + GU - 1) / GU) * GU); S = nlev - spill; }   // whole groups spill
   const size_t sh = fixed + (size_t)S * GC * sizeof(double);
   const dim3 g(cdiv(nxy, GC));
+  GPeer G;
+  memset(&G, 0, sizeof G);
+  const bool peer = g_gauss_peer_out != nullptr;
+  if (peer) G = *g_gauss_peer_out;
 #define GS_GO(PER_, SP_, NG_)                                                                                         \
   {                                                                                                                   \
     static bool attr = false;                                                                                         \
-    if (!attr) { attr = true; cudaFuncSetAttribute(gauss_solve_k<PER_, SP_, NG_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); } \
-    gauss_solve_k<PER_, SP_, NG_><<<g, GC, sh, ctx->stream>>>(nxy, n, spill, sz, a, c, t->Z, t->P2, t->DEN, p);      \
+    if (!attr) {                                                                                                      \
+      attr = true;                                                                                                    \
+      cudaFuncSetAttribute(gauss_solve_k<PER_, SP_, NG_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024); \
+      cudaFuncSetAttribute(gauss_solve_k<PER_, SP_, NG_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);  \
+    }                                                                                                                 \
+    if (peer) gauss_solve_k<PER_, SP_, NG_, true><<<g, GC, sh, ctx->stream>>>(nxy, n, spill, sz, a, c, t->Z, t->P2, t->DEN, p, G);   \
+    else gauss_solve_k<PER_, SP_, NG_, false><<<g, GC, sh, ctx->stream>>>(nxy, n, spill, sz, a, c, t->Z, t->P2, t->DEN, p, G);       \
   }
 #define GS_NG(NG_)                                                                   \
   {                                                                                  \

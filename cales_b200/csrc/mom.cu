@@ -382,6 +382,7 @@ extern "C" int cales_rk(cales_ctx* ctx, const double rkpar[2], const int n[3], c
   CHECK_CTX(ctx);
   int rc = k_rk_dev(ctx, rkpar, n, dli, dzci, dzfi, grid_vol_ratio_c, grid_vol_ratio_f, visc, dt, p, is_forced, velf, bforce, visct, u, v, w);
   if (rc) return rc;
+  if (!f) return CALES_OK;                             // f(3) stays on the device: no synchronisation (see cales_bulk_forcing)
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->red_host + 8, ctx->fdev, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
   for (int c = 0; c < 3; ++c) f[c] = ctx->red_host[8 + c];

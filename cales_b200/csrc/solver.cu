@@ -17,6 +17,11 @@ int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backw
                const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale);
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 int k_transpose_p2p(cales_ctx* ctx, int which, const double* src, PeerBuf* dst);
+struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };
+extern const FftPeerOut* g_fft_peer_out;
+struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };
+extern const GPeer* g_gauss_peer_out;
+bool k_fftb_supported(int n);
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
                   const double* lambdaxy, double* p);
 
@@ -226,6 +231,7 @@ int k_gaussel(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, cons
       if (rc == 1) return CALES_OK;
     }
   }
+  if (g_gauss_peer_out) return cales_fail(ctx, CALES_ERR_INVALID, "peer-fused z solve requested but the cached-pivot kernel is unavailable");
   const int ntile = ((periodic ? n - 1 : n) + TZ - 1) / TZ;
   const size_t sh = ((size_t)ntile * GT * (periodic ? 2 : 1) + (size_t)n * (periodic ? 4 : 3)) * sizeof(double);
   if (sh > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "tridiagonal system of %d points exceeds the checkpoint buffer", n);
@@ -381,6 +387,51 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   double* w0 = p2p ? (double*)pb0->local : (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
   double* w1 = p2p ? (double*)pb1->local : (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
   if (!w0 || !w1) return CALES_ERR_NOMEM;
+  // ---- peer-fused path (process grid 1 x P: x->y is the identity): the forward y pass scatters its spectrum straight
+  // into the Z-pencils of the owning ranks and the z solve scatters its solution straight into their Y-pencils, so the
+  // two transposes cost no pass over memory at all -- only the NVLink stores inside the producing kernels and one
+  // stream-ordered barrier each.
+  static const bool nofuse = getenv("CALES_NO_FUSED_TRANSPOSE") != nullptr;
+  if (p2p && !nofuse && ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fftb_supported(ys[1])) {
+    const int P = ctx->dims[1], me = ctx->coord[1];
+    std::vector<int> yst(P), yen(P), ysz(P), zst(P), zen(P), zsz(P);
+    cales_distribute(ctx->ng[1], P, yst.data(), yen.data(), ysz.data());
+    cales_distribute(ctx->ng[2], P, zst.data(), zen.data(), zsz.data());
+    FftPeerOut FP; GPeer GP;
+    FP.np = GP.np = P; FP.nx = ys[0]; FP.zoff = zst[me] - 1;
+    GP.plane = (long)ys[0] * ys[1]; GP.coff = (long)ys[0] * (yst[me] - 1);
+    for (int q = 0; q < P; ++q) {
+      const int r = ctx->coord[0] * ctx->dims[1] + q;
+      FP.pbase[q] = (double*)pb1->ptr[r]; FP.pys[q] = yst[q] - 1; FP.pny[q] = ysz[q];
+      GP.pbase[q] = (double*)pb0->ptr[r]; GP.pzs[q] = zst[q] - 1;
+    }
+    FP.pys[P] = ctx->ng[1]; GP.pzs[P] = ctx->ng[2];
+    if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, w0, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+    static const int fmask = getenv("CALES_FUSE_MASK") ? atoi(getenv("CALES_FUSE_MASK")) : 1;   // bit 0: forward y pass pushes, bit 1: z solve pushes (slower: its few warps stall on NVLink stores)
+    if (fmask & 1) {
+      g_fft_peer_out = &FP;
+      rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0);
+      g_fft_peer_out = nullptr;
+      if (rc) return rc;
+      if ((rc = k_barrier(ctx))) return rc;
+    } else {
+      if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w0, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
+      if ((rc = k_transpose_p2p(ctx, 1, w0, pb1))) return rc;
+    }
+    if (fmask & 2) {
+      g_gauss_peer_out = &GP;
+      rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w1);
+      g_gauss_peer_out = nullptr;
+      if (rc) return rc;
+      if ((rc = k_barrier(ctx))) return rc;
+    } else {
+      if ((rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w1))) return rc;
+      if ((rc = k_transpose_p2p(ctx, 2, w1, pb0))) return rc;
+    }
+    if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w0, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
+    if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, xs[0], xs[1], xs[2], w0, xs[0], (long)xs[0] * xs[1], p + d.idx(1, 1, 1), d.s1, d.s2, normfft))) return rc;
+    return CALES_OK;
+  }
   double *cur = w0, *oth = w1, *t_;
   PeerBuf *pcur = pb0, *poth = pb1, *pt_;
 #define TRANSPOSE(which, P)                                                                       \

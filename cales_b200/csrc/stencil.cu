@@ -163,6 +163,8 @@ int k_bulk_forcing_dev(cales_ctx* ctx, const int n[3], const int is_forced[3], c
 extern "C" int cales_bulk_forcing(cales_ctx* ctx, const int n[3], const int is_forced[3], const double f[3], double* u,
                                   double* v, double* w) {
   CHECK_CTX(ctx);
+  // f == NULL: use the device-resident f(3) left by the last cales_rk (no host round trip)
+  if (!f) return k_bulk_forcing_dev(ctx, n, is_forced, ctx->fdev, u, v, w);
   double* tmp = (double*)cales_scratch(ctx, "bulkf_arg", 3 * sizeof(double));
   if (!tmp) return CALES_ERR_NOMEM;
   CUDA_TRY(ctx, cudaMemcpyAsync(tmp, f, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));

@@ -93,6 +93,7 @@ class Simulation:
         for nm in ("u", "v", "w", "p", "pp", "visct"):
             self.fields[nm] = torch.zeros(self.ncell, dtype=torch.float64, device=self.device)
         self.f = np.zeros(3)
+        self.want_f = False
         self.dt = self.dti = self.dt_cfl = 0.0
 
     # ---- helpers -------------------------------------------------------------------------------------------
@@ -168,18 +169,19 @@ class Simulation:
                                            None if skip_xy else rhsb["x"].data_ptr(), None if skip_xy else rhsb["y"].data_ptr(),
                                            rhsb["z"].data_ptr(), self.ptr(name)))
 
-    def rk(self, irk):
+    def rk(self, irk, want_f=True):
+        """want_f=False leaves f(3) on the device (no host synchronisation); bulk_forcing(None) then consumes it there."""
         d, D = self.deck, self.d
         f = np.zeros(3)
         self.chk(self.lib.cales_rk(self.ctx, L._da(rkcoeff[irk]), L._ia(self.n), L._da(d.dli), D["dzci"].data_ptr(), D["dzfi"].data_ptr(),
                                    D["gvr_c"].data_ptr(), D["gvr_f"].data_ptr(), d.visc, self.dt, self.ptr("p"),
                                    L._ia(np.array(d.is_forced, dtype=np.int32)), L._da(d.velf), L._da(d.bforce), self.ptr("visct"),
-                                   self.ptr("u"), self.ptr("v"), self.ptr("w"), f.ctypes.data_as(L.c_dbl_p)))
-        return f
+                                   self.ptr("u"), self.ptr("v"), self.ptr("w"), f.ctypes.data_as(L.c_dbl_p) if want_f else None))
+        return f if want_f else None
 
     def bulk_forcing(self, f):
-        self.chk(self.lib.cales_bulk_forcing(self.ctx, L._ia(self.n), L._ia(np.array(self.deck.is_forced, dtype=np.int32)), L._da(f),
-                                             self.ptr("u"), self.ptr("v"), self.ptr("w")))
+        self.chk(self.lib.cales_bulk_forcing(self.ctx, L._ia(self.n), L._ia(np.array(self.deck.is_forced, dtype=np.int32)),
+                                             L._da(f) if f is not None else None, self.ptr("u"), self.ptr("v"), self.ptr("w")))
 
     def fillps(self, dti):
         self.chk(self.lib.cales_fillps(self.ctx, L._ia(self.n), L._da(self.deck.dli), self.d["dzfi"].data_ptr(), dti,
@@ -232,9 +234,9 @@ class Simulation:
         d = self.deck
         dtrk = (rkcoeff[irk][0] + rkcoeff[irk][1]) * self.dt
         dtrki = dtrk ** (-1)
-        f = self.rk(irk)
-        self.f = f
-        self.bulk_forcing(f)
+        # f(3) stays on the device inside the time loop (the reference reads it back only for its log, main.f90:559-565)
+        self.f = self.rk(irk, want_f=self.want_f)
+        self.bulk_forcing(self.f)
         if d.impdiff:                                          # main.f90:423-491
             alpha = -.5 * d.visc * dtrk
             self.alpha = alpha

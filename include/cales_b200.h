@@ -114,7 +114,8 @@ int cales_solver_gaussel_z(cales_ctx* ctx, const int n[3], const double* a, cons
 /* ---- momentum / RK ---------------------------------------------------------------------------------
  * replaces rk (src/rk.f90:17-121) incl. mom_xyz_ad (src/mom.f90:17-309) and cmpt_bulk_forcing
  * (src/rk.f90:197-222).  The callee owns the RK history (the `save`d arrays, rk.f90:36-72).
- * f(3) is returned on the host (stream synchronised, as bulk_mean does, src/utils.f90:34-46). */
+ * f(3) is returned on the host (stream synchronised, as bulk_mean does, src/utils.f90:34-46); pass f = NULL to keep
+ * it on the device only (no synchronisation) and hand NULL to cales_bulk_forcing, which then reads it there. */
 int cales_rk(cales_ctx* ctx, const double rkpar[2], const int n[3], const double dli[3], const double* dzci,
              const double* dzfi, const double* grid_vol_ratio_c, const double* grid_vol_ratio_f, double visc,
              double dt, const double* p, const int is_forced[3], const double velf[3], const double bforce[3],
