@@ -21,7 +21,7 @@ struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };
 extern const FftPeerOut* g_fft_peer_out;
 struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };
 extern const GPeer* g_gauss_peer_out;
-bool k_fftb_supported(int n);
+bool k_fft_peer_capable(const char bc[2], char c_or_f, int n);
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
                   const double* lambdaxy, double* p);
 
@@ -392,7 +392,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   // two transposes cost no pass over memory at all -- only the NVLink stores inside the producing kernels and one
   // stream-ordered barrier each.
   static const bool nofuse = getenv("CALES_NO_FUSED_TRANSPOSE") != nullptr;
-  if (p2p && !nofuse && ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fftb_supported(ys[1])) {
+  if (p2p && !nofuse && ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fft_peer_capable(pl.bc[1], pl.c_or_f[1], ys[1])) {
     const int P = ctx->dims[1], me = ctx->coord[1];
     std::vector<int> yst(P), yen(P), ysz(P), zst(P), zen(P), zsz(P);
     cales_distribute(ctx->ng[1], P, yst.data(), yen.data(), ysz.data());

@@ -217,27 +217,59 @@ def test_reductions(env, n):
         assert abs(out.value - ref) <= 1e-13 * np.abs(u[1:-1, 1:-1, 1:-1] * gvr[None, None, 1:-1]).sum()
 
 
-KINDS = [("PP", "R2HC", "HC2R"), ("NN", "REDFT10", "REDFT01"), ("DD", "RODFT10", "RODFT01")]
+# the ten BC/stagger combinations of find_fft (fft.f90:192-245): (bc, c_or_f, forward kind, backward kind)
+KINDS = [("PP", "c", "R2HC", "HC2R"), ("NN", "c", "REDFT10", "REDFT01"), ("DD", "c", "RODFT10", "RODFT01"),
+         ("ND", "c", "REDFT11", "REDFT11"), ("DN", "c", "RODFT11", "RODFT11"),
+         ("PP", "f", "R2HC", "HC2R"), ("NN", "f", "REDFT00", "REDFT00"), ("DD", "f", "RODFT00", "RODFT00"),
+         ("ND", "f", "REDFT10", "REDFT01"), ("DN", "f", "RODFT01", "RODFT10")]
 
 
-@pytest.mark.parametrize("bc,kf,kb", KINDS)
+@pytest.mark.parametrize("bc,cf,kf,kb", KINDS)
 @pytest.mark.parametrize("n", [(16, 12, 3), (64, 48, 5), (96, 30, 4), (192, 256, 2), (512, 2, 2), (1024, 6, 2), (14, 22, 3), (2, 4, 2)])
-def test_fft_lines_vs_fftw_definitions(env, bc, kf, kb, n):
+def test_fft_lines_vs_fftw_definitions(env, bc, cf, kf, kb, n):
     """Each transform kind, both directions, forward and backward, against the FFTW r2r definitions
-    (scipy/pocketfft).  Tolerance: 2e-15 * log2(n) relative to max|result| (FFT round-off)."""
+    (scipy/pocketfft).  Face-centred DD transforms n-1 points and leaves the last one alone (fft.f90:66-69).
+    Tolerance: 2e-15 * log2(n) relative to max|result| (FFT round-off); the type-I kinds run a complex FFT of
+    n-1 / n points through generic-radix butterflies (n-1 = 3.5.17, 7.73, 3.11.31 ...), whose O(R) sums are
+    allowed 4x that."""
     from oracle import solver as osl
     L, lib = env
     rng = np.random.default_rng(5)
     a = np.asfortranarray(rng.standard_normal(n))
+    ix = 1 if (bc == "DD" and cf == "f") else 0
     with Ctx(L, lib, n) as c:
         for dir_ in (0, 1):
             for backward, kind in ((0, kf), (1, kb)):
-                ref = a.copy(order="F"); osl.fft(kind, n[dir_], ref, dir_)
+                ref = a.copy(order="F"); osl.fft(kind, n[dir_] - ix, ref, dir_)
                 da = dev(a)
-                c.chk(lib.cales_fft_lines(c.ctx, L._ia(n), dir_, bc.encode(), b"c", backward, da.data_ptr()))
+                c.chk(lib.cales_fft_lines(c.ctx, L._ia(n), dir_, bc.encode(), cf.encode(), backward, da.data_ptr()))
                 got = host(da, a.shape)
-                tol = 2e-15 * max(1., np.log2(n[dir_])) * np.abs(ref).max()
-                assert np.abs(got - ref).max() <= tol, (bc, dir_, backward, np.abs(got - ref).max(), tol)
+                tol = (8e-15 if kind.endswith("00") else 2e-15) * max(1., np.log2(n[dir_])) * np.abs(ref).max()
+                assert np.abs(got - ref).max() <= tol, (bc, cf, dir_, backward, np.abs(got - ref).max(), tol)
+                if ix:
+                    idx = [slice(None)] * 3; idx[dir_] = n[dir_] - 1
+                    assert np.array_equal(got[tuple(idx)], a[tuple(idx)])
+
+
+@pytest.mark.parametrize("bc,cf,kf,kb", KINDS)
+def test_fft_round_trip_normfft(env, bc, cf, kf, kb):
+    """bwd(fwd(x)) * normfft = x for every kind, with normfft as fftini computes it (fft.f90:99,136,142)."""
+    from oracle import solver as osl
+    L, lib = env
+    n = (64, 32, 2)
+    rng = np.random.default_rng(7)
+    a = np.asfortranarray(rng.standard_normal(n))
+    with Ctx(L, lib, n) as c:
+        for dir_ in (0, 1):
+            _, _, norm = osl.find_fft(bc, cf)
+            ix = 1 if (bc == "DD" and cf == "f") else 0
+            nf = 1. / (norm[0] * (n[dir_] + norm[1] - ix))
+            da = dev(a)
+            for backward in (0, 1):
+                c.chk(lib.cales_fft_lines(c.ctx, L._ia(n), dir_, bc.encode(), cf.encode(), backward, da.data_ptr()))
+            got = host(da, a.shape) * nf
+            idx = [slice(None)] * 3; idx[dir_] = slice(0, n[dir_] - ix)
+            assert np.abs(got[tuple(idx)] - a[tuple(idx)]).max() <= 1e-14 * np.abs(a).max()
 
 
 @pytest.mark.parametrize("periodic", [0, 1])
