@@ -2,189 +2,145 @@
 //   mom_xyz_ad  src/mom.f90:17-309   (one fused kernel: advection + diffusion + SGS stress divergence)
 //   rk          src/rk.f90:17-121    cmpt_bulk_forcing src/rk.f90:197-222
 // Layout: a CTA owns a TX x TY tile of (i,j) columns and marches in k through a z-chunk.  The four
-// input fields are staged plane by plane in shared memory with a one-cell halo ring (three rotating
-// planes k-1,k,k+1), so each field value is fetched from HBM/L2 once per CTA and the 13-16 point
-// stencils are served from shared memory.  Arithmetic keeps the reference's association order
-// (-fmad=false): bit-identical to a non-contracting CPU build.
+// input fields are staged plane by plane in shared memory with a one-cell halo ring by cp.async (three
+// rotating slots: planes k and k+1 in use, k+2 in flight; one barrier per plane), so each field value is
+// fetched from HBM/L2 once per CTA and the stencils are served from shared memory.  Arithmetic keeps the
+// reference's association order (-fmad=false): bit-identical to a non-contracting CPU build.
 #include "common.cuh"
 
-#define TX 32
-#define TY 8
-#define PX (TX + 2)
-#define PY (TY + 2)
-#define PLANE (PX * PY)
+#include "tile.cuh"
 
-// Per-thread staging descriptors: every thread moves the same (at most two) tile points of each plane, so
-// the tile-local index and the global offset are computed once, not per plane.
-struct Stage {
-  long g0, g1;      // global offsets (without the k term) of my two tile points, -1 if outside the array
-  int q0, q1;       // their positions in the PX x PY tile, -1 if none
-};
-
-__device__ __forceinline__ Stage make_stage(const Dims& d, int i0, int j0) {
-  Stage st;
-  const int t = threadIdx.x + TX * threadIdx.y;
-  st.q0 = t;                                   // PLANE = 340 > 256 = TX*TY: first point always exists
-  st.q1 = t + TX * TY < PLANE ? t + TX * TY : -1;
-  {
-    const int li = st.q0 % PX, lj = st.q0 / PX;
-    const int i = i0 + li - 1, j = j0 + lj - 1;
-    st.g0 = (i <= d.n1 + 1 && j <= d.n2 + 1) ? (long)i + d.s1 * j : -1;
-  }
-  if (st.q1 >= 0) {
-    const int li = st.q1 % PX, lj = st.q1 / PX;
-    const int i = i0 + li - 1, j = j0 + lj - 1;
-    st.g1 = (i <= d.n1 + 1 && j <= d.n2 + 1) ? (long)i + d.s1 * j : -1;
-  } else st.g1 = -1;
-  return st;
-}
-
+// Shared sub-expressions.  Every face/edge quantity of the staggered stencil is needed by two cells and (for the
+// cross terms) by two momentum components; mom.f90 writes it out at each use (e.g. wu_km of level k is wu_kp of level
+// k-1, uv_ip is vu_jp with the factors swapped).  Floating-point + and * are commutative, so those duplicates are the
+// same bits, and this kernel computes each of them once:
+//   * the k-1/2 quantities of level k are the k+1/2 quantities of level k-1 -> carried in registers along the z march
+//     (9 values + 3 eddy viscosities), so plane k-1 is not read at all;
+//   * the 0.25 of the advective averages and of the four-point eddy-viscosity averages is a power of two: scaling by
+//     it commutes with rounding, so it is folded into the metric factor of the difference, 0.25*dxi etc. (exact unless a
+//     flux underflows, |flux| < 2^-1020).
+// The association order of everything else is the reference's; the library is built with -fmad=false.
 template <int MODE>  // 0 explicit, 1 _IMPDIFF, 2 _IMPDIFF + _IMPDIFF_1D
 __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci, const double* __restrict__ dzfi,
                                                     double visc, const double* __restrict__ u, const double* __restrict__ v,
                                                     const double* __restrict__ w, const double* __restrict__ s,
                                                     double* __restrict__ dudt, double* __restrict__ dvdt, double* __restrict__ dwdt,
                                                     double* __restrict__ dudtd, double* __restrict__ dvdtd, double* __restrict__ dwdtd, int kc) {
-  extern __shared__ double smem[];   // [4 fields][3 planes][PLANE]
+  extern __shared__ double smem[];   // [3 slots][4 fields][PLANE]: planes k, k+1 in use, k+2 in flight
   const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
-  const double* fld[4] = {u, v, w, s};
+  const double* const fld[4] = {u, v, w, s};
   const Stage st = make_stage(d, i0, j0);
-  double r0[4], r1[4];                // register stage of the plane in flight
-#define FETCH(k_)                                                                      \
-  {                                                                                    \
-    const long ko = d.s2 * (long)(k_);                                                 \
-    _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                    \
-      r0[f] = st.g0 >= 0 ? fld[f][st.g0 + ko] : 0.;                                    \
-      r1[f] = st.g1 >= 0 ? fld[f][st.g1 + ko] : 0.;                                    \
-    }                                                                                  \
-  }
-#define COMMIT(slot)                                                                   \
-  {                                                                                    \
-    _Pragma("unroll") for (int f = 0; f < 4; ++f) {                                    \
-      smem[(f * 3 + (slot)) * PLANE + st.q0] = r0[f];                                  \
-      if (st.q1 >= 0) smem[(f * 3 + (slot)) * PLANE + st.q1] = r1[f];                  \
-    }                                                                                  \
-  }
-  FETCH(k0 - 1) COMMIT(0)
-  FETCH(k0) COMMIT(1)
-  FETCH(k0 + 1) COMMIT(2)
+  tile_issue<4>(st, d, fld, smem, k0 - 1, 0);
+  tile_issue<4>(st, d, fld, smem, k0, 1);
+  tile_issue<4>(st, d, fld, smem, k0 + 1, 2);
+  tile_wait_all();
   __syncthreads();
-  int pm = 0, pc = 1, pp = 2;
   const bool active = i <= d.n1 && j <= d.n2;
   const int c = (threadIdx.x + 1) + PX * (threadIdx.y + 1);
   const long n12 = (long)d.n1 * d.n2;
+  const double qdxi = 0.25 * dxi, qdyi = 0.25 * dyi;
+  // k-1/2 quantities of level k0 = k+1/2 quantities of level k0-1 (planes k0-1, k0 = slots 0, 1)
+  double wu_km = 0., dudz_km = 0., sxz_km = 0., wv_km = 0., dvdz_km = 0., syz_km = 0., ww_km = 0., dwdz_km = 0., fzz_km = 0.;
+  double s_ccm = 0., s_pcm = 0., s_cpm = 0.;
+  if (active) {
+    const double* uc = smem + 0 * PLANE; const double* vc = smem + 1 * PLANE; const double* wc = smem + 2 * PLANE; const double* sc = smem + 3 * PLANE;
+    const double* up = uc + 4 * PLANE; const double* vp = vc + 4 * PLANE; const double* wp = wc + 4 * PLANE; const double* sp = sc + 4 * PLANE;
+    const double dzci_m = dzci[k0 - 1], dzfi_k = dzfi[k0];
+    const double u_ccc = uc[c], u_ccp = up[c], v_ccc = vc[c], v_ccp = vp[c], w_ccc = wc[c], w_pcc = wc[c + 1], w_cpc = wc[c + PX], w_ccp = wp[c];
+    wu_km = (w_pcc + w_ccc) * (u_ccc + u_ccp);
+    dudz_km = (u_ccp - u_ccc) * dzci_m;
+    sxz_km = dudz_km + (w_pcc - w_ccc) * dxi;
+    wv_km = (w_ccc + w_cpc) * (v_ccc + v_ccp);
+    dvdz_km = (v_ccp - v_ccc) * dzci_m;
+    syz_km = dvdz_km + (w_cpc - w_ccc) * dyi;
+    ww_km = (w_ccc + w_ccp) * (w_ccc + w_ccp);
+    dwdz_km = (w_ccp - w_ccc) * dzfi_k;
+    fzz_km = sp[c] * (dwdz_km + dwdz_km);
+    s_ccm = sc[c]; s_pcm = sc[c + 1]; s_cpm = sc[c + PX];
+  }
+  __syncthreads();                   // slot 0 (plane k0-1) may now be overwritten
+  int sl_c = 1, sl_p = 2, sl_n = 0;  // slots of planes k, k+1 and of the plane to prefetch (k+2)
   for (int k = k0; k <= k1; ++k) {
     const bool more = k < k1;
-    if (more) FETCH(k + 2)            // in flight while plane k is computed (k+2 <= n3+1)
+    if (more) tile_issue<4>(st, d, fld, smem, k + 2, sl_n);     // in flight while plane k is computed (k+2 <= n3+1)
     if (active) {
-      const double* um = smem + (0 * 3 + pm) * PLANE; const double* uc = smem + (0 * 3 + pc) * PLANE; const double* up = smem + (0 * 3 + pp) * PLANE;
-      const double* vm = smem + (1 * 3 + pm) * PLANE; const double* vc = smem + (1 * 3 + pc) * PLANE; const double* vp = smem + (1 * 3 + pp) * PLANE;
-      const double* wm = smem + (2 * 3 + pm) * PLANE; const double* wc = smem + (2 * 3 + pc) * PLANE; const double* wp = smem + (2 * 3 + pp) * PLANE;
-      const double* sm_ = smem + (3 * 3 + pm) * PLANE; const double* sc = smem + (3 * 3 + pc) * PLANE; const double* sp = smem + (3 * 3 + pp) * PLANE;
-#define LD(prefix, M, C, P)                                                                                       \
-  const double prefix##_ccm = M[c], prefix##_pcm = M[c + 1], prefix##_cpm = M[c + PX], prefix##_cmc = C[c - PX],     \
-               prefix##_pmc = C[c + 1 - PX], prefix##_mcc = C[c - 1], prefix##_ccc = C[c], prefix##_pcc = C[c + 1],   \
-               prefix##_mpc = C[c - 1 + PX], prefix##_cpc = C[c + PX], prefix##_cmp = P[c - PX], prefix##_mcp = P[c - 1], \
-               prefix##_ccp = P[c];
-      LD(u, um, uc, up)
-      LD(v, vm, vc, vp)
-      LD(w, wm, wc, wp)
-      LD(s, sm_, sc, sp)
-#undef LD
-      const double s_ppc = sc[c + 1 + PX], s_pcp = sp[c + 1], s_cpp = sp[c + PX];
-      const double dzci_k = dzci[k], dzci_km = dzci[k - 1], dzfi_k = dzfi[k], dzfi_kp = dzfi[k + 1];
-      (void)u_pmc; (void)u_cpm; (void)v_pcm; (void)v_mpc; (void)w_mcp; (void)w_mpc; (void)w_cmp; (void)w_pmc;
-      (void)u_pcm; (void)v_mcp; (void)s_mcp; (void)s_cmp; (void)s_mpc;
-      double visc_ip, visc_im, visc_jp, visc_jm, visc_kp, visc_km;
-      // ---- x momentum (mom.f90:142-186)
-      visc_ip = s_pcc;
-      visc_im = s_ccc;
-      visc_jp = 0.25 * (s_ccc + s_pcc + s_cpc + s_ppc);
-      visc_jm = 0.25 * (s_ccc + s_pcc + s_cmc + s_pmc);
-      visc_kp = 0.25 * (s_ccc + s_pcc + s_ccp + s_pcp);
-      visc_km = 0.25 * (s_ccc + s_pcc + s_ccm + s_pcm);
+      const double* uc = smem + (sl_c * 4 + 0) * PLANE; const double* up = smem + (sl_p * 4 + 0) * PLANE;
+      const double* vc = smem + (sl_c * 4 + 1) * PLANE; const double* vp = smem + (sl_p * 4 + 1) * PLANE;
+      const double* wc = smem + (sl_c * 4 + 2) * PLANE; const double* wp = smem + (sl_p * 4 + 2) * PLANE;
+      const double* sc = smem + (sl_c * 4 + 3) * PLANE; const double* sp = smem + (sl_p * 4 + 3) * PLANE;
+      const double u_cmc = uc[c - PX], u_mcc = uc[c - 1], u_ccc = uc[c], u_pcc = uc[c + 1], u_mpc = uc[c - 1 + PX], u_cpc = uc[c + PX];
+      const double u_mcp = up[c - 1], u_ccp = up[c];
+      const double v_cmc = vc[c - PX], v_pmc = vc[c + 1 - PX], v_mcc = vc[c - 1], v_ccc = vc[c], v_pcc = vc[c + 1], v_cpc = vc[c + PX];
+      const double v_cmp = vp[c - PX], v_ccp = vp[c];
+      const double w_cmc = wc[c - PX], w_mcc = wc[c - 1], w_ccc = wc[c], w_pcc = wc[c + 1], w_cpc = wc[c + PX], w_ccp = wp[c];
+      const double s_cmc = sc[c - PX], s_pmc = sc[c + 1 - PX], s_mcc = sc[c - 1], s_ccc = sc[c], s_pcc = sc[c + 1], s_mpc = sc[c - 1 + PX],
+                   s_cpc = sc[c + PX], s_ppc = sc[c + 1 + PX];
+      const double s_cmp = sp[c - PX], s_mcp = sp[c - 1], s_ccp = sp[c], s_pcp = sp[c + 1], s_cpp = sp[c + PX];
+      const double dzci_k = dzci[k], dzfi_k = dzfi[k], dzfi_kp = dzfi[k + 1];
+      const double qdzfi_k = 0.25 * dzfi_k, qdzci_k = 0.25 * dzci_k;
+      // ---- face/edge quantities on the + side of this cell (shared with the neighbour at k+1 through the carry,
+      //      and between the two momentum components that meet at the edge)
       const double dudx_ip = (u_pcc - u_ccc) * dxi;
+      const double dudy_jp = (u_cpc - u_ccc) * dyi;              // = dudy_ip of the y equation
+      const double dudz_kp = (u_ccp - u_ccc) * dzci_k;           // = dudz_ip of the z equation
+      const double dvdx_jp = (v_pcc - v_ccc) * dxi;              // = dvdx_ip
+      const double dvdy_jp = (v_cpc - v_ccc) * dyi;
+      const double dvdz_kp = (v_ccp - v_ccc) * dzci_k;           // = dvdz_jp of the z equation
+      const double dwdx_kp = (w_pcc - w_ccc) * dxi;              // = dwdx_ip
+      const double dwdy_kp = (w_cpc - w_ccc) * dyi;              // = dwdy_jp
+      const double dwdz_kp = (w_ccp - w_ccc) * dzfi_kp;
+      const double sxy_p = dudy_jp + dvdx_jp;                    // (dudy_jp+dvdx_jp) = (dvdx_ip+dudy_ip)
+      const double sxz_p = dudz_kp + dwdx_kp;                    // (dudz_kp+dwdx_kp) = (dwdx_ip+dudz_ip)
+      const double syz_p = dvdz_kp + dwdy_kp;                    // (dvdz_kp+dwdy_kp) = (dwdy_jp+dvdz_jp)
+      const double uv_p = (v_pcc + v_ccc) * (u_ccc + u_cpc);     // 4 vu_jp = 4 uv_ip
+      const double uw_p = (w_pcc + w_ccc) * (u_ccc + u_ccp);     // 4 wu_kp = 4 uw_ip
+      const double vw_p = (w_ccc + w_cpc) * (v_ccc + v_ccp);     // 4 wv_kp = 4 vw_jp
+      // ---- x momentum (mom.f90:142-186)
+      const double sx = s_ccc + s_pcc;
       const double dudx_im = (u_ccc - u_mcc) * dxi;
-      const double dudy_jp = (u_cpc - u_ccc) * dyi;
       const double dudy_jm = (u_ccc - u_cmc) * dyi;
-      const double dudz_kp = (u_ccp - u_ccc) * dzci_k;
-      const double dudz_km = (u_ccc - u_ccm) * dzci_km;
-      const double dvdx_jp = (v_pcc - v_ccc) * dxi;
       const double dvdx_jm = (v_pmc - v_cmc) * dxi;
-      const double dwdx_kp = (w_pcc - w_ccc) * dxi;
-      const double dwdx_km = (w_pcm - w_ccm) * dxi;
-      const double uu_ip = 0.25 * (u_pcc + u_ccc) * (u_ccc + u_pcc);
-      const double uu_im = 0.25 * (u_mcc + u_ccc) * (u_ccc + u_mcc);
-      const double vu_jp = 0.25 * (v_pcc + v_ccc) * (u_ccc + u_cpc);
-      const double vu_jm = 0.25 * (v_pmc + v_cmc) * (u_ccc + u_cmc);
-      const double wu_kp = 0.25 * (w_pcc + w_ccc) * (u_ccc + u_ccp);
-      const double wu_km = 0.25 * (w_pcm + w_ccm) * (u_ccc + u_ccm);
+      const double uu_ip = (u_pcc + u_ccc) * (u_ccc + u_pcc);
+      const double uu_im = (u_mcc + u_ccc) * (u_ccc + u_mcc);
+      const double vu_jm = (v_pmc + v_cmc) * (u_ccc + u_cmc);
       const double dudtd_xy_s = visc * (dudx_ip - dudx_im) * dxi + visc * (dudy_jp - dudy_jm) * dyi;
       const double dudtd_z_s = visc * (dudz_kp - dudz_km) * dzfi_k;
-      double dudt_s = -(uu_ip - uu_im) * dxi - (vu_jp - vu_jm) * dyi - (wu_kp - wu_km) * dzfi_k +
-                      (visc_ip * (dudx_ip + dudx_ip) - visc_im * (dudx_im + dudx_im)) * dxi +
-                      (visc_jp * (dudy_jp + dvdx_jp) - visc_jm * (dudy_jm + dvdx_jm)) * dyi +
-                      (visc_kp * (dudz_kp + dwdx_kp) - visc_km * (dudz_km + dwdx_km)) * dzfi_k;
+      const double dudt_s = -(uu_ip - uu_im) * qdxi - (uv_p - vu_jm) * qdyi - (uw_p - wu_km) * qdzfi_k +
+                            (s_pcc * (dudx_ip + dudx_ip) - s_ccc * (dudx_im + dudx_im)) * dxi +
+                            ((sx + s_cpc + s_ppc) * sxy_p - (sx + s_cmc + s_pmc) * (dudy_jm + dvdx_jm)) * qdyi +
+                            ((sx + s_ccp + s_pcp) * sxz_p - (sx + s_ccm + s_pcm) * sxz_km) * qdzfi_k;
       // ---- y momentum (mom.f90:187-231)
-      visc_ip = 0.25 * (s_ccc + s_cpc + s_pcc + s_ppc);
-      visc_im = 0.25 * (s_ccc + s_cpc + s_mcc + s_mpc);
-      visc_jp = s_cpc;
-      visc_jm = s_ccc;
-      visc_kp = 0.25 * (s_ccc + s_cpc + s_ccp + s_cpp);
-      visc_km = 0.25 * (s_ccc + s_cpc + s_ccm + s_cpm);
-      const double dvdx_ip = (v_pcc - v_ccc) * dxi;
+      const double sy = s_ccc + s_cpc;
       const double dvdx_im = (v_ccc - v_mcc) * dxi;
-      const double dvdy_jp = (v_cpc - v_ccc) * dyi;
       const double dvdy_jm = (v_ccc - v_cmc) * dyi;
-      const double dvdz_kp = (v_ccp - v_ccc) * dzci_k;
-      const double dvdz_km = (v_ccc - v_ccm) * dzci_km;
-      const double dudy_ip = (u_cpc - u_ccc) * dyi;
       const double dudy_im = (u_mpc - u_mcc) * dyi;
-      const double dwdy_kp = (w_cpc - w_ccc) * dyi;
-      const double dwdy_km = (w_cpm - w_ccm) * dyi;
-      const double uv_ip = 0.25 * (u_ccc + u_cpc) * (v_ccc + v_pcc);
-      const double uv_im = 0.25 * (u_mcc + u_mpc) * (v_ccc + v_mcc);
-      const double vv_jp = 0.25 * (v_ccc + v_cpc) * (v_ccc + v_cpc);
-      const double vv_jm = 0.25 * (v_ccc + v_cmc) * (v_ccc + v_cmc);
-      const double wv_kp = 0.25 * (w_ccc + w_cpc) * (v_ccc + v_ccp);
-      const double wv_km = 0.25 * (w_ccm + w_cpm) * (v_ccc + v_ccm);
-      const double dvdtd_xy_s = visc * (dvdx_ip - dvdx_im) * dxi + visc * (dvdy_jp - dvdy_jm) * dyi;
+      const double uv_im = (u_mcc + u_mpc) * (v_ccc + v_mcc);
+      const double vv_jp = (v_ccc + v_cpc) * (v_ccc + v_cpc);
+      const double vv_jm = (v_ccc + v_cmc) * (v_ccc + v_cmc);
+      const double dvdtd_xy_s = visc * (dvdx_jp - dvdx_im) * dxi + visc * (dvdy_jp - dvdy_jm) * dyi;
       const double dvdtd_z_s = visc * (dvdz_kp - dvdz_km) * dzfi_k;
-      double dvdt_s = -(uv_ip - uv_im) * dxi - (vv_jp - vv_jm) * dyi - (wv_kp - wv_km) * dzfi_k +
-                      (visc_ip * (dvdx_ip + dudy_ip) - visc_im * (dvdx_im + dudy_im)) * dxi +
-                      (visc_jp * (dvdy_jp + dvdy_jp) - visc_jm * (dvdy_jm + dvdy_jm)) * dyi +
-                      (visc_kp * (dvdz_kp + dwdy_kp) - visc_km * (dvdz_km + dwdy_km)) * dzfi_k;
+      const double dvdt_s = -(uv_p - uv_im) * qdxi - (vv_jp - vv_jm) * qdyi - (vw_p - wv_km) * qdzfi_k +
+                            ((sy + s_pcc + s_ppc) * sxy_p - (sy + s_mcc + s_mpc) * (dvdx_im + dudy_im)) * qdxi +
+                            (s_cpc * (dvdy_jp + dvdy_jp) - s_ccc * (dvdy_jm + dvdy_jm)) * dyi +
+                            ((sy + s_ccp + s_cpp) * syz_p - (sy + s_ccm + s_cpm) * syz_km) * qdzfi_k;
       // ---- z momentum (mom.f90:232-276)
-      visc_ip = 0.25 * (s_ccc + s_ccp + s_pcc + s_pcp);
-      visc_im = 0.25 * (s_ccc + s_ccp + s_mcc + s_mcp);
-      visc_jp = 0.25 * (s_ccc + s_ccp + s_cpc + s_cpp);
-      visc_jm = 0.25 * (s_ccc + s_ccp + s_cmc + s_cmp);
-      visc_kp = s_ccp;
-      visc_km = s_ccc;
-      const double dwdx_ip = (w_pcc - w_ccc) * dxi;
+      const double sz = s_ccc + s_ccp;
       const double dwdx_im = (w_ccc - w_mcc) * dxi;
-      const double dwdy_jp = (w_cpc - w_ccc) * dyi;
       const double dwdy_jm = (w_ccc - w_cmc) * dyi;
-      const double dwdz_kp = (w_ccp - w_ccc) * dzfi_kp;
-      const double dwdz_km = (w_ccc - w_ccm) * dzfi_k;
-      const double dudz_ip = (u_ccp - u_ccc) * dzci_k;
       const double dudz_im = (u_mcp - u_mcc) * dzci_k;
-      const double dvdz_jp = (v_ccp - v_ccc) * dzci_k;
       const double dvdz_jm = (v_cmp - v_cmc) * dzci_k;
-      const double uw_ip = 0.25 * (u_ccc + u_ccp) * (w_ccc + w_pcc);
-      const double uw_im = 0.25 * (u_mcc + u_mcp) * (w_ccc + w_mcc);
-      const double vw_jp = 0.25 * (v_ccc + v_ccp) * (w_ccc + w_cpc);
-      const double vw_jm = 0.25 * (v_cmc + v_cmp) * (w_ccc + w_cmc);
-      const double ww_kp = 0.25 * (w_ccc + w_ccp) * (w_ccc + w_ccp);
-      const double ww_km = 0.25 * (w_ccc + w_ccm) * (w_ccc + w_ccm);
-      const double dwdtd_xy_s = visc * (dwdx_ip - dwdx_im) * dxi + visc * (dwdy_jp - dwdy_jm) * dyi;
+      const double uw_im = (u_mcc + u_mcp) * (w_ccc + w_mcc);
+      const double vw_jm = (v_cmc + v_cmp) * (w_ccc + w_cmc);
+      const double ww_kp = (w_ccc + w_ccp) * (w_ccc + w_ccp);
+      const double fzz_kp = s_ccp * (dwdz_kp + dwdz_kp);
+      const double dwdtd_xy_s = visc * (dwdx_kp - dwdx_im) * dxi + visc * (dwdy_kp - dwdy_jm) * dyi;
       const double dwdtd_z_s = visc * (dwdz_kp - dwdz_km) * dzci_k;
-      double dwdt_s = -(uw_ip - uw_im) * dxi - (vw_jp - vw_jm) * dyi - (ww_kp - ww_km) * dzci_k +
-                      (visc_ip * (dwdx_ip + dudz_ip) - visc_im * (dwdx_im + dudz_im)) * dxi +
-                      (visc_jp * (dwdy_jp + dvdz_jp) - visc_jm * (dwdy_jm + dvdz_jm)) * dyi +
-                      (visc_kp * (dwdz_kp + dwdz_kp) - visc_km * (dwdz_km + dwdz_km)) * dzci_k;
+      const double dwdt_s = -(uw_p - uw_im) * qdxi - (vw_p - vw_jm) * qdyi - (ww_kp - ww_km) * qdzci_k +
+                            ((sz + s_pcc + s_pcp) * sxz_p - (sz + s_mcc + s_mcp) * (dwdx_im + dudz_im)) * qdxi +
+                            ((sz + s_cpc + s_cpp) * syz_p - (sz + s_cmc + s_cmp) * (dwdy_jm + dvdz_jm)) * qdyi +
+                            (fzz_kp - fzz_km) * dzci_k;
       const long o = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k - 1);   // dudt(n1,n2,n3): no halo
       if (MODE == 0) {                                                    // mom.f90:296-302
         dudt[o] = dudt_s + dudtd_xy_s + dudtd_z_s;
@@ -199,14 +155,15 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
         dudt[o] = dudt_s + dudtd_xy_s; dvdt[o] = dvdt_s + dvdtd_xy_s; dwdt[o] = dwdt_s + dwdtd_xy_s;
         dudtd[o] = dudtd_z_s; dvdtd[o] = dvdtd_z_s; dwdtd[o] = dwdtd_z_s;
       }
+      wu_km = uw_p; dudz_km = dudz_kp; sxz_km = sxz_p;
+      wv_km = vw_p; dvdz_km = dvdz_kp; syz_km = syz_p;
+      ww_km = ww_kp; dwdz_km = dwdz_kp; fzz_km = fzz_kp;
+      s_ccm = s_ccc; s_pcm = s_pcc; s_cpm = s_cpc;
     }
-    __syncthreads();                 // everyone is done reading plane k-1 (slot pm)
-    if (more) COMMIT(pm)
-    __syncthreads();
-    const int tmp = pm; pm = pc; pc = pp; pp = tmp;
+    tile_wait_all();
+    __syncthreads();                 // plane k+2 has landed; everyone is done reading plane k
+    const int tmp = sl_c; sl_c = sl_p; sl_p = sl_n; sl_n = tmp;
   }
-#undef FETCH
-#undef COMMIT
 }
 
 static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, const double* dzci, const double* dzfi, double visc,

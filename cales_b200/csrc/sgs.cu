@@ -8,6 +8,7 @@
 // and the x-y plane sums fused in one kernel, and the plane average consumed on the device.
 #include "common.cuh"
 #include "reduce.cuh"
+#include "tile.cuh"
 
 #define BX 64
 #define BY 4
@@ -29,7 +30,6 @@ struct SmagArgs {
   const double* zc; const double* dzci0;      // zc(0:n3+1), dzci(0:n3+1)
   const double* delk;                         // (dl(1)*dl(2)*dzf(k))**(1/3), precomputed per k
   const double *u, *v, *w;                    // the UN-extrapolated velocity (wall shear, sgs.f90:117-143)
-  double* visct;
 };
 
 // del(k) = (dl(1)*dl(2)*dzf(k))**(1/3)   (sgs.f90:149)
@@ -90,61 +90,102 @@ __device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, i
 }
 
 // ---- strain rate (sgs.f90:1019-1110) -----------------------------------------------------------------------------
+// Same skeleton as mom_k: a TX x TY tile marches in k, the u,v,w planes k and k+1 sit in shared memory (cp.async ring,
+// one barrier per plane).  The four k-1/2 terms of s13 and of s23 at level k are the k+1/2 terms of level k-1 (same
+// expression, same bits): they are carried in registers, so plane k-1 is never read.  The eight-term sums keep the
+// reference's order.
 template <int SIJ, int SMAG>
-__global__ void __launch_bounds__(BX* BY, 3) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
+__global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
                                                     const double* __restrict__ dzfi, const double* __restrict__ u,
                                                     const double* __restrict__ v, const double* __restrict__ w,
-                                                    double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc, SmagArgs A) {
-  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
-  if (i > d.n1 || j > d.n2) return;
+                                                    double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc, SmagArgs A,
+                                                    double* __restrict__ visct) {
+  extern __shared__ double smem[];   // [3 slots][3 fields][PLANE]
+  const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
+  const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
-  const long s1 = d.s1, s2 = d.s2;
-  long c = d.idx(i, j, k0);
-  // z-march with register rotation: the k-1 values are the previous k values and the k values at (i-1..i, j) / (i, j-1..j)
-  // are the previous k+1 values, so a step loads 17 new values instead of 30 (all but three of them L1 hits)
-  double u_mcm = u[c - 1 - s2], u_ccm = u[c - s2], u_mcc = u[c - 1], u_ccc = u[c];
-  double v_cmm = v[c - s1 - s2], v_ccm = v[c - s2], v_cmc = v[c - s1], v_ccc = v[c];
-  double w_cmm = w[c - s1 - s2], w_mcm = w[c - 1 - s2], w_ccm = w[c - s2], w_pcm = w[c + 1 - s2], w_cpm = w[c + s1 - s2];
-  for (int k = k0; k <= k1; ++k, c += s2) {
-    const double u_mmc = u[c - 1 - s1], u_cmc = u[c - s1], u_mpc = u[c - 1 + s1], u_cpc = u[c + s1], u_mcp = u[c - 1 + s2], u_ccp = u[c + s2];
-    const double v_mmc = v[c - 1 - s1], v_pmc = v[c + 1 - s1], v_mcc = v[c - 1], v_pcc = v[c + 1], v_cmp = v[c - s1 + s2], v_ccp = v[c + s2];
-    const double w_cmc = w[c - s1], w_mcc = w[c - 1], w_ccc = w[c], w_pcc = w[c + 1], w_cpc = w[c + s1];
-    const double dzci_k = dzci[k], dzci_km = dzci[k - 1];
-    const double s11 = (u_ccc - u_mcc) * dxi;
-    const double s22 = (v_ccc - v_cmc) * dyi;
-    const double s33 = (w_ccc - w_ccm) * dzfi[k];
-    const double s12 = .125 * ((u_cpc - u_ccc) * dyi + (v_pcc - v_ccc) * dxi + (u_ccc - u_cmc) * dyi + (v_pmc - v_cmc) * dxi +
-                               (u_mpc - u_mcc) * dyi + (v_ccc - v_mcc) * dxi + (u_mcc - u_mmc) * dyi + (v_cmc - v_mmc) * dxi);
-    const double s13 = .125 * ((u_ccp - u_ccc) * dzci_k + (w_pcc - w_ccc) * dxi + (u_ccc - u_ccm) * dzci_km + (w_pcm - w_ccm) * dxi +
-                               (u_mcp - u_mcc) * dzci_k + (w_ccc - w_mcc) * dxi + (u_mcc - u_mcm) * dzci_km + (w_ccm - w_mcm) * dxi);
-    const double s23 = .125 * ((v_ccp - v_ccc) * dzci_k + (w_cpc - w_ccc) * dyi + (v_ccc - v_ccm) * dzci_km + (w_cpm - w_ccm) * dyi +
-                               (v_cmp - v_cmc) * dzci_k + (w_ccc - w_cmc) * dyi + (v_cmc - v_cmm) * dzci_km + (w_ccm - w_cmm) * dyi);
-    const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
-    if (SMAG) {                                          // visct = (c_smag*del*fd)**2*s0   (sgs.f90:150)
-      const double fd = A.any_wall ? van_driest(d, A, i, j, k) : 1.;
-      const double t = CSMAG * A.delk[k] * fd;
-      A.visct[c] = t * t * s;
-    } else s0[c] = s;
-    if (SIJ) {
-      sij.p[0][c] = s11; sij.p[1][c] = s22; sij.p[2][c] = s33; sij.p[3][c] = s12; sij.p[4][c] = s13; sij.p[5][c] = s23;
-      if (s0copy) s0copy[c] = s;
-    }
-    u_mcm = u_mcc; u_ccm = u_ccc; u_mcc = u_mcp; u_ccc = u_ccp;
-    v_cmm = v_cmc; v_ccm = v_ccc; v_cmc = v_cmp; v_ccc = v_ccp;
-    w_cmm = w_cmc; w_mcm = w_mcc; w_ccm = w_ccc; w_pcm = w_pcc; w_cpm = w_cpc;
+  const double* const fld[3] = {u, v, w};
+  const Stage st = make_stage(d, i0, j0);
+  tile_issue<3>(st, d, fld, smem, k0 - 1, 0);
+  tile_issue<3>(st, d, fld, smem, k0, 1);
+  tile_issue<3>(st, d, fld, smem, k0 + 1, 2);
+  tile_wait_all();
+  __syncthreads();
+  const bool active = i <= d.n1 && j <= d.n2;
+  const int c = (threadIdx.x + 1) + PX * (threadIdx.y + 1);
+  // k+1/2 terms of level k0-1 (planes k0-1, k0 = slots 0, 1)
+  double a_uz = 0., a_wx = 0., a_uzm = 0., a_wxm = 0., b_vz = 0., b_wy = 0., b_vzm = 0., b_wym = 0., w_ccm = 0.;
+  if (active) {
+    const double* uc = smem; const double* vc = smem + PLANE; const double* wc = smem + 2 * PLANE;
+    const double* up = uc + 3 * PLANE; const double* vp = vc + 3 * PLANE;
+    const double dz = dzci[k0 - 1];
+    const double w_ccc = wc[c];
+    a_uz = (up[c] - uc[c]) * dz;          a_wx = (wc[c + 1] - w_ccc) * dxi;
+    a_uzm = (up[c - 1] - uc[c - 1]) * dz; a_wxm = (w_ccc - wc[c - 1]) * dxi;
+    b_vz = (vp[c] - vc[c]) * dz;          b_wy = (wc[c + PX] - w_ccc) * dyi;
+    b_vzm = (vp[c - PX] - vc[c - PX]) * dz; b_wym = (w_ccc - wc[c - PX]) * dyi;
+    w_ccm = w_ccc;
   }
+  __syncthreads();
+  int sl_c = 1, sl_p = 2, sl_n = 0;
+  long o = d.idx(i, j, k0);
+  for (int k = k0; k <= k1; ++k, o += d.s2) {
+    if (k < k1) tile_issue<3>(st, d, fld, smem, k + 2, sl_n);
+    if (active) {
+      const double* uc = smem + (sl_c * 3 + 0) * PLANE; const double* up = smem + (sl_p * 3 + 0) * PLANE;
+      const double* vc = smem + (sl_c * 3 + 1) * PLANE; const double* vp = smem + (sl_p * 3 + 1) * PLANE;
+      const double* wc = smem + (sl_c * 3 + 2) * PLANE;
+      const double u_mmc = uc[c - 1 - PX], u_cmc = uc[c - PX], u_mcc = uc[c - 1], u_ccc = uc[c], u_mpc = uc[c - 1 + PX], u_cpc = uc[c + PX];
+      const double u_mcp = up[c - 1], u_ccp = up[c];
+      const double v_mmc = vc[c - 1 - PX], v_cmc = vc[c - PX], v_pmc = vc[c + 1 - PX], v_mcc = vc[c - 1], v_ccc = vc[c], v_pcc = vc[c + 1];
+      const double v_cmp = vp[c - PX], v_ccp = vp[c];
+      const double w_cmc = wc[c - PX], w_mcc = wc[c - 1], w_ccc = wc[c], w_pcc = wc[c + 1], w_cpc = wc[c + PX];
+      const double dzci_k = dzci[k];
+      const double s11 = (u_ccc - u_mcc) * dxi;
+      const double s22 = (v_ccc - v_cmc) * dyi;
+      const double s33 = (w_ccc - w_ccm) * dzfi[k];
+      const double n_uz = (u_ccp - u_ccc) * dzci_k, n_wx = (w_pcc - w_ccc) * dxi, n_uzm = (u_mcp - u_mcc) * dzci_k, n_wxm = (w_ccc - w_mcc) * dxi;
+      const double n_vz = (v_ccp - v_ccc) * dzci_k, n_wy = (w_cpc - w_ccc) * dyi, n_vzm = (v_cmp - v_cmc) * dzci_k, n_wym = (w_ccc - w_cmc) * dyi;
+      const double s12 = .125 * ((u_cpc - u_ccc) * dyi + (v_pcc - v_ccc) * dxi + (u_ccc - u_cmc) * dyi + (v_pmc - v_cmc) * dxi +
+                                 (u_mpc - u_mcc) * dyi + (v_ccc - v_mcc) * dxi + (u_mcc - u_mmc) * dyi + (v_cmc - v_mmc) * dxi);
+      const double s13 = .125 * (n_uz + n_wx + a_uz + a_wx + n_uzm + n_wxm + a_uzm + a_wxm);
+      const double s23 = .125 * (n_vz + n_wy + b_vz + b_wy + n_vzm + n_wym + b_vzm + b_wym);
+      const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
+      if (SMAG) {                                          // visct = (c_smag*del*fd)**2*s0   (sgs.f90:150)
+        const double fd = A.any_wall ? van_driest(d, A, i, j, k) : 1.;
+        const double t = CSMAG * A.delk[k] * fd;
+        visct[o] = t * t * s;
+      } else s0[o] = s;
+      if (SIJ) {
+        sij.p[0][o] = s11; sij.p[1][o] = s22; sij.p[2][o] = s33; sij.p[3][o] = s12; sij.p[4][o] = s13; sij.p[5][o] = s23;
+        if (s0copy) s0copy[o] = s;
+      }
+      a_uz = n_uz; a_wx = n_wx; a_uzm = n_uzm; a_wxm = n_wxm;
+      b_vz = n_vz; b_wy = n_wy; b_vzm = n_vzm; b_wym = n_wym;
+      w_ccm = w_ccc;
+    }
+    tile_wait_all();
+    __syncthreads();
+    const int tmp = sl_c; sl_c = sl_p; sl_p = sl_n; sl_n = tmp;
+  }
+}
+
+#define STRAIN_SMEM (9 * PLANE * sizeof(double))
+static inline dim3 strain_grid(const int n[3], int& kc) {
+  kc = pick_chunk((long)cdiv(n[0], TX) * cdiv(n[1], TY), n[2], 148 * 3, 12, 2);
+  return dim3(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc));
 }
 
 static int strain_launch(cales_ctx* ctx, const int n[3], const double dli[3], const double* dzci, const double* dzfi, const double* u,
                          const double* v, const double* w, double* s0, double* const* sij, double* s0copy) {
   Dims d(n);
-  const int kc = pick_kc(n[0], n[1], n[2]);
-  dim3 g(cdiv(n[0], BX), cdiv(n[1], BY), cdiv(n[2], kc)), b(BX, BY);
+  int kc;
+  const dim3 g = strain_grid(n, kc), b(TX, TY);
   Ptr6 P;
   for (int m = 0; m < 6; ++m) P.p[m] = sij ? sij[m] : nullptr;
   SmagArgs none{};
-  if (sij) strain_k<1, 0><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, s0copy, kc, none);
-  else strain_k<0, 0><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, nullptr, kc, none);
+  if (sij) strain_k<1, 0><<<g, b, STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, s0copy, kc, none, nullptr);
+  else strain_k<0, 0><<<g, b, STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, nullptr, kc, none, nullptr);
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
@@ -396,9 +437,11 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
         A.any_wall |= wall;
       }
     A.dl0 = dl[0]; A.dl1 = dl[1]; A.l2 = l[2]; A.dxi = dli[0]; A.dyi = dli[1]; A.visc = visc;
-    A.zc = zc; A.dzci0 = dzci; A.delk = delk; A.u = u; A.v = v; A.w = w; A.visct = visct;
+    A.zc = zc; A.dzci0 = dzci; A.delk = delk; A.u = u; A.v = v; A.w = w;
     Ptr6 P{};
-    strain_k<0, 1><<<g, b, 0, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kc, A);
+    int kcs;
+    const dim3 gs = strain_grid(n, kcs);
+    strain_k<0, 1><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);
     KERNEL_CHECK(ctx);
     return CALES_OK;
   }
