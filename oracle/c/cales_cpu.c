@@ -1,0 +1,569 @@
+/* oracle/c/cales_cpu.c -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline; never on the product path).
+ *
+ * Plain C / OpenMP restatement of the reference's per-RK3-substep path for the tri-periodic, explicit-
+ * diffusion, static-Smagorinsky configuration (BASELINE config 2, the bench.py workload): the loops of
+ *   src/mom.f90:17-309 (mom_xyz_ad), src/rk.f90:17-121 (rk), src/fillps.f90:14-48, src/solver.f90:20-80
+ *   (solver: x transform, y transform, gaussel_periodic 109-151 with dgtsv_homebrewed 153-179, backward),
+ *   src/correc.f90:14-68, src/updatep.f90:14-49, src/sgs.f90:69-152 ('smag') + strain_rate 1019-1110,
+ *   src/bound.f90:18-200 (periodic ghost fill only), src/chkdt.f90:17-99, src/chkdiv.f90:16-52,
+ * sequenced as src/main.f90:417-507.  It exists (i) as a second, independently written restatement that
+ * tests/test_oracle_c.py holds against the numpy oracle, and (ii) as the multi-threaded CPU arm of
+ * bench.py (`cpu_baseline`, `--impl reference`): the Fortran/MPI/FFTW reference cannot be built here.
+ *
+ * PARITY UNPINNED (see oracle/__init__.py): the reference ships no golden vectors for this path.
+ *
+ * Third-party arithmetic: the reference plans FFTW3 R2HC/HC2R (unpinned libfftw3-dev; call sites
+ * src/fft.f90:83-84,120-121).  FFTW is absent; the transforms below are an own Stockham mixed-radix
+ * complex FFT, two real lines per complex transform, producing FFTW's halfcomplex layout
+ * (r0..r_{n/2}, i_{(n+1)/2-1}..i_1), unnormalised, forward sign -1.
+ *
+ * Arrays are Fortran ordered with one ghost cell: (i,j,k) -> i + (n1+2)*(j + (n2+2)*k).
+ * Build with -ffp-contract=off: the stencil loops then agree bit for bit with the numpy oracle.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define C_SMAG 0.11 /* param.f90:33 */
+static const double RKCOEFF[3][2] = {{32.0 / 60.0, 0.0}, {25.0 / 60.0, -17.0 / 60.0}, {45.0 / 60.0, -25.0 / 60.0}}; /* param.f90:27-29 */
+
+typedef struct { double re, im; } cpx;
+
+typedef struct {
+  int n, nfac, fac[32];
+  cpx *tw; /* tw[k] = exp(-2 pi i k / n) */
+} fftplan;
+
+typedef struct {
+  int n1, n2, n3;
+  long sj, sk, ntot, nint;
+  double l[3], dl[3], dli[3], visc;
+  double *dzc, *dzf, *dzci, *dzfi;     /* 0:n3+1 */
+  double *u, *v, *w, *p, *pp, *visct, *s0;
+  double *rhs[3], *rhso[3];            /* dudtrk.., dudtrko.. (n1,n2,n3), rk.f90:36-72 */
+  double *a, *b, *c, *lambdaxy, normfft;
+  double *wk;                          /* solver work array (n1,n2,n3) */
+  fftplan px, py;
+  double eps;
+} cpu_t;
+
+#define IDX(s, i, j, k) ((long)(i) + (s)->sj * ((long)(j) + (long)((s)->n2 + 2) * (long)(k)))
+
+/* ------------------------------------------------------------------------------------------------ FFT */
+static void plan_init(fftplan *pl, int n) {
+  pl->n = n; pl->nfac = 0;
+  int m = n;
+  while (m % 4 == 0) { pl->fac[pl->nfac++] = 4; m /= 4; }
+  for (int r = 2; m > 1;) { if (m % r == 0) { pl->fac[pl->nfac++] = r; m /= r; } else r++; }
+  pl->tw = (cpx *)malloc(sizeof(cpx) * (size_t)n);
+  const double pi = acos(-1.0);
+  for (int k = 0; k < n; k++) { pl->tw[k].re = cos(2.0 * pi * k / n); pl->tw[k].im = -sin(2.0 * pi * k / n); }
+}
+
+/* Stockham autosort, decimation in frequency; sign=-1 forward, +1 backward (conjugated twiddles).
+ * Returns the buffer (x or y) that holds the result. */
+static cpx *fft_exec(const fftplan *pl, cpx *x, cpx *y, int sign) {
+  int n = pl->n, s = 1;
+  for (int f = 0; f < pl->nfac; f++) {
+    int r = pl->fac[f], m = n / r, tstep = pl->n / n; /* w_n^p = tw[p*tstep] */
+    if (r == 2) {
+      for (int p = 0; p < m; p++) {
+        cpx w = pl->tw[p * tstep]; if (sign > 0) w.im = -w.im;
+        for (int q = 0; q < s; q++) {
+          cpx a = x[q + s * p], b = x[q + s * (p + m)];
+          cpx d = {a.re - b.re, a.im - b.im};
+          y[q + s * (2 * p)].re = a.re + b.re; y[q + s * (2 * p)].im = a.im + b.im;
+          y[q + s * (2 * p + 1)].re = d.re * w.re - d.im * w.im; y[q + s * (2 * p + 1)].im = d.re * w.im + d.im * w.re;
+        }
+      }
+    } else if (r == 4) {
+      for (int p = 0; p < m; p++) {
+        cpx w1 = pl->tw[p * tstep], w2 = pl->tw[2 * p * tstep], w3 = pl->tw[3 * p * tstep];
+        if (sign > 0) { w1.im = -w1.im; w2.im = -w2.im; w3.im = -w3.im; }
+        for (int q = 0; q < s; q++) {
+          cpx a = x[q + s * p], b = x[q + s * (p + m)], c = x[q + s * (p + 2 * m)], d = x[q + s * (p + 3 * m)];
+          cpx apc = {a.re + c.re, a.im + c.im}, amc = {a.re - c.re, a.im - c.im};
+          cpx bpd = {b.re + d.re, b.im + d.im}, bmd = {b.re - d.re, b.im - d.im};
+          /* multiply (b-d) by -i (forward) or +i (backward) */
+          cpx jb = sign < 0 ? (cpx){bmd.im, -bmd.re} : (cpx){-bmd.im, bmd.re};
+          cpx t0 = {apc.re + bpd.re, apc.im + bpd.im}, t2 = {apc.re - bpd.re, apc.im - bpd.im};
+          cpx t1 = {amc.re + jb.re, amc.im + jb.im}, t3 = {amc.re - jb.re, amc.im - jb.im};
+          cpx *o = &y[q + s * (4 * p)];
+          o[0] = t0;
+          o[s].re = t1.re * w1.re - t1.im * w1.im; o[s].im = t1.re * w1.im + t1.im * w1.re;
+          o[2 * s].re = t2.re * w2.re - t2.im * w2.im; o[2 * s].im = t2.re * w2.im + t2.im * w2.re;
+          o[3 * s].re = t3.re * w3.re - t3.im * w3.im; o[3 * s].im = t3.re * w3.im + t3.im * w3.re;
+        }
+      }
+    } else { /* generic radix */
+      int rstep = pl->n / r; /* W_r^t = tw[t*rstep] */
+      for (int p = 0; p < m; p++)
+        for (int q = 0; q < s; q++)
+          for (int uo = 0; uo < r; uo++) {
+            double sr = 0., si = 0.;
+            for (int t = 0; t < r; t++) {
+              cpx a = x[q + s * (p + t * m)], w = pl->tw[((long)t * uo % r) * rstep];
+              if (sign > 0) w.im = -w.im;
+              sr += a.re * w.re - a.im * w.im; si += a.re * w.im + a.im * w.re;
+            }
+            cpx w = pl->tw[((long)p * uo * tstep) % pl->n]; if (sign > 0) w.im = -w.im;
+            y[q + s * (r * p + uo)].re = sr * w.re - si * w.im; y[q + s * (r * p + uo)].im = sr * w.im + si * w.re;
+          }
+    }
+    cpx *t = x; x = y; y = t;
+    n = m; s *= r;
+  }
+  return x;
+}
+
+/* Two real lines (a,b; element stride `st`) -> halfcomplex in place (FFTW R2HC). b may be NULL. */
+static void r2hc_pair(const fftplan *pl, double *a, double *b, long st, cpx *x, cpx *y) {
+  int n = pl->n;
+  for (int j = 0; j < n; j++) { x[j].re = a[j * st]; x[j].im = b ? b[j * st] : 0.0; }
+  cpx *z = fft_exec(pl, x, y, -1);
+  a[0] = z[0].re; if (b) b[0] = z[0].im;
+  for (int k = 1; k <= n / 2; k++) {
+    cpx zk = z[k], zc = z[n - k];
+    double are = 0.5 * (zk.re + zc.re), aim = 0.5 * (zk.im - zc.im);
+    double bre = 0.5 * (zk.im + zc.im), bim = -0.5 * (zk.re - zc.re);
+    a[k * st] = are; if (2 * k < n) a[(n - k) * st] = aim;
+    if (b) { b[k * st] = bre; if (2 * k < n) b[(n - k) * st] = bim; }
+  }
+}
+
+/* Halfcomplex -> real, unnormalised (FFTW HC2R), two lines at once. */
+static void hc2r_pair(const fftplan *pl, double *a, double *b, long st, cpx *x, cpx *y) {
+  int n = pl->n;
+  x[0].re = a[0]; x[0].im = b ? b[0] : 0.0;
+  for (int k = 1; k <= n / 2; k++) {
+    double are = a[k * st], aim = (2 * k < n) ? a[(n - k) * st] : 0.0;
+    double bre = b ? b[k * st] : 0.0, bim = (b && 2 * k < n) ? b[(n - k) * st] : 0.0;
+    /* Z[k] = A[k] + i B[k];  Z[n-k] = conj(A[k]) + i conj(B[k]) */
+    x[k].re = are - bim; x[k].im = aim + bre;
+    x[n - k].re = are + bim; x[n - k].im = -aim + bre;
+  }
+  cpx *z = fft_exec(pl, x, y, +1);
+  for (int j = 0; j < n; j++) { a[j * st] = z[j].re; if (b) b[j * st] = z[j].im; }
+}
+
+/* ------------------------------------------------------------------------------------------ ghost fill */
+/* bound.f90:175-199 / 42-46 with all-periodic BCs on one rank: direction by direction, full extent. */
+static void bound_periodic(const cpu_t *s, double *p) {
+  int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 0; k <= n3 + 1; k++)
+    for (int j = 0; j <= n2 + 1; j++) { p[IDX(s, 0, j, k)] = p[IDX(s, n1, j, k)]; p[IDX(s, n1 + 1, j, k)] = p[IDX(s, 1, j, k)]; }
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k <= n3 + 1; k++)
+    for (int i = 0; i <= n1 + 1; i++) { p[IDX(s, i, 0, k)] = p[IDX(s, i, n2, k)]; p[IDX(s, i, n2 + 1, k)] = p[IDX(s, i, 1, k)]; }
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j <= n2 + 1; j++)
+    for (int i = 0; i <= n1 + 1; i++) { p[IDX(s, i, j, 0)] = p[IDX(s, i, j, n3)]; p[IDX(s, i, j, n3 + 1)] = p[IDX(s, i, j, 1)]; }
+}
+
+/* ------------------------------------------------------------------------------------------------ SGS */
+/* sgs.f90:1019-1110 (s0 only) fused with the 'smag' model of sgs.f90:69-152; no walls -> fd = 1. */
+static void cmpt_sgs_smag(cpu_t *s) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj, sk = s->sk;
+  const double dxi = s->dli[0], dyi = s->dli[1];
+  const double *u = s->u, *v = s->v, *w = s->w;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++) {
+      const double dzci_k = s->dzci[k], dzci_km = s->dzci[k - 1], dzfi_k = s->dzfi[k];
+      const double dele = pow(s->dl[0] * s->dl[1] * s->dzf[k], 1. / 3.);
+      const double cs = C_SMAG * dele * 1.0;
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+        double s11 = (u[c] - u[c - 1]) * dxi;
+        double s22 = (v[c] - v[c - sj]) * dyi;
+        double s33 = (w[c] - w[c - sk]) * dzfi_k;
+        double s12 = .125 * ((u[c + sj] - u[c]) * dyi + (v[c + 1] - v[c]) * dxi +
+                             (u[c] - u[c - sj]) * dyi + (v[c + 1 - sj] - v[c - sj]) * dxi +
+                             (u[c - 1 + sj] - u[c - 1]) * dyi + (v[c] - v[c - 1]) * dxi +
+                             (u[c - 1] - u[c - 1 - sj]) * dyi + (v[c - sj] - v[c - 1 - sj]) * dxi);
+        double s13 = .125 * ((u[c + sk] - u[c]) * dzci_k + (w[c + 1] - w[c]) * dxi +
+                             (u[c] - u[c - sk]) * dzci_km + (w[c + 1 - sk] - w[c - sk]) * dxi +
+                             (u[c - 1 + sk] - u[c - 1]) * dzci_k + (w[c] - w[c - 1]) * dxi +
+                             (u[c - 1] - u[c - 1 - sk]) * dzci_km + (w[c - sk] - w[c - 1 - sk]) * dxi);
+        double s23 = .125 * ((v[c + sk] - v[c]) * dzci_k + (w[c + sj] - w[c]) * dyi +
+                             (v[c] - v[c - sk]) * dzci_km + (w[c + sj - sk] - w[c - sk]) * dyi +
+                             (v[c - sj + sk] - v[c - sj]) * dzci_k + (w[c] - w[c - sj]) * dyi +
+                             (v[c - sj] - v[c - sj - sk]) * dzci_km + (w[c - sk] - w[c - sj - sk]) * dyi);
+        double s0 = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
+        s->s0[c] = s0;
+        s->visct[c] = (cs * cs) * s0;
+      }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------- mom + rk */
+/* mom.f90:142-302 (explicit branch) and rk.f90:45-100; bforce = 0, nothing forced (TGV deck). */
+static void rk_substep(cpu_t *s, const double rkpar[2], double dt) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj, sk = s->sk;
+  const double dxi = s->dli[0], dyi = s->dli[1], visc = s->visc;
+  const double *u = s->u, *v = s->v, *w = s->w, *t = s->visct;
+  double *du = s->rhs[0], *dv = s->rhs[1], *dw = s->rhs[2];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++) {
+      const double dzci_k = s->dzci[k], dzci_km = s->dzci[k - 1], dzfi_k = s->dzfi[k], dzfi_kp = s->dzfi[k + 1];
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k), o = (long)(i - 1) + (long)n1 * ((long)(j - 1) + (long)n2 * (long)(k - 1));
+#define A(f, di, dj, dk) f[c + (di) + (dj) * sj + (dk) * sk]
+        const double u_ccm = A(u, 0, 0, -1), u_pcm = A(u, 1, 0, -1), u_cpm = A(u, 0, 1, -1), u_cmc = A(u, 0, -1, 0), u_pmc = A(u, 1, -1, 0),
+                     u_mcc = A(u, -1, 0, 0), u_ccc = A(u, 0, 0, 0), u_pcc = A(u, 1, 0, 0), u_mpc = A(u, -1, 1, 0), u_cpc = A(u, 0, 1, 0),
+                     u_cmp = A(u, 0, -1, 1), u_mcp = A(u, -1, 0, 1), u_ccp = A(u, 0, 0, 1);
+        const double v_ccm = A(v, 0, 0, -1), v_pcm = A(v, 1, 0, -1), v_cpm = A(v, 0, 1, -1), v_cmc = A(v, 0, -1, 0), v_pmc = A(v, 1, -1, 0),
+                     v_mcc = A(v, -1, 0, 0), v_ccc = A(v, 0, 0, 0), v_pcc = A(v, 1, 0, 0), v_mpc = A(v, -1, 1, 0), v_cpc = A(v, 0, 1, 0),
+                     v_cmp = A(v, 0, -1, 1), v_mcp = A(v, -1, 0, 1), v_ccp = A(v, 0, 0, 1);
+        const double w_ccm = A(w, 0, 0, -1), w_pcm = A(w, 1, 0, -1), w_cpm = A(w, 0, 1, -1), w_cmc = A(w, 0, -1, 0), w_pmc = A(w, 1, -1, 0),
+                     w_mcc = A(w, -1, 0, 0), w_ccc = A(w, 0, 0, 0), w_pcc = A(w, 1, 0, 0), w_mpc = A(w, -1, 1, 0), w_cpc = A(w, 0, 1, 0),
+                     w_cmp = A(w, 0, -1, 1), w_mcp = A(w, -1, 0, 1), w_ccp = A(w, 0, 0, 1);
+        const double s_ccm = A(t, 0, 0, -1), s_pcm = A(t, 1, 0, -1), s_cpm = A(t, 0, 1, -1), s_cmc = A(t, 0, -1, 0), s_pmc = A(t, 1, -1, 0),
+                     s_mcc = A(t, -1, 0, 0), s_ccc = A(t, 0, 0, 0), s_pcc = A(t, 1, 0, 0), s_mpc = A(t, -1, 1, 0), s_cpc = A(t, 0, 1, 0),
+                     s_cmp = A(t, 0, -1, 1), s_mcp = A(t, -1, 0, 1), s_ccp = A(t, 0, 0, 1), s_ppc = A(t, 1, 1, 0), s_pcp = A(t, 1, 0, 1),
+                     s_cpp = A(t, 0, 1, 1);
+#undef A
+        (void)u_pcm; (void)u_cpm; (void)u_pmc; (void)u_cmp; (void)v_pcm; (void)v_cpm; (void)v_mpc; (void)v_mcp; (void)w_pmc; (void)w_mpc;
+        (void)w_cmp; (void)w_mcp;
+        double visc_ip, visc_im, visc_jp, visc_jm, visc_kp, visc_km;
+        /* x momentum, mom.f90:142-186 */
+        visc_ip = s_pcc; visc_im = s_ccc;
+        visc_jp = 0.25 * (s_ccc + s_pcc + s_cpc + s_ppc);
+        visc_jm = 0.25 * (s_ccc + s_pcc + s_cmc + s_pmc);
+        visc_kp = 0.25 * (s_ccc + s_pcc + s_ccp + s_pcp);
+        visc_km = 0.25 * (s_ccc + s_pcc + s_ccm + s_pcm);
+        {
+          double dudx_ip = (u_pcc - u_ccc) * dxi, dudx_im = (u_ccc - u_mcc) * dxi;
+          double dudy_jp = (u_cpc - u_ccc) * dyi, dudy_jm = (u_ccc - u_cmc) * dyi;
+          double dudz_kp = (u_ccp - u_ccc) * dzci_k, dudz_km = (u_ccc - u_ccm) * dzci_km;
+          double dvdx_jp = (v_pcc - v_ccc) * dxi, dvdx_jm = (v_pmc - v_cmc) * dxi;
+          double dwdx_kp = (w_pcc - w_ccc) * dxi, dwdx_km = (w_pcm - w_ccm) * dxi;
+          double uu_ip = 0.25 * (u_pcc + u_ccc) * (u_ccc + u_pcc), uu_im = 0.25 * (u_mcc + u_ccc) * (u_ccc + u_mcc);
+          double vu_jp = 0.25 * (v_pcc + v_ccc) * (u_ccc + u_cpc), vu_jm = 0.25 * (v_pmc + v_cmc) * (u_ccc + u_cmc);
+          double wu_kp = 0.25 * (w_pcc + w_ccc) * (u_ccc + u_ccp), wu_km = 0.25 * (w_pcm + w_ccm) * (u_ccc + u_ccm);
+          double d_xy = visc * (dudx_ip - dudx_im) * dxi + visc * (dudy_jp - dudy_jm) * dyi;
+          double d_z = visc * (dudz_kp - dudz_km) * dzfi_k;
+          double r = -(uu_ip - uu_im) * dxi - (vu_jp - vu_jm) * dyi - (wu_kp - wu_km) * dzfi_k +
+                     (visc_ip * (dudx_ip + dudx_ip) - visc_im * (dudx_im + dudx_im)) * dxi +
+                     (visc_jp * (dudy_jp + dvdx_jp) - visc_jm * (dudy_jm + dvdx_jm)) * dyi +
+                     (visc_kp * (dudz_kp + dwdx_kp) - visc_km * (dudz_km + dwdx_km)) * dzfi_k;
+          du[o] = r + d_xy + d_z;
+        }
+        /* y momentum, mom.f90:187-231 */
+        visc_ip = 0.25 * (s_ccc + s_cpc + s_pcc + s_ppc);
+        visc_im = 0.25 * (s_ccc + s_cpc + s_mcc + s_mpc);
+        visc_jp = s_cpc; visc_jm = s_ccc;
+        visc_kp = 0.25 * (s_ccc + s_cpc + s_ccp + s_cpp);
+        visc_km = 0.25 * (s_ccc + s_cpc + s_ccm + s_cpm);
+        {
+          double dvdx_ip = (v_pcc - v_ccc) * dxi, dvdx_im = (v_ccc - v_mcc) * dxi;
+          double dvdy_jp = (v_cpc - v_ccc) * dyi, dvdy_jm = (v_ccc - v_cmc) * dyi;
+          double dvdz_kp = (v_ccp - v_ccc) * dzci_k, dvdz_km = (v_ccc - v_ccm) * dzci_km;
+          double dudy_ip = (u_cpc - u_ccc) * dyi, dudy_im = (u_mpc - u_mcc) * dyi;
+          double dwdy_kp = (w_cpc - w_ccc) * dyi, dwdy_km = (w_cpm - w_ccm) * dyi;
+          double uv_ip = 0.25 * (u_ccc + u_cpc) * (v_ccc + v_pcc), uv_im = 0.25 * (u_mcc + u_mpc) * (v_ccc + v_mcc);
+          double vv_jp = 0.25 * (v_ccc + v_cpc) * (v_ccc + v_cpc), vv_jm = 0.25 * (v_ccc + v_cmc) * (v_ccc + v_cmc);
+          double wv_kp = 0.25 * (w_ccc + w_cpc) * (v_ccc + v_ccp), wv_km = 0.25 * (w_ccm + w_cpm) * (v_ccc + v_ccm);
+          double d_xy = visc * (dvdx_ip - dvdx_im) * dxi + visc * (dvdy_jp - dvdy_jm) * dyi;
+          double d_z = visc * (dvdz_kp - dvdz_km) * dzfi_k;
+          double r = -(uv_ip - uv_im) * dxi - (vv_jp - vv_jm) * dyi - (wv_kp - wv_km) * dzfi_k +
+                     (visc_ip * (dvdx_ip + dudy_ip) - visc_im * (dvdx_im + dudy_im)) * dxi +
+                     (visc_jp * (dvdy_jp + dvdy_jp) - visc_jm * (dvdy_jm + dvdy_jm)) * dyi +
+                     (visc_kp * (dvdz_kp + dwdy_kp) - visc_km * (dvdz_km + dwdy_km)) * dzfi_k;
+          dv[o] = r + d_xy + d_z;
+        }
+        /* z momentum, mom.f90:232-276 */
+        visc_ip = 0.25 * (s_ccc + s_ccp + s_pcc + s_pcp);
+        visc_im = 0.25 * (s_ccc + s_ccp + s_mcc + s_mcp);
+        visc_jp = 0.25 * (s_ccc + s_ccp + s_cpc + s_cpp);
+        visc_jm = 0.25 * (s_ccc + s_ccp + s_cmc + s_cmp);
+        visc_kp = s_ccp; visc_km = s_ccc;
+        {
+          double dwdx_ip = (w_pcc - w_ccc) * dxi, dwdx_im = (w_ccc - w_mcc) * dxi;
+          double dwdy_jp = (w_cpc - w_ccc) * dyi, dwdy_jm = (w_ccc - w_cmc) * dyi;
+          double dwdz_kp = (w_ccp - w_ccc) * dzfi_kp, dwdz_km = (w_ccc - w_ccm) * dzfi_k;
+          double dudz_ip = (u_ccp - u_ccc) * dzci_k, dudz_im = (u_mcp - u_mcc) * dzci_k;
+          double dvdz_jp = (v_ccp - v_ccc) * dzci_k, dvdz_jm = (v_cmp - v_cmc) * dzci_k;
+          double uw_ip = 0.25 * (u_ccc + u_ccp) * (w_ccc + w_pcc), uw_im = 0.25 * (u_mcc + u_mcp) * (w_ccc + w_mcc);
+          double vw_jp = 0.25 * (v_ccc + v_ccp) * (w_ccc + w_cpc), vw_jm = 0.25 * (v_cmc + v_cmp) * (w_ccc + w_cmc);
+          double ww_kp = 0.25 * (w_ccc + w_ccp) * (w_ccc + w_ccp), ww_km = 0.25 * (w_ccc + w_ccm) * (w_ccc + w_ccm);
+          double d_xy = visc * (dwdx_ip - dwdx_im) * dxi + visc * (dwdy_jp - dwdy_jm) * dyi;
+          double d_z = visc * (dwdz_kp - dwdz_km) * dzci_k;
+          double r = -(uw_ip - uw_im) * dxi - (vw_jp - vw_jm) * dyi - (ww_kp - ww_km) * dzci_k +
+                     (visc_ip * (dwdx_ip + dudz_ip) - visc_im * (dwdx_im + dudz_im)) * dxi +
+                     (visc_jp * (dwdy_jp + dvdz_jp) - visc_jm * (dwdy_jm + dvdz_jm)) * dyi +
+                     (visc_kp * (dwdz_kp + dwdz_kp) - visc_km * (dwdz_km + dwdz_km)) * dzci_k;
+          dw[o] = r + d_xy + d_z;
+        }
+      }
+    }
+  /* rk.f90:76-100: update (needs the old u,v,w everywhere above, hence a second sweep) */
+  const double factor1 = rkpar[0] * dt, factor2 = rkpar[1] * dt, factor12 = factor1 + factor2;
+  double *uu = s->u, *vv = s->v, *ww = s->w;
+  const double *p = s->p;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++) {
+      const double dzci_k = s->dzci[k];
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k), o = (long)(i - 1) + (long)n1 * ((long)(j - 1) + (long)n2 * (long)(k - 1));
+        uu[c] = uu[c] + factor1 * du[o] + factor2 * s->rhso[0][o] + factor12 * (0.0 - dxi * (p[c + 1] - p[c]));
+        vv[c] = vv[c] + factor1 * dv[o] + factor2 * s->rhso[1][o] + factor12 * (0.0 - dyi * (p[c + sj] - p[c]));
+        ww[c] = ww[c] + factor1 * dw[o] + factor2 * s->rhso[2][o] + factor12 * (0.0 - dzci_k * (p[c + sk] - p[c]));
+      }
+    }
+  for (int m = 0; m < 3; m++) { double *tmp = s->rhs[m]; s->rhs[m] = s->rhso[m]; s->rhso[m] = tmp; } /* swap, rk.f90:92-100 */
+}
+
+/* -------------------------------------------------------------------------------- pressure correction */
+static void fillps(cpu_t *s, double dti) { /* fillps.f90:33-47 */
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj, sk = s->sk;
+  const double dtidxi = dti * s->dli[0], dtidyi = dti * s->dli[1];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++) {
+      const double dzfi_k = s->dzfi[k];
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+        s->pp[c] = (s->w[c] - s->w[c - sk]) * dti * dzfi_k + (s->v[c] - s->v[c - sj]) * dtidyi + (s->u[c] - s->u[c - 1]) * dtidxi;
+      }
+    }
+}
+
+/* solver.f90:153-179 for the columns of one j-row, vectorised over i (same operation order per column). */
+static void dgtsv_row(int n1, int n, const double *a, const double *bb, const double *c, double *p, double *d, double eps) {
+  /* bb, p, d: [l][i] with row length n1 */
+  for (int i = 0; i < n1; i++) { double z = 1. / (bb[i] + eps); d[i] = c[0] * z; p[i] = p[i] * z; }
+  for (int l = 1; l < n; l++)
+    for (int i = 0; i < n1; i++) {
+      double z = 1. / (bb[(long)l * n1 + i] - a[l] * d[(long)(l - 1) * n1 + i] + eps);
+      d[(long)l * n1 + i] = c[l] * z;
+      p[(long)l * n1 + i] = (p[(long)l * n1 + i] - a[l] * p[(long)(l - 1) * n1 + i]) * z;
+    }
+  for (int l = n - 2; l >= 0; l--)
+    for (int i = 0; i < n1; i++) p[(long)l * n1 + i] = p[(long)l * n1 + i] - d[(long)l * n1 + i] * p[(long)(l + 1) * n1 + i];
+}
+
+static void solver(cpu_t *s) { /* solver.f90:20-80, one rank: no transposes */
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  double *wk = s->wk;
+  const int nmax = n1 > n2 ? n1 : n2;
+#pragma omp parallel
+  {
+    cpx *x = (cpx *)malloc(sizeof(cpx) * (size_t)nmax), *y = (cpx *)malloc(sizeof(cpx) * (size_t)nmax);
+#pragma omp for schedule(static)
+    for (int k = 0; k < n3; k++) {
+      double *pl = wk + (long)n1 * n2 * k;
+      for (int j = 0; j < n2; j++) memcpy(pl + (long)n1 * j, s->pp + IDX(s, 1, j + 1, k + 1), sizeof(double) * (size_t)n1);
+      for (int j = 0; j < n2; j += 2) r2hc_pair(&s->px, pl + (long)n1 * j, j + 1 < n2 ? pl + (long)n1 * (j + 1) : NULL, 1, x, y);
+      for (int i = 0; i < n1; i += 2) r2hc_pair(&s->py, pl + i, i + 1 < n1 ? pl + i + 1 : NULL, n1, x, y);
+    }
+    free(x); free(y);
+  }
+  /* gaussel_periodic, solver.f90:109-151 */
+#pragma omp parallel
+  {
+    const int n = n3;
+    size_t rowsz = (size_t)n1 * (size_t)n;
+    double *bb = (double *)malloc(sizeof(double) * rowsz), *p1 = (double *)malloc(sizeof(double) * rowsz),
+           *p2 = (double *)malloc(sizeof(double) * rowsz), *d = (double *)malloc(sizeof(double) * rowsz);
+#pragma omp for schedule(static)
+    for (int j = 0; j < n2; j++) {
+      for (int l = 0; l < n; l++)
+        for (int i = 0; i < n1; i++) {
+          bb[(long)l * n1 + i] = s->b[l] + s->lambdaxy[i + (long)n1 * j];
+          p1[(long)l * n1 + i] = wk[i + (long)n1 * (j + (long)n2 * l)];
+          p2[(long)l * n1 + i] = 0.0;
+        }
+      for (int i = 0; i < n1; i++) { p2[i] = -s->a[0]; p2[(long)(n - 2) * n1 + i] = -s->c[n - 2]; }
+      dgtsv_row(n1, n - 1, s->a, bb, s->c, p1, d, s->eps);
+      dgtsv_row(n1, n - 1, s->a, bb, s->c, p2, d, s->eps);
+      for (int i = 0; i < n1; i++) {
+        double pn = (p1[(long)(n - 1) * n1 + i] - s->c[n - 1] * p1[i] - s->a[n - 1] * p1[(long)(n - 2) * n1 + i]) /
+                    (bb[(long)(n - 1) * n1 + i] + s->c[n - 1] * p2[i] + s->a[n - 1] * p2[(long)(n - 2) * n1 + i] + s->eps);
+        wk[i + (long)n1 * (j + (long)n2 * (n - 1))] = pn;
+        for (int l = 0; l < n - 1; l++) wk[i + (long)n1 * (j + (long)n2 * l)] = p1[(long)l * n1 + i] + p2[(long)l * n1 + i] * pn;
+      }
+    }
+    free(bb); free(p1); free(p2); free(d);
+  }
+#pragma omp parallel
+  {
+    cpx *x = (cpx *)malloc(sizeof(cpx) * (size_t)nmax), *y = (cpx *)malloc(sizeof(cpx) * (size_t)nmax);
+#pragma omp for schedule(static)
+    for (int k = 0; k < n3; k++) {
+      double *pl = wk + (long)n1 * n2 * k;
+      for (int i = 0; i < n1; i += 2) hc2r_pair(&s->py, pl + i, i + 1 < n1 ? pl + i + 1 : NULL, n1, x, y);
+      for (int j = 0; j < n2; j += 2) hc2r_pair(&s->px, pl + (long)n1 * j, j + 1 < n2 ? pl + (long)n1 * (j + 1) : NULL, 1, x, y);
+      for (int j = 0; j < n2; j++) {
+        double *dst = s->pp + IDX(s, 1, j + 1, k + 1);
+        for (int i = 0; i < n1; i++) dst[i] = pl[(long)n1 * j + i] * s->normfft;
+      }
+    }
+    free(x); free(y);
+  }
+}
+
+static void correc(cpu_t *s, double dt) { /* correc.f90:41-67 (ghost rows included) */
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj, sk = s->sk;
+  const double factori = dt * s->dli[0], factorj = dt * s->dli[1];
+  const double *p = s->pp;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 0; k <= n3 + 1; k++)
+    for (int j = 0; j <= n2 + 1; j++) {
+      for (int i = 0; i <= n1 + 1; i++) {
+        const long c = IDX(s, i, j, k);
+        if (i <= n1) s->u[c] = s->u[c] - factori * (p[c + 1] - p[c]);
+        if (j <= n2) s->v[c] = s->v[c] - factorj * (p[c + sj] - p[c]);
+        if (k <= n3) s->w[c] = s->w[c] - dt * s->dzci[k] * (p[c + sk] - p[c]);
+      }
+    }
+}
+
+static void updatep(cpu_t *s) { /* updatep.f90:44-48 (explicit diffusion) */
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++)
+      for (int i = 1; i <= n1; i++) { const long c = IDX(s, i, j, k); s->p[c] = s->p[c] + s->pp[c]; }
+}
+
+/* ------------------------------------------------------------------------------------------------ API */
+void *cales_cpu_new(int n1, int n2, int n3, const double *l, double visc, const double *dzc, const double *dzf) {
+  cpu_t *s = (cpu_t *)calloc(1, sizeof(cpu_t));
+  s->n1 = n1; s->n2 = n2; s->n3 = n3; s->sj = n1 + 2; s->sk = (long)(n1 + 2) * (n2 + 2);
+  s->ntot = s->sk * (n3 + 2); s->nint = (long)n1 * n2 * n3;
+  int ng[3] = {n1, n2, n3};
+  for (int d = 0; d < 3; d++) { s->l[d] = l[d]; s->dl[d] = l[d] / (1. * ng[d]); s->dli[d] = 1. / s->dl[d]; } /* param.f90:152-153 */
+  s->visc = visc; s->eps = 2.220446049250313e-16; /* epsilon(1._rp), param.f90:20 */
+  size_t nz = (size_t)(n3 + 2);
+  s->dzc = (double *)malloc(8 * nz); s->dzf = (double *)malloc(8 * nz); s->dzci = (double *)malloc(8 * nz); s->dzfi = (double *)malloc(8 * nz);
+  for (int k = 0; k < n3 + 2; k++) { s->dzc[k] = dzc[k]; s->dzf[k] = dzf[k]; s->dzci[k] = 1. / dzc[k]; s->dzfi[k] = 1. / dzf[k]; }
+  double **f[] = {&s->u, &s->v, &s->w, &s->p, &s->pp, &s->visct, &s->s0};
+  for (int m = 0; m < 7; m++) *f[m] = (double *)calloc((size_t)s->ntot, 8);
+  for (int m = 0; m < 3; m++) { s->rhs[m] = (double *)calloc((size_t)s->nint, 8); s->rhso[m] = (double *)calloc((size_t)s->nint, 8); }
+  s->wk = (double *)calloc((size_t)s->nint, 8);
+  plan_init(&s->px, n1); plan_init(&s->py, n2);
+  /* initsolver.f90:17-64 with cbcpre = P/P/P, c_or_f = c,c,c: eigenvalues 66-78, tridmatrix 127-169, normfft fft.f90:99,136 */
+  const double pi = acos(-1.0);
+  double *lx = (double *)malloc(8 * (size_t)n1), *ly = (double *)malloc(8 * (size_t)n2);
+  for (int i = 0; i < n1; i++) lx[i] = -2. * (1. - cos((2 * i) * pi / (1. * n1))) * (s->dli[0] * s->dli[0]);
+  for (int j = 0; j < n2; j++) ly[j] = -2. * (1. - cos((2 * j) * pi / (1. * n2))) * (s->dli[1] * s->dli[1]);
+  s->lambdaxy = (double *)malloc(8 * (size_t)n1 * n2);
+  for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) s->lambdaxy[i + (long)n1 * j] = lx[i] + ly[j];
+  free(lx); free(ly);
+  s->a = (double *)malloc(8 * (size_t)n3); s->b = (double *)malloc(8 * (size_t)n3); s->c = (double *)malloc(8 * (size_t)n3);
+  for (int k = 1; k <= n3; k++) { s->a[k - 1] = s->dzfi[k] * s->dzci[k - 1]; s->c[k - 1] = s->dzfi[k] * s->dzci[k]; s->b[k - 1] = -(s->a[k - 1] + s->c[k - 1]); }
+  s->normfft = 1. / ((1. * (n1 + 0.)) * (1. * (n2 + 0.)));
+  return s;
+}
+
+double *cales_cpu_field(void *h, int which) { /* 0 u, 1 v, 2 w, 3 p, 4 pp, 5 visct, 6 s0 */
+  cpu_t *s = (cpu_t *)h;
+  double *f[] = {s->u, s->v, s->w, s->p, s->pp, s->visct, s->s0};
+  return (which >= 0 && which < 7) ? f[which] : NULL;
+}
+
+double *cales_cpu_lambdaxy(void *h) { return ((cpu_t *)h)->lambdaxy; }
+
+/* main.f90:370-375: ghost fill of the initial fields and the first eddy viscosity */
+void cales_cpu_start(void *h) {
+  cpu_t *s = (cpu_t *)h;
+  bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w); bound_periodic(s, s->p);
+  cmpt_sgs_smag(s); bound_periodic(s, s->visct);
+}
+
+void cales_cpu_cmpt_sgs(void *h) { cmpt_sgs_smag((cpu_t *)h); }
+void cales_cpu_boundp(void *h, int which) { bound_periodic((cpu_t *)h, cales_cpu_field(h, which)); }
+void cales_cpu_solver(void *h) { solver((cpu_t *)h); }
+void cales_cpu_fillps(void *h, double dti) { fillps((cpu_t *)h, dti); }
+void cales_cpu_correc(void *h, double dt) { correc((cpu_t *)h, dt); }
+void cales_cpu_rk(void *h, int irk, double dt) { rk_substep((cpu_t *)h, RKCOEFF[irk], dt); }
+
+/* one time step = 3 substeps, main.f90:417-507 */
+void cales_cpu_step(void *h, double dt) {
+  cpu_t *s = (cpu_t *)h;
+  for (int irk = 0; irk < 3; irk++) {
+    const double dtrk = (RKCOEFF[irk][0] + RKCOEFF[irk][1]) * dt, dtrki = 1. / dtrk;
+    rk_substep(s, RKCOEFF[irk], dt);                                             /* main.f90:420 */
+    bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w);   /* 493 */
+    fillps(s, dtrki);                                                            /* 495 (updt_rhs_b: nothing for P) */
+    solver(s);                                                                   /* 497 */
+    bound_periodic(s, s->pp);                                                    /* 498 */
+    correc(s, dtrk);                                                             /* 499 */
+    bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w);   /* 500 */
+    updatep(s);                                                                  /* 502 */
+    bound_periodic(s, s->p);                                                     /* 503 */
+    cmpt_sgs_smag(s);                                                            /* 504 */
+    bound_periodic(s, s->visct);                                                 /* 506 */
+  }
+}
+
+/* chkdiv.f90:27-47 (max part; the sum is order dependent and left to the numpy oracle) */
+double cales_cpu_divmax(void *h) {
+  cpu_t *s = (cpu_t *)h;
+  double mx = 0.;
+#pragma omp parallel for collapse(2) reduction(max : mx) schedule(static)
+  for (int k = 1; k <= s->n3; k++)
+    for (int j = 1; j <= s->n2; j++)
+      for (int i = 1; i <= s->n1; i++) {
+        const long c = IDX(s, i, j, k);
+        double div = (s->w[c] - s->w[c - s->sk]) * s->dzfi[k] + (s->v[c] - s->v[c - s->sj]) * s->dli[1] + (s->u[c] - s->u[c - 1]) * s->dli[0];
+        if (fabs(div) > mx) mx = fabs(div);
+      }
+  return mx;
+}
+
+/* chkdt.f90:40-97, explicit diffusion */
+double cales_cpu_chkdt(void *h) {
+  cpu_t *s = (cpu_t *)h;
+  const long sj = s->sj, sk = s->sk;
+  const double dxi = 1. / s->dl[0], dyi = 1. / s->dl[1], dl2i = dxi * dxi + dyi * dyi, visc = s->visc;
+  const double *u = s->u, *v = s->v, *w = s->w, *t = s->visct;
+  double dti = 0., dtid = 0.;
+#pragma omp parallel for collapse(2) reduction(max : dti, dtid) schedule(static)
+  for (int k = 1; k <= s->n3; k++)
+    for (int j = 1; j <= s->n2; j++)
+      for (int i = 1; i <= s->n1; i++) {
+        const long c = IDX(s, i, j, k);
+        const double dzfi_k = s->dzfi[k], dzci_k = s->dzci[k];
+        double ux = fabs(u[c]), vx = 0.25 * fabs(v[c] + v[c - sj] + v[c + 1] + v[c + 1 - sj]), wx = 0.25 * fabs(w[c] + w[c - sk] + w[c + 1] + w[c + 1 - sk]);
+        double uy = 0.25 * fabs(u[c] + u[c + sj] + u[c - 1 + sj] + u[c - 1]), vy = fabs(v[c]), wy = 0.25 * fabs(w[c] + w[c + sj] + w[c + sj - sk] + w[c - sk]);
+        double uz = 0.25 * fabs(u[c] + u[c - 1] + u[c - 1 + sk] + u[c + sk]), vz = 0.25 * fabs(v[c] + v[c - sj] + v[c - sj + sk] + v[c + sk]), wz = fabs(w[c]);
+        double dtix = ux * dxi + vx * dyi + wx * dzfi_k, dtiy = uy * dxi + vy * dyi + wy * dzfi_k, dtiz = uz * dxi + vz * dyi + wz * dzci_k;
+        double m = fmax(dtix, fmax(dtiy, dtiz)); if (m > dti) dti = m;
+        double dtidx = 0.5 * (t[c] + t[c + 1]) * (dl2i + dzfi_k * dzfi_k) + visc * dl2i + visc * (dzfi_k * dzfi_k);
+        double dtidy = 0.5 * (t[c] + t[c + sj]) * (dl2i + dzfi_k * dzfi_k) + visc * dl2i + visc * (dzfi_k * dzfi_k);
+        double dtidz = 0.5 * (t[c] + t[c + sk]) * (dl2i + dzci_k * dzci_k) + visc * dl2i + visc * (dzci_k * dzci_k);
+        m = fmax(dtidx, fmax(dtidy, dtidz)); if (m > dtid) dtid = m;
+      }
+  if (dti == 0.) dti = 1.;
+  if (dtid == 0.) dtid = s->eps;
+  return fmin(0.4125 / dtid, 1.732 / dti);
+}
+
+int cales_cpu_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+void cales_cpu_free(void *h) {
+  cpu_t *s = (cpu_t *)h;
+  if (!s) return;
+  double *f[] = {s->u, s->v, s->w, s->p, s->pp, s->visct, s->s0, s->wk, s->dzc, s->dzf, s->dzci, s->dzfi, s->a, s->b, s->c, s->lambdaxy};
+  for (size_t m = 0; m < sizeof(f) / sizeof(f[0]); m++) free(f[m]);
+  for (int m = 0; m < 3; m++) { free(s->rhs[m]); free(s->rhso[m]); }
+  free(s->px.tw); free(s->py.tw); free(s);
+}

@@ -1,0 +1,87 @@
+"""ctypes front end of oracle/c/libcales_cpu.so -- the C/OpenMP restatement of the tri-periodic, explicit,
+static-Smagorinsky RK3 step (see the header of oracle/c/cales_cpu.c for the reference lines it follows).
+TEST INFRASTRUCTURE ONLY: the checker in tests/ and the CPU arm of bench.py."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_LIB = None
+FIELDS = {"u": 0, "v": 1, "w": 2, "p": 3, "pp": 4, "visct": 5, "s0": 6}
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "c", "libcales_cpu.so")
+        if not os.path.exists(path):
+            raise RuntimeError("oracle/c/libcales_cpu.so is missing: run `make -C oracle/c` (or __graft_entry__.build())")
+        lib = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        lib.cales_cpu_new.restype = C.c_void_p
+        lib.cales_cpu_new.argtypes = [C.c_int, C.c_int, C.c_int, dp, C.c_double, dp, dp]
+        lib.cales_cpu_field.restype = dp
+        lib.cales_cpu_field.argtypes = [C.c_void_p, C.c_int]
+        lib.cales_cpu_lambdaxy.restype = dp
+        lib.cales_cpu_lambdaxy.argtypes = [C.c_void_p]
+        for nm in ("start", "cmpt_sgs", "solver", "free"):
+            getattr(lib, "cales_cpu_" + nm).argtypes = [C.c_void_p]
+            getattr(lib, "cales_cpu_" + nm).restype = None
+        lib.cales_cpu_boundp.argtypes = [C.c_void_p, C.c_int]; lib.cales_cpu_boundp.restype = None
+        for nm in ("fillps", "correc", "step"):
+            getattr(lib, "cales_cpu_" + nm).argtypes = [C.c_void_p, C.c_double]
+            getattr(lib, "cales_cpu_" + nm).restype = None
+        lib.cales_cpu_rk.argtypes = [C.c_void_p, C.c_int, C.c_double]; lib.cales_cpu_rk.restype = None
+        lib.cales_cpu_divmax.argtypes = [C.c_void_p]; lib.cales_cpu_divmax.restype = C.c_double
+        lib.cales_cpu_chkdt.argtypes = [C.c_void_p]; lib.cales_cpu_chkdt.restype = C.c_double
+        lib.cales_cpu_threads.restype = C.c_int
+        _LIB = lib
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class CSim:
+    """Mirror of oracle.main.Sim for an all-periodic 'smag' deck on one rank, backed by the C library."""
+
+    def __init__(self, deck):
+        from .initflow import initflow
+        from .initgrid import initgrid
+        assert (deck.cbcvel == "P").all() and deck.sgstype == "smag" and not deck.impdiff and tuple(deck.dims) == (1, 1)
+        self.lib = load()
+        self.deck = deck
+        n = self.n = tuple(int(x) for x in deck.ng)
+        dzc, dzf, zc, zf = initgrid(deck.gtype, n[2], deck.gr, deck.l[2])
+        l = np.array(deck.l, dtype=np.float64)
+        self.h = C.c_void_p(self.lib.cales_cpu_new(n[0], n[1], n[2], _dp(l), float(deck.visc), _dp(np.ascontiguousarray(dzc)),
+                                                   _dp(np.ascontiguousarray(dzf))))
+        shp = (n[0] + 2, n[1] + 2, n[2] + 2)
+        self.f = {nm: np.ctypeslib.as_array(self.lib.cales_cpu_field(self.h, i), shape=shp[::-1]).T for nm, i in FIELDS.items()}
+        u, v, w, p = initflow(deck, (1, 1, 1), n, zc, zf, dzc, dzf)
+        for nm, a in (("u", u), ("v", v), ("w", w), ("p", p)):
+            self.f[nm][...] = a
+        self.lib.cales_cpu_start(self.h)                                # main.f90:370-375
+        self.dt_cfl = self.lib.cales_cpu_chkdt(self.h)                  # main.f90:395-398
+        self.dt = deck.dt_f if deck.dt_f > 0. else min(deck.cfl * self.dt_cfl, deck.dtmax)
+        self.istep = 0
+
+    def step(self, icheck=0):
+        self.istep += 1
+        self.lib.cales_cpu_step(self.h, self.dt)
+        if icheck > 0 and self.istep % icheck == 0:
+            self.dt_cfl = self.lib.cales_cpu_chkdt(self.h)
+            d = self.deck
+            self.dt = d.dt_f if d.dt_f > 0. else min(d.cfl * self.dt_cfl, d.dtmax)
+            return self.lib.cales_cpu_divmax(self.h)
+        return None
+
+    def threads(self):
+        return int(self.lib.cales_cpu_threads())
+
+    def close(self):
+        if self.h:
+            self.f = {}
+            self.lib.cales_cpu_free(self.h)
+            self.h = None
