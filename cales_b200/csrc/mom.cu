@@ -20,35 +20,35 @@
 //     it commutes with rounding, so it is folded into the metric factor of the difference, 0.25*dxi etc. (exact unless a
 //     flux underflows, |flux| < 2^-1020).
 // The association order of everything else is the reference's; the library is built with -fmad=false.
-template <int MODE>  // 0 explicit, 1 _IMPDIFF, 2 _IMPDIFF + _IMPDIFF_1D
+template <int MODE, bool V16>  // MODE 0 explicit, 1 _IMPDIFF, 2 _IMPDIFF + _IMPDIFF_1D; V16: 16-byte plane staging (tile.cuh)
 __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci, const double* __restrict__ dzfi,
                                                     double visc, const double* __restrict__ u, const double* __restrict__ v,
                                                     const double* __restrict__ w, const double* __restrict__ s,
                                                     double* __restrict__ dudt, double* __restrict__ dvdt, double* __restrict__ dwdt,
                                                     double* __restrict__ dudtd, double* __restrict__ dvdtd, double* __restrict__ dwdtd, int kc) {
-  extern __shared__ double smem[];   // [3 slots][4 fields][PLANE]: planes k, k+1 in use, k+2 in flight
+  extern __shared__ __align__(16) double smem[];   // [4 slots][4 fields][PLANE]: planes k, k+1 in use, k+2 and k+3 in flight
   const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
-  const double* const fld[4] = {u, v, w, s};
-  const Stage st = make_stage(d, i0, j0);
-  tile_issue<4>(st, d, fld, smem, k0 - 1, 0);
-  tile_issue<4>(st, d, fld, smem, k0, 1);
-  tile_issue<4>(st, d, fld, smem, k0 + 1, 2);
-  tile_wait_all();
+  Stager<4, V16> st(d, i0, j0, u, v, w, s, smem, k0 - 1, k1 + 1);
+  st.template issue<0>();
+  st.template issue<1>();
+  st.template issue<2>();
+  st.template issue<3>();
+  tile_wait_1();
   __syncthreads();
   const bool active = i <= d.n1 && j <= d.n2;
-  const int c = (threadIdx.x + 1) + PX * (threadIdx.y + 1);
+  const double* const sm = smem + (threadIdx.x + 1) + PX * (threadIdx.y + 1);     // my cell in field 0 of slot 0
+  constexpr int SL = 4 * PLANE;
   const long n12 = (long)d.n1 * d.n2;
   const double qdxi = 0.25 * dxi, qdyi = 0.25 * dyi;
   // k-1/2 quantities of level k0 = k+1/2 quantities of level k0-1 (planes k0-1, k0 = slots 0, 1)
-  double wu_km = 0., dudz_km = 0., sxz_km = 0., wv_km = 0., dvdz_km = 0., syz_km = 0., ww_km = 0., dwdz_km = 0., fzz_km = 0.;
-  double s_ccm = 0., s_pcm = 0., s_cpm = 0.;
-  if (active) {
-    const double* uc = smem + 0 * PLANE; const double* vc = smem + 1 * PLANE; const double* wc = smem + 2 * PLANE; const double* sc = smem + 3 * PLANE;
-    const double* up = uc + 4 * PLANE; const double* vp = vc + 4 * PLANE; const double* wp = wc + 4 * PLANE; const double* sp = sc + 4 * PLANE;
+  double wu_km, dudz_km, sxz_km, wv_km, dvdz_km, syz_km, ww_km, dwdz_km, fzz_km, s_ccm, s_pcm, s_cpm;
+  {
+    const double* uc = sm; const double* vc = sm + PLANE; const double* wc = sm + 2 * PLANE; const double* sc = sm + 3 * PLANE;
+    const double* up = uc + SL; const double* vp = vc + SL; const double* wp = wc + SL; const double* sp = sc + SL;
     const double dzci_m = dzci[k0 - 1], dzfi_k = dzfi[k0];
-    const double u_ccc = uc[c], u_ccp = up[c], v_ccc = vc[c], v_ccp = vp[c], w_ccc = wc[c], w_pcc = wc[c + 1], w_cpc = wc[c + PX], w_ccp = wp[c];
+    const double u_ccc = uc[0], u_ccp = up[0], v_ccc = vc[0], v_ccp = vp[0], w_ccc = wc[0], w_pcc = wc[1], w_cpc = wc[PX], w_ccp = wp[0];
     wu_km = (w_pcc + w_ccc) * (u_ccc + u_ccp);
     dudz_km = (u_ccp - u_ccc) * dzci_m;
     sxz_km = dudz_km + (w_pcc - w_ccc) * dxi;
@@ -57,27 +57,30 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
     syz_km = dvdz_km + (w_cpc - w_ccc) * dyi;
     ww_km = (w_ccc + w_ccp) * (w_ccc + w_ccp);
     dwdz_km = (w_ccp - w_ccc) * dzfi_k;
-    fzz_km = sp[c] * (dwdz_km + dwdz_km);
-    s_ccm = sc[c]; s_pcm = sc[c + 1]; s_cpm = sc[c + PX];
+    fzz_km = sp[0] * (dwdz_km + dwdz_km);
+    s_ccm = sc[0]; s_pcm = sc[1]; s_cpm = sc[PX];
   }
   __syncthreads();                   // slot 0 (plane k0-1) may now be overwritten
-  int sl_c = 1, sl_p = 2, sl_n = 0;  // slots of planes k, k+1 and of the plane to prefetch (k+2)
-  for (int k = k0; k <= k1; ++k) {
-    const bool more = k < k1;
-    if (more) tile_issue<4>(st, d, fld, smem, k + 2, sl_n);     // in flight while plane k is computed (k+2 <= n3+1)
-    if (active) {
-      const double* uc = smem + (sl_c * 4 + 0) * PLANE; const double* up = smem + (sl_p * 4 + 0) * PLANE;
-      const double* vc = smem + (sl_c * 4 + 1) * PLANE; const double* vp = smem + (sl_p * 4 + 1) * PLANE;
-      const double* wc = smem + (sl_c * 4 + 2) * PLANE; const double* wp = smem + (sl_p * 4 + 2) * PLANE;
-      const double* sc = smem + (sl_c * 4 + 3) * PLANE; const double* sp = smem + (sl_p * 4 + 3) * PLANE;
-      const double u_cmc = uc[c - PX], u_mcc = uc[c - 1], u_ccc = uc[c], u_pcc = uc[c + 1], u_mpc = uc[c - 1 + PX], u_cpc = uc[c + PX];
-      const double u_mcp = up[c - 1], u_ccp = up[c];
-      const double v_cmc = vc[c - PX], v_pmc = vc[c + 1 - PX], v_mcc = vc[c - 1], v_ccc = vc[c], v_pcc = vc[c + 1], v_cpc = vc[c + PX];
-      const double v_cmp = vp[c - PX], v_ccp = vp[c];
-      const double w_cmc = wc[c - PX], w_mcc = wc[c - 1], w_ccc = wc[c], w_pcc = wc[c + 1], w_cpc = wc[c + PX], w_ccp = wp[c];
-      const double s_cmc = sc[c - PX], s_pmc = sc[c + 1 - PX], s_mcc = sc[c - 1], s_ccc = sc[c], s_pcc = sc[c + 1], s_mpc = sc[c - 1 + PX],
-                   s_cpc = sc[c + PX], s_ppc = sc[c + 1 + PX];
-      const double s_cmp = sp[c - PX], s_mcp = sp[c - 1], s_ccp = sp[c], s_pcp = sp[c + 1], s_cpp = sp[c + PX];
+  long o = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k0 - 1);   // dudt(n1,n2,n3): no halo
+  int k = k0;
+  // one level: planes k, k+1 in slots SC, SP; plane k+3 goes into slot SN (which held plane k-1).  Threads outside the
+  // array compute on whatever their tile cells hold and store nothing.
+  auto step = [&](auto sc_, auto sp_, auto sn_) {
+    constexpr int SC = decltype(sc_)::v, SP = decltype(sp_)::v, SN = decltype(sn_)::v;
+    st.template issue<SN>();
+    {
+      const double* uc = sm + SC * SL; const double* up = sm + SP * SL;
+      const double* vc = uc + PLANE; const double* vp = up + PLANE;
+      const double* wc = uc + 2 * PLANE; const double* wp = up + 2 * PLANE;
+      const double* sc = uc + 3 * PLANE; const double* sp = up + 3 * PLANE;
+      const double u_cmc = uc[-PX], u_mcc = uc[-1], u_ccc = uc[0], u_pcc = uc[1], u_mpc = uc[PX - 1], u_cpc = uc[PX];
+      const double u_mcp = up[-1], u_ccp = up[0];
+      const double v_cmc = vc[-PX], v_pmc = vc[1 - PX], v_mcc = vc[-1], v_ccc = vc[0], v_pcc = vc[1], v_cpc = vc[PX];
+      const double v_cmp = vp[-PX], v_ccp = vp[0];
+      const double w_cmc = wc[-PX], w_mcc = wc[-1], w_ccc = wc[0], w_pcc = wc[1], w_cpc = wc[PX], w_ccp = wp[0];
+      const double s_cmc = sc[-PX], s_pmc = sc[1 - PX], s_mcc = sc[-1], s_ccc = sc[0], s_pcc = sc[1], s_mpc = sc[PX - 1],
+                   s_cpc = sc[PX], s_ppc = sc[1 + PX];
+      const double s_cmp = sp[-PX], s_mcp = sp[-1], s_ccp = sp[0], s_pcp = sp[1], s_cpp = sp[PX];
       const double dzci_k = dzci[k], dzfi_k = dzfi[k], dzfi_kp = dzfi[k + 1];
       const double qdzfi_k = 0.25 * dzfi_k, qdzci_k = 0.25 * dzci_k;
       // ---- face/edge quantities on the + side of this cell (shared with the neighbour at k+1 through the carry,
@@ -141,29 +144,33 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
                             ((sz + s_pcc + s_pcp) * sxz_p - (sz + s_mcc + s_mcp) * (dwdx_im + dudz_im)) * qdxi +
                             ((sz + s_cpc + s_cpp) * syz_p - (sz + s_cmc + s_cmp) * (dwdy_jm + dvdz_jm)) * qdyi +
                             (fzz_kp - fzz_km) * dzci_k;
-      const long o = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k - 1);   // dudt(n1,n2,n3): no halo
-      if (MODE == 0) {                                                    // mom.f90:296-302
-        dudt[o] = dudt_s + dudtd_xy_s + dudtd_z_s;
-        dvdt[o] = dvdt_s + dvdtd_xy_s + dvdtd_z_s;
-        dwdt[o] = dwdt_s + dwdtd_xy_s + dwdtd_z_s;
-      } else if (MODE == 1) {                                             // mom.f90:286-295
-        dudt[o] = dudt_s; dvdt[o] = dvdt_s; dwdt[o] = dwdt_s;
-        dudtd[o] = dudtd_xy_s + dudtd_z_s;
-        dvdtd[o] = dvdtd_xy_s + dvdtd_z_s;
-        dwdtd[o] = dwdtd_xy_s + dwdtd_z_s;
-      } else {                                                            // mom.f90:278-284
-        dudt[o] = dudt_s + dudtd_xy_s; dvdt[o] = dvdt_s + dvdtd_xy_s; dwdt[o] = dwdt_s + dwdtd_xy_s;
-        dudtd[o] = dudtd_z_s; dvdtd[o] = dvdtd_z_s; dwdtd[o] = dwdtd_z_s;
+      if (active) {
+        if (MODE == 0) {                                                    // mom.f90:296-302
+          dudt[o] = dudt_s + dudtd_xy_s + dudtd_z_s;
+          dvdt[o] = dvdt_s + dvdtd_xy_s + dvdtd_z_s;
+          dwdt[o] = dwdt_s + dwdtd_xy_s + dwdtd_z_s;
+        } else if (MODE == 1) {                                             // mom.f90:286-295
+          dudt[o] = dudt_s; dvdt[o] = dvdt_s; dwdt[o] = dwdt_s;
+          dudtd[o] = dudtd_xy_s + dudtd_z_s;
+          dvdtd[o] = dvdtd_xy_s + dvdtd_z_s;
+          dwdtd[o] = dwdtd_xy_s + dwdtd_z_s;
+        } else {                                                            // mom.f90:278-284
+          dudt[o] = dudt_s + dudtd_xy_s; dvdt[o] = dvdt_s + dvdtd_xy_s; dwdt[o] = dwdt_s + dwdtd_xy_s;
+          dudtd[o] = dudtd_z_s; dvdtd[o] = dvdtd_z_s; dwdtd[o] = dwdtd_z_s;
+        }
       }
       wu_km = uw_p; dudz_km = dudz_kp; sxz_km = sxz_p;
       wv_km = vw_p; dvdz_km = dvdz_kp; syz_km = syz_p;
       ww_km = ww_kp; dwdz_km = dwdz_kp; fzz_km = fzz_kp;
       s_ccm = s_ccc; s_pcm = s_pcc; s_cpm = s_cpc;
     }
-    tile_wait_all();
-    __syncthreads();                 // plane k+2 has landed; everyone is done reading plane k
-    const int tmp = sl_c; sl_c = sl_p; sl_p = sl_n; sl_n = tmp;
-  }
+    tile_wait_1();                   // plane k+2 has landed (k+3 may still be in flight)
+    __syncthreads();                 // ... for everyone, and everyone is done reading plane k
+    o += n12;
+    return ++k <= k1;
+  };
+  while (step(Slot<1>{}, Slot<2>{}, Slot<0>{}) && step(Slot<2>{}, Slot<3>{}, Slot<1>{}) && step(Slot<3>{}, Slot<0>{}, Slot<2>{}) &&
+         step(Slot<0>{}, Slot<1>{}, Slot<3>{})) {}
 }
 
 static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, const double* dzci, const double* dzfi, double visc,
@@ -173,13 +180,13 @@ static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, co
   long cols = (long)cdiv(n[0], TX) * cdiv(n[1], TY);
   const int kc = pick_chunk(cols, n[2], 148 * 2, 12, 2);
   dim3 g(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc)), b(TX, TY);
-  const size_t sh = 12 * PLANE * sizeof(double);
-  if (ctx->diffusion == CALES_DIFF_EXPLICIT)
-    mom_k<0><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc);
-  else if (ctx->diffusion == CALES_DIFF_IMPLICIT_3D)
-    mom_k<1><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc);
-  else
-    mom_k<2><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc);
+  const size_t sh = TSLOTS * 4 * PLANE * sizeof(double);
+  const bool v16 = tile_v16(n[0], u, v, w, visct);
+#define MOM_GO(M_, V_) mom_k<M_, V_><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc)
+  if (ctx->diffusion == CALES_DIFF_EXPLICIT) { if (v16) MOM_GO(0, true); else MOM_GO(0, false); }
+  else if (ctx->diffusion == CALES_DIFF_IMPLICIT_3D) { if (v16) MOM_GO(1, true); else MOM_GO(1, false); }
+  else { if (v16) MOM_GO(2, true); else MOM_GO(2, false); }
+#undef MOM_GO
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }

@@ -94,52 +94,55 @@ __device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, i
 // one barrier per plane).  The four k-1/2 terms of s13 and of s23 at level k are the k+1/2 terms of level k-1 (same
 // expression, same bits): they are carried in registers, so plane k-1 is never read.  The eight-term sums keep the
 // reference's order.
-template <int SIJ, int SMAG>
+template <int SIJ, int SMAG, bool V16>
 __global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
                                                     const double* __restrict__ dzfi, const double* __restrict__ u,
                                                     const double* __restrict__ v, const double* __restrict__ w,
                                                     double* __restrict__ s0, Ptr6 sij, double* __restrict__ s0copy, int kc, SmagArgs A,
                                                     double* __restrict__ visct) {
-  extern __shared__ double smem[];   // [3 slots][3 fields][PLANE]
+  extern __shared__ __align__(16) double smem[];   // [4 slots][3 fields][PLANE]
   const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
-  const double* const fld[3] = {u, v, w};
-  const Stage st = make_stage(d, i0, j0);
-  tile_issue<3>(st, d, fld, smem, k0 - 1, 0);
-  tile_issue<3>(st, d, fld, smem, k0, 1);
-  tile_issue<3>(st, d, fld, smem, k0 + 1, 2);
-  tile_wait_all();
+  Stager<3, V16> st(d, i0, j0, u, v, w, nullptr, smem, k0 - 1, k1 + 1);
+  st.template issue<0>();
+  st.template issue<1>();
+  st.template issue<2>();
+  st.template issue<3>();
+  tile_wait_1();
   __syncthreads();
   const bool active = i <= d.n1 && j <= d.n2;
-  const int c = (threadIdx.x + 1) + PX * (threadIdx.y + 1);
+  const double* const sm = smem + (threadIdx.x + 1) + PX * (threadIdx.y + 1);     // my cell in field 0 of slot 0
+  constexpr int SL = 3 * PLANE;
   // k+1/2 terms of level k0-1 (planes k0-1, k0 = slots 0, 1)
   double a_uz = 0., a_wx = 0., a_uzm = 0., a_wxm = 0., b_vz = 0., b_wy = 0., b_vzm = 0., b_wym = 0., w_ccm = 0.;
   if (active) {
-    const double* uc = smem; const double* vc = smem + PLANE; const double* wc = smem + 2 * PLANE;
-    const double* up = uc + 3 * PLANE; const double* vp = vc + 3 * PLANE;
+    const double* uc = sm; const double* vc = sm + PLANE; const double* wc = sm + 2 * PLANE;
+    const double* up = uc + SL; const double* vp = vc + SL;
     const double dz = dzci[k0 - 1];
-    const double w_ccc = wc[c];
-    a_uz = (up[c] - uc[c]) * dz;          a_wx = (wc[c + 1] - w_ccc) * dxi;
-    a_uzm = (up[c - 1] - uc[c - 1]) * dz; a_wxm = (w_ccc - wc[c - 1]) * dxi;
-    b_vz = (vp[c] - vc[c]) * dz;          b_wy = (wc[c + PX] - w_ccc) * dyi;
-    b_vzm = (vp[c - PX] - vc[c - PX]) * dz; b_wym = (w_ccc - wc[c - PX]) * dyi;
+    const double w_ccc = wc[0];
+    a_uz = (up[0] - uc[0]) * dz;          a_wx = (wc[1] - w_ccc) * dxi;
+    a_uzm = (up[-1] - uc[-1]) * dz;       a_wxm = (w_ccc - wc[-1]) * dxi;
+    b_vz = (vp[0] - vc[0]) * dz;          b_wy = (wc[PX] - w_ccc) * dyi;
+    b_vzm = (vp[-PX] - vc[-PX]) * dz;     b_wym = (w_ccc - wc[-PX]) * dyi;
     w_ccm = w_ccc;
   }
   __syncthreads();
-  int sl_c = 1, sl_p = 2, sl_n = 0;
   long o = d.idx(i, j, k0);
-  for (int k = k0; k <= k1; ++k, o += d.s2) {
-    if (k < k1) tile_issue<3>(st, d, fld, smem, k + 2, sl_n);
-    if (active) {
-      const double* uc = smem + (sl_c * 3 + 0) * PLANE; const double* up = smem + (sl_p * 3 + 0) * PLANE;
-      const double* vc = smem + (sl_c * 3 + 1) * PLANE; const double* vp = smem + (sl_p * 3 + 1) * PLANE;
-      const double* wc = smem + (sl_c * 3 + 2) * PLANE;
-      const double u_mmc = uc[c - 1 - PX], u_cmc = uc[c - PX], u_mcc = uc[c - 1], u_ccc = uc[c], u_mpc = uc[c - 1 + PX], u_cpc = uc[c + PX];
-      const double u_mcp = up[c - 1], u_ccp = up[c];
-      const double v_mmc = vc[c - 1 - PX], v_cmc = vc[c - PX], v_pmc = vc[c + 1 - PX], v_mcc = vc[c - 1], v_ccc = vc[c], v_pcc = vc[c + 1];
-      const double v_cmp = vp[c - PX], v_ccp = vp[c];
-      const double w_cmc = wc[c - PX], w_mcc = wc[c - 1], w_ccc = wc[c], w_pcc = wc[c + 1], w_cpc = wc[c + PX];
+  int k = k0;
+  // one level: planes k, k+1 in slots SC, SP; plane k+3 goes into slot SN (which held plane k-1)
+  auto step = [&](auto sc_, auto sp_, auto sn_) {
+    constexpr int SC = decltype(sc_)::v, SP = decltype(sp_)::v, SN = decltype(sn_)::v;
+    st.template issue<SN>();
+    {   // threads outside the array compute on whatever their tile cells hold and store nothing
+      const double* uc = sm + SC * SL; const double* up = sm + SP * SL;
+      const double* vc = uc + PLANE; const double* vp = up + PLANE;
+      const double* wc = uc + 2 * PLANE;
+      const double u_mmc = uc[-1 - PX], u_cmc = uc[-PX], u_mcc = uc[-1], u_ccc = uc[0], u_mpc = uc[-1 + PX], u_cpc = uc[PX];
+      const double u_mcp = up[-1], u_ccp = up[0];
+      const double v_mmc = vc[-1 - PX], v_cmc = vc[-PX], v_pmc = vc[1 - PX], v_mcc = vc[-1], v_ccc = vc[0], v_pcc = vc[1];
+      const double v_cmp = vp[-PX], v_ccp = vp[0];
+      const double w_cmc = wc[-PX], w_mcc = wc[-1], w_ccc = wc[0], w_pcc = wc[1], w_cpc = wc[PX];
       const double dzci_k = dzci[k];
       const double s11 = (u_ccc - u_mcc) * dxi;
       const double s22 = (v_ccc - v_cmc) * dyi;
@@ -152,11 +155,11 @@ __global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double
       const double s23 = .125 * (n_vz + n_wy + b_vz + b_wy + n_vzm + n_wym + b_vzm + b_wym);
       const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
       if (SMAG) {                                          // visct = (c_smag*del*fd)**2*s0   (sgs.f90:150)
-        const double fd = A.any_wall ? van_driest(d, A, i, j, k) : 1.;
+        const double fd = (A.any_wall && active) ? van_driest(d, A, i, j, k) : 1.;
         const double t = CSMAG * A.delk[k] * fd;
-        visct[o] = t * t * s;
-      } else s0[o] = s;
-      if (SIJ) {
+        if (active) visct[o] = t * t * s;
+      } else if (active) s0[o] = s;
+      if (SIJ && active) {
         sij.p[0][o] = s11; sij.p[1][o] = s22; sij.p[2][o] = s33; sij.p[3][o] = s12; sij.p[4][o] = s13; sij.p[5][o] = s23;
         if (s0copy) s0copy[o] = s;
       }
@@ -164,13 +167,16 @@ __global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double
       b_vz = n_vz; b_wy = n_wy; b_vzm = n_vzm; b_wym = n_wym;
       w_ccm = w_ccc;
     }
-    tile_wait_all();
-    __syncthreads();
-    const int tmp = sl_c; sl_c = sl_p; sl_p = sl_n; sl_n = tmp;
-  }
+    tile_wait_1();                   // plane k+2 has landed (k+3 may still be in flight)
+    __syncthreads();                 // ... for everyone, and everyone is done reading plane k
+    o += d.s2;
+    return ++k <= k1;
+  };
+  while (step(Slot<1>{}, Slot<2>{}, Slot<0>{}) && step(Slot<2>{}, Slot<3>{}, Slot<1>{}) && step(Slot<3>{}, Slot<0>{}, Slot<2>{}) &&
+         step(Slot<0>{}, Slot<1>{}, Slot<3>{})) {}
 }
 
-#define STRAIN_SMEM (9 * PLANE * sizeof(double))
+#define STRAIN_SMEM (TSLOTS * 3 * PLANE * sizeof(double))
 static inline dim3 strain_grid(const int n[3], int& kc) {
   kc = pick_chunk((long)cdiv(n[0], TX) * cdiv(n[1], TY), n[2], 148 * 3, 12, 2);
   return dim3(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc));
@@ -184,8 +190,11 @@ static int strain_launch(cales_ctx* ctx, const int n[3], const double dli[3], co
   Ptr6 P;
   for (int m = 0; m < 6; ++m) P.p[m] = sij ? sij[m] : nullptr;
   SmagArgs none{};
-  if (sij) strain_k<1, 0><<<g, b, STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, s0copy, kc, none, nullptr);
-  else strain_k<0, 0><<<g, b, STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, nullptr, kc, none, nullptr);
+  const bool v16 = tile_v16(n[0], u, v, w);
+#define STRAIN_GO(SIJ_, V_, S0C_) strain_k<SIJ_, 0, V_><<<g, b, STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, S0C_, kc, none, nullptr)
+  if (sij) { if (v16) STRAIN_GO(1, true, s0copy); else STRAIN_GO(1, false, s0copy); }
+  else { if (v16) STRAIN_GO(0, true, nullptr); else STRAIN_GO(0, false, nullptr); }
+#undef STRAIN_GO
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
@@ -441,7 +450,10 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
     Ptr6 P{};
     int kcs;
     const dim3 gs = strain_grid(n, kcs);
-    strain_k<0, 1><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);
+    if (tile_v16(n[0], us, vs, ws))
+      strain_k<0, 1, true><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);
+    else
+      strain_k<0, 1, false><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);
     KERNEL_CHECK(ctx);
     return CALES_OK;
   }

@@ -1,7 +1,14 @@
 // Plane staging for the z-marching stencil kernels (mom_k, strain_k): a CTA owns a TX x TY tile of (i,j)
 // columns; whole (TX+2) x (TY+2) planes of NF haloed fields are copied global -> shared with cp.async
-// (no register staging), into a ring of three slots: planes k and k+1 in use, plane k+2 in flight.
+// (no register staging) into a ring of FOUR slots: planes k and k+1 in use, planes k+2 and k+3 in flight, so a
+// plane has two compute iterations to arrive.  Slots are compile-time constants (the k loop is unrolled by four):
+// every shared-memory access of the stencil is [one base register + immediate].
+//
+// V16: 16-byte copies.  The tile starts at i = 32*bx (even) and a row of the array holds n1+2 values, so with n1
+// even and 16-byte aligned base pointers every pair (i, i+1) of a tile row is one aligned 16-byte chunk that lies
+// entirely inside or outside the array.  Otherwise (V16 = false) the same code moves 8-byte chunks.
 #pragma once
+#include <cstdint>
 #include "common.cuh"
 
 #define TX 32
@@ -9,49 +16,61 @@
 #define PX (TX + 2)
 #define PY (TY + 2)
 #define PLANE (PX * PY)
+#define TSLOTS 4
 
-// Every thread moves the same (at most two) tile points of each plane, so the tile-local index and the
-// global offset are computed once, not per plane.
-struct Stage {
-  long g0, g1;      // global offsets (without the k term) of my two tile points, -1 if outside the array
-  int q0, q1;       // their positions in the PX x PY tile
+template <int S> struct Slot { static constexpr int v = S; };
+
+template <int NF, bool V16>
+struct Stager {
+  static constexpr int CE = V16 ? 2 : 1;            // elements per chunk
+  static constexpr int CPR = PX / CE;               // chunks per tile row
+  static constexpr int CPP = CPR * PY;              // chunks per field plane
+  static constexpr int NCH = NF * CPP;              // chunks per slot
+  static constexpr int NR = (NCH + TX * TY - 1) / (TX * TY);
+  static constexpr int SLOT_BYTES = NF * PLANE * 8;
+  const double* src[NR];    // advancing source pointers (plane `knext`); nullptr = this thread has no chunk in round r
+  unsigned dst[NR];         // shared-memory byte address of the chunk in slot 0
+  long s2;
+  int knext, klast;         // next plane to issue, last plane this CTA needs
+
+  __device__ __forceinline__ Stager(const Dims& d, int i0, int j0, const double* f0, const double* f1, const double* f2,
+                                    const double* f3, const double* smem, int kfirst, int klast_) {
+    const int t = threadIdx.x + TX * threadIdx.y;
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    s2 = d.s2; knext = kfirst; klast = klast_;
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      const int q = t + r * (TX * TY);
+      const int f = q / CPP, rem = q - f * CPP;
+      const int lj = rem / CPR, li = (rem - lj * CPR) * CE;
+      const int i = i0 - 1 + li, j = j0 - 1 + lj;
+      const double* fb = f == 0 ? f0 : f == 1 ? f1 : f == 2 ? f2 : f3;
+      const bool ok = q < NCH && i + CE - 1 <= d.n1 + 1 && j <= d.n2 + 1;
+      src[r] = ok ? fb + i + d.s1 * j + d.s2 * (long)kfirst : nullptr;
+      dst[r] = sbase + 8u * (unsigned)(f * PLANE + lj * PX + li);
+    }
+  }
+
+  // stage plane `knext` into slot S (nothing if the CTA does not need it); always one commit group
+  template <int S>
+  __device__ __forceinline__ void issue() {
+    if (knext <= klast) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+        if (src[r]) {
+          if (V16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst[r] + S * SLOT_BYTES), "l"(src[r]) : "memory");
+          else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst[r] + S * SLOT_BYTES), "l"(src[r]) : "memory");
+          src[r] += s2;
+        }
+    }
+    ++knext;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 };
 
-__device__ __forceinline__ Stage make_stage(const Dims& d, int i0, int j0) {
-  Stage st;
-  const int t = threadIdx.x + TX * threadIdx.y;
-  st.q0 = t;                                   // PLANE = 340 > 256 = TX*TY: first point always exists
-  st.q1 = t + TX * TY;
-  {
-    const int li = st.q0 % PX, lj = st.q0 / PX;
-    const int i = i0 + li - 1, j = j0 + lj - 1;
-    st.g0 = (i <= d.n1 + 1 && j <= d.n2 + 1) ? (long)i + d.s1 * j : -1;
-  }
-  st.g1 = -1;
-  if (st.q1 < PLANE) {
-    const int li = st.q1 % PX, lj = st.q1 / PX;
-    const int i = i0 + li - 1, j = j0 + lj - 1;
-    st.g1 = (i <= d.n1 + 1 && j <= d.n2 + 1) ? (long)i + d.s1 * j : -1;
-  }
-  return st;
-}
+// all but the most recent commit group have landed
+__device__ __forceinline__ void tile_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
-__device__ __forceinline__ void tile_cp8(double* dst_smem, const double* src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+static inline bool tile_v16(int n1, const void* a, const void* b, const void* c, const void* e = nullptr) {
+  return n1 % 2 == 0 && (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c | (uintptr_t)e) & 15) == 0;
 }
-
-// stage plane k of NF fields into slot `slot` of smem laid out [3 slots][NF fields][PLANE]; one commit group
-template <int NF>
-__device__ __forceinline__ void tile_issue(const Stage& st, const Dims& d, const double* const (&fld)[NF], double* smem, int k, int slot) {
-  const long ko = d.s2 * (long)k;
-  double* dst = smem + slot * (NF * PLANE);
-#pragma unroll
-  for (int f = 0; f < NF; ++f) {
-    if (st.g0 >= 0) tile_cp8(dst + f * PLANE + st.q0, fld[f] + st.g0 + ko);
-    if (st.g1 >= 0) tile_cp8(dst + f * PLANE + st.q1, fld[f] + st.g1 + ko);
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-__device__ __forceinline__ void tile_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
