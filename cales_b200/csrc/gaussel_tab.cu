@@ -9,12 +9,22 @@
 // arrays with the cached copies, and the table-build kernel that follows is a no-op unless something changed.  No host
 // synchronisation anywhere.
 //
-// Solve kernel: one warp per CTA, one thread per (i,j) column.  Right-hand side and pivots stream in through an
+// Two solve kernels share that scheme.  gauss_tma_k (default whenever a whole column fits in shared memory with at least
+// two CTAs per SM, and the transpose is not peer-fused): every group of GU levels x 32 columns of the right-hand side,
+// of the pivots and of p2 is ONE tensor-map bulk copy (TMA) issued by one lane and signalled through an mbarrier, and
+// every group of the solution leaves through one bulk tensor store -- no per-thread address arithmetic and no per-thread
+// copy instructions, ~20 warp instructions per level instead of ~58.  gauss_solve_k (below it) is the general kernel:
+//
+// gauss_solve_k: one warp per CTA, one thread per (i,j) column.  Right-hand side and pivots stream in through an
 // cp.async ring (GD levels ahead, thread-private slots: no barriers), the forward sweep leaves its result in shared
 // memory (the last S levels; earlier levels of very long columns spill to global memory), the backward sweep reads
 // it back from there and stores the solution: 8 B read + 8 B pivots + 8 B write per cell (+ 8 B for p2 when periodic).
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
+
+#include <cuda.h>
+#include <cudaTypedefs.h>
 
 #include "common.cuh"
 
@@ -29,6 +39,8 @@ struct GaussTab {
   const void* key[4] = {nullptr, nullptr, nullptr, nullptr};
   int nxy = 0, n = 0, periodic = 0;
   long last_use = 0;
+  CUtensorMap tmZ, tmP2;                                // tensor maps of Z and P2 (valid when has_tmap)
+  bool has_tmap = false;
 };
 
 static std::map<cales_ctx*, std::vector<GaussTab>> g_tabs;
@@ -288,6 +300,190 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
 #undef GSTORE
 }
 
+
+// ---- TMA solve kernel ----------------------------------------------------------------------------------------------------
+// One warp per CTA solving CW columns (lane = column; with CW = 16 or 8 the upper lanes repeat the work of the lower ones:
+// the solve is bound by the latency of its dependent chain, not by lanes, and narrower column blocks let more warps share
+// an SM's shared memory).  Shared memory: keep[ngrp*GU][CW] (the whole column block: right-hand side in, forward
+// result, solution out -- all in place), zr[TNG][GU][32] ring for pivots / p2, a(n), c(n), TNG mbarriers.  Rows past the
+// end of a tensor are zero-filled on load (z = 0 keeps the recurrences finite) and clipped on store.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  unsigned ok = 0;
+#pragma unroll 1
+  for (int spin = 0; spin < (1 << 24); ++spin) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return;
+  }
+  __trap();     // a copy never arrived: fail loudly instead of hanging the device
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* tm, int c0, int c1, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+               "l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int c1, unsigned src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(src)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int PER, int TGU, int CW>
+__global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmP2,
+                                                   const __grid_constant__ CUtensorMap tmP, int nxy, int n, long sz, int tng,
+                                                   const double* __restrict__ a, const double* __restrict__ c,
+                                                   const double* __restrict__ DEN, double* __restrict__ p) {
+  extern __shared__ __align__(128) unsigned char shraw[];
+  constexpr unsigned BOX = TGU * CW * sizeof(double);
+  const int nlev = PER ? n - 1 : n;
+  const int ngrp = (nlev + TGU - 1) / TGU, nfull = nlev / TGU, ntail = nlev - nfull * TGU;
+  double* keep = reinterpret_cast<double*>(shraw);
+  double* zr = keep + (size_t)ngrp * TGU * CW;
+  const unsigned bar0 = smem_u32(zr + (size_t)tng * TGU * CW), keep0 = smem_u32(keep), zr0 = smem_u32(zr);
+  const int lane = threadIdx.x % CW, col0 = blockIdx.x * CW, col = col0 + lane;   // CW < 32: the upper lanes repeat the lower ones
+  if (threadIdx.x == 0) {
+    for (int q = 0; q < tng; ++q) mbar_init(bar0 + 8 * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  __syncwarp();
+  const bool valid = col < nxy;
+  double plast = 0., den = 1.;
+  if (PER && valid) { plast = p[(long)(n - 1) * sz + col]; den = DEN[col]; }
+  unsigned islot = 0, cslot = 0, cpar = 0;     // ring slot of the next group to issue / to consume, mbarrier parity of the latter
+  double* kl = keep + lane;
+  // ================= forward elimination: p'(l) = (p(l) - a(l) p'(l-1)) z(l) ======================================
+#define T_ISSUE(cond_, body_)                                        \
+  {                                                                  \
+    if (cond_) {                                                     \
+      if (threadIdx.x == 0) {                                               \
+        const unsigned bar = bar0 + 8 * islot;                       \
+        const unsigned zdst = zr0 + islot * BOX;                     \
+        body_                                                        \
+      }                                                              \
+      if (++islot == (unsigned)tng) islot = 0;                       \
+    }                                                                \
+  }
+#define T_WAIT()                                                     \
+  mbar_wait(bar0 + 8 * cslot, cpar);                                 \
+  const double* zs = zr + cslot * (TGU * CW) + lane;                 \
+  if (++cslot == (unsigned)tng) { cslot = 0; cpar ^= 1u; }
+#define FWD_ISSUE(g_) T_ISSUE((g_) < ngrp, { mbar_expect_tx(bar, 2 * BOX); tma_load_2d(zdst, &tmZ, col0, (g_) * TGU, bar); \
+                                             tma_load_2d(keep0 + (g_) * BOX, &tmP, col0, (g_) * TGU, bar); })
+  for (int g = 0; g < tng; ++g) FWD_ISSUE(g)
+  double pl = 0.;
+  for (int g = 0; g < ngrp; ++g) {
+    T_WAIT()
+    double* ks = kl + (size_t)g * (TGU * CW);
+    const double* as = a + g * TGU;        // warp-uniform addresses: one broadcast load each
+    if (g < nfull) {
+      double r[TGU], z[TGU], aa[TGU];
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { z[q] = zs[q * CW]; r[q] = ks[q * CW]; aa[q] = __ldg(as + q); }
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { pl = (r[q] - aa[q] * pl) * z[q]; ks[q * CW] = pl; }
+    } else {
+      for (int q = 0; q < ntail; ++q) { pl = (ks[q * CW] - as[q] * pl) * zs[q * CW]; ks[q * CW] = pl; }
+    }
+    __syncwarp();
+    FWD_ISSUE(g + tng)
+  }
+  const double p1n = pl;                      // p1(n-1) of the periodic solve
+  // ================= backward substitution: p(l) = p'(l) - d(l) p(l+1), d(l) = c(l) z(l) =============================
+#define BWD_ISSUE(g_) T_ISSUE((g_) >= 0, { mbar_expect_tx(bar, BOX); tma_load_2d(zdst, &tmZ, col0, (g_) * TGU, bar); })
+  for (int q = 0; q < tng; ++q) BWD_ISSUE(ngrp - 1 - q)
+  pl = 0.;
+  for (int g = ngrp - 1; g >= 0; --g) {
+    T_WAIT()
+    double* ks = kl + (size_t)g * (TGU * CW);
+    const double* cs = c + g * TGU;
+    if (g < nfull) {
+      double r[TGU], d[TGU];
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { d[q] = __ldg(cs + q) * zs[q * CW]; r[q] = ks[q * CW]; }
+#pragma unroll
+      for (int q = TGU - 1; q >= 0; --q) { pl = r[q] - d[q] * pl; ks[q * CW] = pl; }
+    } else {
+      for (int q = ntail - 1; q >= 0; --q) { pl = ks[q * CW] - (cs[q] * zs[q * CW]) * pl; ks[q * CW] = pl; }
+    }
+    if (!PER) fence_async_smem();
+    __syncwarp();
+    if (!PER && threadIdx.x == 0) tma_store_2d(&tmP, col0, g * TGU, keep0 + g * BOX);
+    BWD_ISSUE(g - tng)
+  }
+  if (PER) {
+    // ================= periodic closure (solver.f90:142-145): p(n) and p(1:n-1) = p1 + p2 p(n) =========================
+    const double pn = (plast - c[n - 1] * pl - a[n - 1] * p1n) / den;
+#define CMB_ISSUE(g_) T_ISSUE((g_) < ngrp, { mbar_expect_tx(bar, BOX); tma_load_2d(zdst, &tmP2, col0, (g_) * TGU, bar); })
+    for (int g = 0; g < tng; ++g) CMB_ISSUE(g)
+    for (int g = 0; g < ngrp; ++g) {
+      T_WAIT()
+      double* ks = kl + (size_t)g * (TGU * CW);
+      if (g < nfull) {
+        double r[TGU];
+#pragma unroll
+        for (int q = 0; q < TGU; ++q) r[q] = ks[q * CW] + zs[q * CW] * pn;
+#pragma unroll
+        for (int q = 0; q < TGU; ++q) ks[q * CW] = r[q];
+      } else {
+        for (int q = 0; q < ntail; ++q) ks[q * CW] = ks[q * CW] + zs[q * CW] * pn;
+        ks[ntail * CW] = pn;                  // level n-1 shares the last (partial) box
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (threadIdx.x == 0) tma_store_2d(&tmP, col0, g * TGU, keep0 + g * BOX);
+      CMB_ISSUE(g + tng)
+    }
+    if (ntail == 0 && valid) p[(long)(n - 1) * sz + col] = pn;
+  }
+  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the bulk stores
+#undef T_ISSUE
+#undef T_WAIT
+#undef FWD_ISSUE
+#undef BWD_ISSUE
+#undef CMB_ISSUE
+}
+
+static PFN_cuTensorMapEncodeTiled tmap_encoder() {
+  static PFN_cuTensorMapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+  }
+  return fn;
+}
+
+// levels per box of gauss_tma_k (8 or 16, CALES_GAUSS_TGU); the ring takes whatever shared memory the column block leaves
+static int tma_gu() { static const int v = getenv("CALES_GAUSS_TGU") ? atoi(getenv("CALES_GAUSS_TGU")) : 16; return v == 8 ? 8 : 16; }
+
+// columns per CTA of gauss_tma_k (32, 16 or 8, CALES_GAUSS_CW)
+static int tma_cw() { static const int v = getenv("CALES_GAUSS_CW") ? atoi(getenv("CALES_GAUSS_CW")) : 16; return v == 32 ? 32 : v == 8 ? 8 : 16; }
+
+// [rows][cols] fp64 array with row stride `stride` elements, boxes of `boxrows` rows x `boxcols` columns
+static bool make_tmap(CUtensorMap* tm, const double* base, int cols, int rows, long stride, int boxrows, int boxcols) {
+  PFN_cuTensorMapEncodeTiled enc = tmap_encoder();
+  if (!enc) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)stride * sizeof(double)};
+  const cuuint32_t box[2] = {(cuuint32_t)boxcols, (cuuint32_t)boxrows};
+  const cuuint32_t est[2] = {1, 1};
+  static const int promo_env = getenv("CALES_GAUSS_L2PROMO") ? atoi(getenv("CALES_GAUSS_L2PROMO")) : -1;
+  const int rowb = promo_env >= 0 ? promo_env : boxcols * 8;
+  const CUtensorMapL2promotion promo = rowb >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : rowb >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                       : rowb >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const double* a, const double* b, const double* c, const double* lam) {
   std::vector<GaussTab>& v = g_tabs[ctx];
   for (auto& t : v)
@@ -313,6 +509,10 @@ static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const do
   cudaMemsetAsync(t->clam, 0xff, nxy * sizeof(double), ctx->stream);
   cudaMemsetAsync(t->flag, 0, sizeof(unsigned), ctx->stream);
   t->nxy = nxy; t->n = n; t->periodic = periodic;
+  {
+    const int nlev = periodic ? n - 1 : n;
+    t->has_tmap = nxy % 2 == 0 && make_tmap(&t->tmZ, t->Z, nxy, nlev, nxy, tma_gu(), tma_cw()) && make_tmap(&t->tmP2, periodic ? t->P2 : t->Z, nxy, nlev, nxy, tma_gu(), tma_cw());
+  }
   t->key[0] = a; t->key[1] = b; t->key[2] = c; t->key[3] = lam;
   return t;
 }
@@ -342,6 +542,37 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   if (periodic) gauss_build_k<1><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->flag, gen);
   else gauss_build_k<0><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->flag, gen);
   ctx->launches++;
+  const bool peer = g_gauss_peer_out != nullptr;
+  {
+    // TMA kernel: whole column block resident, at least two CTAs per SM, 16-byte aligned rows
+    static const int use_tma = getenv("CALES_GAUSS_TMA") ? atoi(getenv("CALES_GAUSS_TMA")) : 1;
+    // Shared memory per CTA: the column block + the ring (at least two slots); the CTA count per SM follows.
+    static const int tng_env = getenv("CALES_GAUSS_TNG") ? atoi(getenv("CALES_GAUSS_TNG")) : 0;
+    const int tgu = tma_gu(), cw = tma_cw();
+    const int ngrp = (nlev + tgu - 1) / tgu;
+    const size_t box = (size_t)tgu * cw * sizeof(double), keepb = (size_t)ngrp * box;
+    const int tng = std::min(ngrp, tng_env > 0 ? tng_env : (tgu == 16 ? 6 : 8));
+    const size_t sht = keepb + (size_t)tng * (box + 8);
+    CUtensorMap tmP;
+    if (use_tma && !peer && t->has_tmap && tng >= 2 && sht <= 112 * 1024 && sz % 2 == 0 && ((uintptr_t)p & 15) == 0 &&
+        make_tmap(&tmP, p, nxy, n, sz, tgu, cw)) {
+#define GT_GO(PER_, GU_, CW_)                                                                                              \
+  {                                                                                                                        \
+    static bool attr = false;                                                                                              \
+    if (!attr) { attr = true; cudaFuncSetAttribute(gauss_tma_k<PER_, GU_, CW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); } \
+    gauss_tma_k<PER_, GU_, CW_><<<cdiv(nxy, CW_), 32, sht, ctx->stream>>>(t->tmZ, t->tmP2, tmP, nxy, n, sz, tng, a, c, t->DEN, p);           \
+  }
+#define GT_PER(GU_, CW_) { if (periodic) GT_GO(1, GU_, CW_) else GT_GO(0, GU_, CW_) }
+#define GT_CW(GU_) { if (cw == 32) GT_PER(GU_, 32) else if (cw == 16) GT_PER(GU_, 16) else GT_PER(GU_, 8) }
+      if (tgu == 8) GT_CW(8) else GT_CW(16)
+#undef GT_CW
+#undef GT_PER
+#undef GT_GO
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) return -cales_fail(ctx, CALES_ERR_CUDA, "gauss_tma_k launch failed");
+      return 1;
+    }
+  }
   // shared memory: coefficients + kept levels + the two rings; keep three CTAs per SM when the column is long
   static const size_t budget = getenv("CALES_GAUSS_SMEM") ? (size_t)atol(getenv("CALES_GAUSS_SMEM")) : 76800;   // 3 CTAs per SM
   static const int gng = getenv("CALES_GAUSS_GNG") ? atoi(getenv("CALES_GAUSS_GNG")) : 3;
@@ -358,7 +589,6 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   const dim3 g(cdiv(nxy, GC));
   GPeer G;
   memset(&G, 0, sizeof G);
-  const bool peer = g_gauss_peer_out != nullptr;
   if (peer) G = *g_gauss_peer_out;
 #define GS_GO(PER_, SP_, NG_)                                                                                         \
   {                                                                                                                   \
