@@ -55,7 +55,9 @@ struct cales_ctx {
   cudaStream_t comm_stream = nullptr;
   std::map<std::string, PeerBuf> peerbufs;
   int p2p = -1;                         // -1 untested, 0 unavailable (NCCL send/recv transposes), 1 peer memory mapped
-  double* bar = nullptr;                // barrier token
+  double* bar = nullptr;                // barrier token (NCCL all-reduce barrier)
+  unsigned long long bar_seq = 0;       // sequence number of the peer-memory flag barrier
+  unsigned halo_seq = 0;                // parity of the double-buffered peer halo buffers
   // scratch owned by the callee (the reference's `save`d allocatables and module buffers)
   std::map<std::string, std::pair<void*, size_t>> scratch;
   double* red = nullptr;                // device reduction slots
