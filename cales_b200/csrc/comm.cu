@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include <algorithm>
+#include <cstdint>
 
 #include "common.cuh"
 
@@ -359,7 +360,68 @@ __global__ void __launch_bounds__(256) boxcopy_k(const double* __restrict__ src,
   }
 }
 
+// 16-byte variant: every extent, offset and stride of every segment is even and all pointers are 16-byte aligned
+__global__ void __launch_bounds__(256) boxcopy2_k(const double* __restrict__ src, double* __restrict__ dst, SegList L) {
+  const Seg& g = L.s[blockIdx.z];
+  const int i = 2 * (blockIdx.x * 64 + threadIdx.x);
+  if (i >= g.b0) return;
+  const long rows = (long)g.b1 * g.b2;
+  double* out = g.dptr ? g.dptr : dst;
+  for (long r = blockIdx.y * 4 + threadIdx.y; r < rows; r += (long)gridDim.y * 4) {
+    const int j = (int)(r % g.b1), k = (int)(r / g.b1);
+    *reinterpret_cast<double2*>(out + g.doff + i + j * g.ds1 + k * g.ds2) = *reinterpret_cast<const double2*>(src + g.soff + i + j * g.ss1 + k * g.ss2);
+  }
+}
+
+// Copy-engine variant for boxes that are complete along i in both pencils (the y <-> z transposes): per peer ONE strided
+// 2-D DMA (rows of b0*b1 contiguous values, b2 rows), each on its own stream so that the peers' links run concurrently;
+// NVLink at copy-engine efficiency and no SM time.  Returns 0 if some segment does not collapse to 2-D.
+static cudaStream_t g_ce_stream[8];
+static cudaEvent_t g_ce_ev[17];
+static bool g_ce_init = false;
+static int boxcopy_ce(cales_ctx* ctx, const double* src, double* dst, const SegList& L, int first) {
+  for (int q = 0; q < L.n; ++q) if (L.s[q].b0 != L.s[q].ss1 || L.s[q].b0 != L.s[q].ds1) return 0;
+  if (!g_ce_init) {
+    g_ce_init = true;
+    for (auto& st : g_ce_stream) cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    for (auto& e : g_ce_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+  }
+  cudaEventRecord(g_ce_ev[16], ctx->stream);
+  for (int d = 0; d < L.n; ++d) {
+    const int q = (first + d) % L.n;
+    const Seg& g = L.s[q];
+    cudaStream_t st = g_ce_stream[d % 8];
+    cudaStreamWaitEvent(st, g_ce_ev[16], 0);
+    if (cudaMemcpy2DAsync((g.dptr ? g.dptr : dst) + g.doff, (size_t)g.ds2 * sizeof(double), src + g.soff, (size_t)g.ss2 * sizeof(double),
+                          (size_t)g.b0 * g.b1 * sizeof(double), (size_t)g.b2, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+      return -cales_fail(ctx, CALES_ERR_CUDA, "peer cudaMemcpy2DAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaEventRecord(g_ce_ev[d % 16], st);
+    cudaStreamWaitEvent(ctx->stream, g_ce_ev[d % 16], 0);
+  }
+  ctx->launches += L.n;
+  return 1;
+}
+
 static int boxcopy(cales_ctx* ctx, const double* src, double* dst, const SegList& L) {
+  static const int mode = getenv("CALES_TRANSPOSE_MODE") ? atoi(getenv("CALES_TRANSPOSE_MODE")) : 1;   // 0: 8-byte kernel, 1: 16-byte kernel, 2: copy engines
+  if (mode == 2 && L.n <= 16) {
+    const int rc = boxcopy_ce(ctx, src, dst, L, (ctx->coord[1] + 1) % L.n);
+    if (rc < 0) return -rc;
+    if (rc == 1) return CALES_OK;
+  }
+  bool even = mode >= 1 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0;
+  for (int q = 0; q < L.n && even; ++q) {
+    const Seg& g = L.s[q];
+    even = !((g.b0 | g.soff | g.doff | g.ss1 | g.ss2 | g.ds1 | g.ds2) & 1) && ((uintptr_t)g.dptr & 15) == 0;
+  }
+  if (even) {
+    int b0 = 2; long rows = 1;
+    for (int q = 0; q < L.n; ++q) { if (L.s[q].b0 > b0) b0 = L.s[q].b0; if ((long)L.s[q].b1 * L.s[q].b2 > rows) rows = (long)L.s[q].b1 * L.s[q].b2; }
+    long gy = (rows + 3) / 4; if (gy > 16384) gy = 16384;
+    boxcopy2_k<<<dim3(cdiv(b0 / 2, 64), (unsigned)gy, L.n), dim3(64, 4), 0, ctx->stream>>>(src, dst, L);
+    KERNEL_CHECK(ctx);
+    return CALES_OK;
+  }
   int b0 = 1; long rows = 1;
   for (int q = 0; q < L.n; ++q) { if (L.s[q].b0 > b0) b0 = L.s[q].b0; if ((long)L.s[q].b1 * L.s[q].b2 > rows) rows = (long)L.s[q].b1 * L.s[q].b2; }
   long gy = (rows + 3) / 4; if (gy > 16384) gy = 16384;

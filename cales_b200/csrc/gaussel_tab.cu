@@ -333,11 +333,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, int c0, int 
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int PER, int TGU, int CW>
+// PEER (distributed solver, process grid 1 x P): the solution does not go back to p but straight into the Y-pencils of the
+// ranks that own each z range -- one tensor map per destination rank over its peer-mapped pencil, rows outside a rank's
+// range clipped by the TMA unit -- so the z -> y transpose costs no kernel and no pass over memory.
+struct TmaPeerOut { CUtensorMap m[8]; int np; int zs[9]; double* last; };   // zs: first global level of each rank; last: row of level n-1
+
+template <int PER, int TGU, int CW, bool PEER>
 __global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmP2,
                                                    const __grid_constant__ CUtensorMap tmP, int nxy, int n, long sz, int tng,
                                                    const double* __restrict__ a, const double* __restrict__ c,
-                                                   const double* __restrict__ DEN, double* __restrict__ p) {
+                                                   const double* __restrict__ DEN, double* __restrict__ p,
+                                                   const __grid_constant__ TmaPeerOut PO) {
   extern __shared__ __align__(128) unsigned char shraw[];
   constexpr unsigned BOX = TGU * CW * sizeof(double);
   const int nlev = PER ? n - 1 : n;
@@ -373,6 +379,14 @@ __global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtens
   mbar_wait(bar0 + 8 * cslot, cpar);                                 \
   const double* zs = zr + cslot * (TGU * CW) + lane;                 \
   if (++cslot == (unsigned)tng) { cslot = 0; cpar ^= 1u; }
+#define T_STORE(g_)                                                                                   \
+  {                                                                                                   \
+    const int l0_ = (g_) * TGU;                                                                       \
+    if (!PEER) tma_store_2d(&tmP, col0, l0_, keep0 + (g_) * BOX);                                     \
+    else                                                                                              \
+      for (int r_ = 0; r_ < PO.np; ++r_)                                                              \
+        if (l0_ < PO.zs[r_ + 1] && l0_ + TGU > PO.zs[r_]) tma_store_2d(&PO.m[r_], col0, l0_ - PO.zs[r_], keep0 + (g_) * BOX); \
+  }
 #define FWD_ISSUE(g_) T_ISSUE((g_) < ngrp, { mbar_expect_tx(bar, 2 * BOX); tma_load_2d(zdst, &tmZ, col0, (g_) * TGU, bar); \
                                              tma_load_2d(keep0 + (g_) * BOX, &tmP, col0, (g_) * TGU, bar); })
   for (int g = 0; g < tng; ++g) FWD_ISSUE(g)
@@ -413,7 +427,7 @@ __global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtens
     }
     if (!PER) fence_async_smem();
     __syncwarp();
-    if (!PER && threadIdx.x == 0) tma_store_2d(&tmP, col0, g * TGU, keep0 + g * BOX);
+    if (!PER && threadIdx.x == 0) T_STORE(g)
     BWD_ISSUE(g - tng)
   }
   if (PER) {
@@ -436,14 +450,18 @@ __global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtens
       }
       fence_async_smem();
       __syncwarp();
-      if (threadIdx.x == 0) tma_store_2d(&tmP, col0, g * TGU, keep0 + g * BOX);
+      if (threadIdx.x == 0) T_STORE(g)
       CMB_ISSUE(g + tng)
     }
-    if (ntail == 0 && valid) p[(long)(n - 1) * sz + col] = pn;
+    if (ntail == 0 && valid) { if (PEER) PO.last[col] = pn; else p[(long)(n - 1) * sz + col] = pn; }
   }
-  if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory must outlive the bulk stores
+  if (threadIdx.x == 0) {                          // shared memory must outlive the bulk stores; peer stores must have landed
+    if (PEER) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
 #undef T_ISSUE
 #undef T_WAIT
+#undef T_STORE
 #undef FWD_ISSUE
 #undef BWD_ISSUE
 #undef CMB_ISSUE
@@ -554,19 +572,33 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
     const int tng = std::min(ngrp, tng_env > 0 ? tng_env : (tgu == 16 ? 6 : 8));
     const size_t sht = keepb + (size_t)tng * (box + 8);
     CUtensorMap tmP;
-    if (use_tma && !peer && t->has_tmap && tng >= 2 && sht <= 112 * 1024 && sz % 2 == 0 && ((uintptr_t)p & 15) == 0 &&
+    TmaPeerOut PO;
+    memset(&PO, 0, sizeof PO);
+    bool peer_ok = true;
+    if (peer) {                    // destination pencils: base + coff, rows = levels of that rank, row stride = Y-pencil plane
+      const GPeer& GPr = *g_gauss_peer_out;
+      peer_ok = GPr.np <= 8 && GPr.plane % 2 == 0 && GPr.coff % 2 == 0 && GPr.pzs[GPr.np] == n && nxy % cw == 0;
+      PO.np = GPr.np;
+      for (int r = 0; r <= GPr.np && peer_ok; ++r) PO.zs[r] = GPr.pzs[r];
+      for (int r = 0; r < GPr.np && peer_ok; ++r)
+        peer_ok = ((uintptr_t)GPr.pbase[r] & 15) == 0 && make_tmap(&PO.m[r], GPr.pbase[r] + GPr.coff, nxy, GPr.pzs[r + 1] - GPr.pzs[r], GPr.plane, tgu, cw);
+      if (peer_ok) PO.last = GPr.pbase[GPr.np - 1] + GPr.coff + GPr.plane * (long)(n - 1 - GPr.pzs[GPr.np - 1]);
+    }
+    if (use_tma && peer_ok && t->has_tmap && tng >= 2 && sht <= 112 * 1024 && sz % 2 == 0 && ((uintptr_t)p & 15) == 0 &&
         make_tmap(&tmP, p, nxy, n, sz, tgu, cw)) {
-#define GT_GO(PER_, GU_, CW_)                                                                                              \
+#define GT_GO(PER_, GU_, CW_, PEER_)                                                                                       \
   {                                                                                                                        \
     static bool attr = false;                                                                                              \
-    if (!attr) { attr = true; cudaFuncSetAttribute(gauss_tma_k<PER_, GU_, CW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); } \
-    gauss_tma_k<PER_, GU_, CW_><<<cdiv(nxy, CW_), 32, sht, ctx->stream>>>(t->tmZ, t->tmP2, tmP, nxy, n, sz, tng, a, c, t->DEN, p);           \
+    if (!attr) { attr = true; cudaFuncSetAttribute(gauss_tma_k<PER_, GU_, CW_, PEER_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); } \
+    gauss_tma_k<PER_, GU_, CW_, PEER_><<<cdiv(nxy, CW_), 32, sht, ctx->stream>>>(t->tmZ, t->tmP2, tmP, nxy, n, sz, tng, a, c, t->DEN, p, PO);       \
   }
-#define GT_PER(GU_, CW_) { if (periodic) GT_GO(1, GU_, CW_) else GT_GO(0, GU_, CW_) }
+#define GT_PEER(PER_, GU_, CW_) { if (peer) GT_GO(PER_, GU_, CW_, true) else GT_GO(PER_, GU_, CW_, false) }
+#define GT_PER(GU_, CW_) { if (periodic) GT_PEER(1, GU_, CW_) else GT_PEER(0, GU_, CW_) }
 #define GT_CW(GU_) { if (cw == 32) GT_PER(GU_, 32) else if (cw == 16) GT_PER(GU_, 16) else GT_PER(GU_, 8) }
       if (tgu == 8) GT_CW(8) else GT_CW(16)
 #undef GT_CW
 #undef GT_PER
+#undef GT_PEER
 #undef GT_GO
       ctx->launches++;
       if (cudaGetLastError() != cudaSuccess) return -cales_fail(ctx, CALES_ERR_CUDA, "gauss_tma_k launch failed");

@@ -407,7 +407,9 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
     }
     FP.pys[P] = ctx->ng[1]; GP.pzs[P] = ctx->ng[2];
     if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, w0, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
-    static const int fmask = getenv("CALES_FUSE_MASK") ? atoi(getenv("CALES_FUSE_MASK")) : 1;   // bit 0: forward y pass pushes, bit 1: z solve pushes (slower: its few warps stall on NVLink stores)
+    // bit 0: the forward y pass pushes its spectrum, bit 1: the z solve pushes its solution (asynchronous bulk tensor stores
+    // of gauss_tma_k; only when every level is solved, i.e. not for the shortened face-centred Dirichlet system)
+    static const int fmask = getenv("CALES_FUSE_MASK") ? atoi(getenv("CALES_FUSE_MASK")) : 3;
     if (fmask & 1) {
       g_fft_peer_out = &FP;
       rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0);
@@ -418,7 +420,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
       if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w0, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
       if ((rc = k_transpose_p2p(ctx, 1, w0, pb1))) return rc;
     }
-    if (fmask & 2) {
+    if ((fmask & 2) && q == 0) {
       g_gauss_peer_out = &GP;
       rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w1);
       g_gauss_peer_out = nullptr;
