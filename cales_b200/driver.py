@@ -10,6 +10,7 @@ import os
 import numpy as np
 import torch
 
+from . import checkpoint
 from . import hostinit
 from . import lib as L
 from .deck import rkcoeff
@@ -286,6 +287,20 @@ class Simulation:
             self.dti = 1. / self.dt
             return self.chkdiv()
         return None
+
+    # ---- restart files (main.f90:358-369, 590-611) ---------------------------------------------------------------
+    def save(self, filename, barrier=None):
+        """`load_all('w', ...)`: download u,v,w,p (`!$acc update self`, main.f90:607) and write this rank's sub-box."""
+        torch.cuda.synchronize(self.device)
+        f = [self.get(nm) for nm in ("u", "v", "w", "p")]
+        checkpoint.load_all("w", filename, self.deck.ng, self.lo, self.hi, *f, time=self.time, istep=self.istep, rank=self.rank,
+                            barrier=barrier)
+
+    def load(self, filename):
+        """`load_all('r', ...)` instead of `initflow` (main.f90:365); call `start()` afterwards as after `init_flow()`."""
+        f = [np.zeros(self.shape, order="F") for _ in range(4)]
+        self.time, self.istep = checkpoint.load_all("r", filename, self.deck.ng, self.lo, self.hi, *f)
+        self.set_fields(u=f[0], v=f[1], w=f[2], p=f[3])
 
     def close(self):
         if self.ctx:

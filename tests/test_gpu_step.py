@@ -100,6 +100,34 @@ def test_hundred_steps(case):
     g.close()
 
 
+@pytest.mark.parametrize("case", ["channel_dsmag", "tgv_smag"])
+def test_restart_from_checkpoint(case, tmp_path):
+    """`fld.bin` (load.f90:20-187): 2 steps + save + load in a fresh context + 2 steps == 4 steps to round-off (the first
+    RK substep has rkpar(2) = 0, so no history crosses the restart; main.f90:524 suggests icheck=1 for this check)."""
+    import cales_b200.deck as pd
+    from cales_b200.driver import Simulation
+    name, kw = CASES[case]
+    a = Simulation(getattr(pd, name)(**kw))
+    a.init_flow(); a.start()
+    for _ in range(2):
+        a.step(icheck=1)
+    fn = str(tmp_path / "fld.bin")
+    a.save(fn)
+    for _ in range(2):
+        a.step(icheck=1)
+    b = Simulation(getattr(pd, name)(**kw))
+    b.load(fn)
+    assert b.istep == 2 and b.time > 0.
+    b.start()
+    for _ in range(2):
+        b.step(icheck=1)
+    assert b.istep == a.istep == 4 and abs(b.time - a.time) <= 1e-14 * a.time and abs(b.dt - a.dt) <= 1e-14 * a.dt
+    for nm in ("u", "v", "w", "p", "visct"):
+        fa, fb = a.get(nm)[1:-1, 1:-1, 1:-1], b.get(nm)[1:-1, 1:-1, 1:-1]
+        assert np.abs(fa - fb).max() <= 1e-13 * max(np.abs(fa).max(), 1e-300), nm
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("case,mode", [("channel_smag", "3d"), ("channel_smag", "1d"), ("tgv_smag", "1d"), ("channel_wm_smag", "1d"),
                                        ("tgv_smag", "3d"), ("duct_smag", "3d"), ("cavity_smag", "3d"), ("duct_smag", "1d")])
 def test_implicit_diffusion(case, mode):
