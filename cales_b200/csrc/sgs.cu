@@ -38,9 +38,20 @@ __global__ void smag_del_k(int n3, double dl0, double dl1, const double* __restr
   if (k <= n3 + 1) delk[k] = pow(dl0 * dl1 * dzf[k], 1. / 3.);
 }
 
-__device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, int i, int j, int k) {
+// sqrt(tau_w) of the z walls (sgs.f90:135-142) depends on (i,j) only: a thread evaluates it once for its column and
+// reuses it at every level (same operations, same bits as evaluating it per cell)
+__device__ __forceinline__ double wall_sqrt_tau_z(const Dims& d, const SmagArgs& A, int i, int j, int top) {
+  const double* __restrict__ u = A.u; const double* __restrict__ v = A.v;
+  const int ka = top ? d.n3 : 1, kb = top ? d.n3 + 1 : 0;
+  const double t1 = u[d.idx(i, j, ka)] - u[d.idx(i, j, kb)] + u[d.idx(i - 1, j, ka)] - u[d.idx(i - 1, j, kb)];
+  const double t2 = v[d.idx(i, j, ka)] - v[d.idx(i, j, kb)] + v[d.idx(i, j - 1, ka)] - v[d.idx(i, j - 1, kb)];
+  const double tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dzci0[top ? d.n3 : 0];
+  return sqrt(0.5 * A.visc * tauw_s);
+}
+
+__device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, int i, int j, int k, double sq_bot, double sq_top) {
   const double* __restrict__ u = A.u; const double* __restrict__ v = A.v; const double* __restrict__ w = A.w;
-  const int n1 = d.n1, n2 = d.n2, n3 = d.n3;
+  const int n1 = d.n1, n2 = d.n2;
   double dw[6];
   dw[0] = A.dl0 * (i - 0.5); dw[1] = A.dl0 * (n1 - i + 0.5);
   dw[2] = A.dl1 * (j - 0.5); dw[3] = A.dl1 * (n2 - j + 0.5);
@@ -52,40 +63,37 @@ __device__ __forceinline__ double van_driest(const Dims& d, const SmagArgs& A, i
     dw[q] = dw[q] * A.is_wall[q] + BIG * (1. - A.is_wall[q]);
     if (q == 0 || dw[q] < dw_min) { dw_min = dw[q]; loc = q; }     // minloc: first minimum
   }
-  double t1, t2, tauw_s;
+  double sq;
+  if (loc == 4) sq = sq_bot;
+  else if (loc == 5) sq = sq_top;
+  else {
+    double t1, t2, tauw_s;
 #define U(ii, jj, kk) u[d.idx(ii, jj, kk)]
 #define V(ii, jj, kk) v[d.idx(ii, jj, kk)]
 #define W(ii, jj, kk) w[d.idx(ii, jj, kk)]
-  if (loc == 0) {
-    t1 = V(1, j, k) - V(0, j, k) + V(1, j - 1, k) - V(0, j - 1, k);
-    t2 = W(1, j, k) - W(0, j, k) + W(1, j, k - 1) - W(0, j, k - 1);
-    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
-  } else if (loc == 1) {
-    t1 = V(n1, j, k) - V(n1 + 1, j, k) + V(n1, j - 1, k) - V(n1 + 1, j - 1, k);
-    t2 = W(n1, j, k) - W(n1 + 1, j, k) + W(n1, j, k - 1) - W(n1 + 1, j, k - 1);
-    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
-  } else if (loc == 2) {
-    t1 = U(i, 1, k) - U(i, 0, k) + U(i - 1, 1, k) - U(i - 1, 0, k);
-    t2 = W(i, 1, k) - W(i, 0, k) + W(i, 1, k - 1) - W(i, 0, k - 1);
-    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
-  } else if (loc == 3) {
-    t1 = U(i, n2, k) - U(i, n2 + 1, k) + U(i - 1, n2, k) - U(i - 1, n2 + 1, k);
-    t2 = W(i, n2, k) - W(i, n2 + 1, k) + W(i, n2, k - 1) - W(i, n2 + 1, k - 1);
-    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
-  } else if (loc == 4) {
-    t1 = U(i, j, 1) - U(i, j, 0) + U(i - 1, j, 1) - U(i - 1, j, 0);
-    t2 = V(i, j, 1) - V(i, j, 0) + V(i, j - 1, 1) - V(i, j - 1, 0);
-    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dzci0[0];
-  } else {
-    t1 = U(i, j, n3) - U(i, j, n3 + 1) + U(i - 1, j, n3) - U(i - 1, j, n3 + 1);
-    t2 = V(i, j, n3) - V(i, j, n3 + 1) + V(i, j - 1, n3) - V(i, j - 1, n3 + 1);
-    tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dzci0[n3];
-  }
+    if (loc == 0) {
+      t1 = V(1, j, k) - V(0, j, k) + V(1, j - 1, k) - V(0, j - 1, k);
+      t2 = W(1, j, k) - W(0, j, k) + W(1, j, k - 1) - W(0, j, k - 1);
+      tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
+    } else if (loc == 1) {
+      t1 = V(n1, j, k) - V(n1 + 1, j, k) + V(n1, j - 1, k) - V(n1 + 1, j - 1, k);
+      t2 = W(n1, j, k) - W(n1 + 1, j, k) + W(n1, j, k - 1) - W(n1 + 1, j, k - 1);
+      tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dxi;
+    } else if (loc == 2) {
+      t1 = U(i, 1, k) - U(i, 0, k) + U(i - 1, 1, k) - U(i - 1, 0, k);
+      t2 = W(i, 1, k) - W(i, 0, k) + W(i, 1, k - 1) - W(i, 0, k - 1);
+      tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
+    } else {
+      t1 = U(i, n2, k) - U(i, n2 + 1, k) + U(i - 1, n2, k) - U(i - 1, n2 + 1, k);
+      t2 = W(i, n2, k) - W(i, n2 + 1, k) + W(i, n2, k - 1) - W(i, n2 + 1, k - 1);
+      tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dyi;
+    }
 #undef U
 #undef V
 #undef W
-  tauw_s = 0.5 * A.visc * tauw_s;
-  const double dw_plus = dw_min * sqrt(tauw_s) * (1. / A.visc);
+    sq = sqrt(0.5 * A.visc * tauw_s);
+  }
+  const double dw_plus = dw_min * sq * (1. / A.visc);
   return 1. - exp(-dw_plus / 25.);
 }
 
@@ -130,6 +138,11 @@ __global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double
   __syncthreads();
   long o = d.idx(i, j, k0);
   int k = k0;
+  double sq_bot = 0., sq_top = 0.;
+  if (SMAG && A.any_wall && active) {
+    if (A.is_wall[4] != 0.) sq_bot = wall_sqrt_tau_z(d, A, i, j, 0);
+    if (A.is_wall[5] != 0.) sq_top = wall_sqrt_tau_z(d, A, i, j, 1);
+  }
   // one level: planes k, k+1 in slots SC, SP; plane k+3 goes into slot SN (which held plane k-1)
   auto step = [&](auto sc_, auto sp_, auto sn_) {
     constexpr int SC = decltype(sc_)::v, SP = decltype(sp_)::v, SN = decltype(sn_)::v;
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double
       const double s23 = .125 * (n_vz + n_wy + b_vz + b_wy + n_vzm + n_wym + b_vzm + b_wym);
       const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
       if (SMAG) {                                          // visct = (c_smag*del*fd)**2*s0   (sgs.f90:150)
-        const double fd = (A.any_wall && active) ? van_driest(d, A, i, j, k) : 1.;
+        const double fd = (A.any_wall && active) ? van_driest(d, A, i, j, k, sq_bot, sq_top) : 1.;
         const double t = CSMAG * A.delk[k] * fd;
         if (active) visct[o] = t * t * s;
       } else if (active) s0[o] = s;
