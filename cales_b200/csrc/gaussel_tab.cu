@@ -542,6 +542,20 @@ void k_gaussel_tab_free(cales_ctx* ctx) {
   g_tabs.erase(it);
 }
 
+// Would k_gaussel_tab run the TMA kernel for this problem?  The distributed solver fuses the z -> y transpose into the z
+// solve only then (the general kernel's per-thread NVLink stores are slower than a separate transpose).
+bool k_gauss_tma_fits(int nxy, int n, int periodic) {
+  static const int use_tma = getenv("CALES_GAUSS_TMA") ? atoi(getenv("CALES_GAUSS_TMA")) : 1;
+  static const int tng_env = getenv("CALES_GAUSS_TNG") ? atoi(getenv("CALES_GAUSS_TNG")) : 0;
+  const int nlev = periodic ? n - 1 : n;
+  if (!use_tma || nlev < 1 || nxy % 2 != 0 || nxy % tma_cw() != 0) return false;
+  const int tgu = tma_gu(), cw = tma_cw();
+  const int ngrp = (nlev + tgu - 1) / tgu;
+  const size_t box = (size_t)tgu * cw * sizeof(double);
+  const int tng = std::min(ngrp, tng_env > 0 ? tng_env : (tgu == 16 ? 6 : 8));
+  return tng >= 2 && (size_t)ngrp * box + (size_t)tng * (box + 8) <= 112 * 1024;
+}
+
 // returns 1 if handled, 0 if the caller should use the direct kernels, < 0 on error
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
                   const double* lambdaxy, double* p) {

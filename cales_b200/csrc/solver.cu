@@ -22,6 +22,7 @@ extern const FftPeerOut* g_fft_peer_out;
 struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };
 extern const GPeer* g_gauss_peer_out;
 bool k_fft_peer_capable(const char bc[2], char c_or_f, int n);
+bool k_gauss_tma_fits(int nxy, int n, int periodic);
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
                   const double* lambdaxy, double* p);
 
@@ -420,7 +421,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
       if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w0, ys[0], (long)ys[0] * ys[1], 1.0))) return rc;
       if ((rc = k_transpose_p2p(ctx, 1, w0, pb1))) return rc;
     }
-    if ((fmask & 2) && q == 0) {
+    if ((fmask & 2) && q == 0 && k_gauss_tma_fits(zs[0] * zs[1], zs[2], zper)) {
       g_gauss_peer_out = &GP;
       rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w1);
       g_gauss_peer_out = nullptr;
