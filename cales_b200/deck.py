@@ -48,6 +48,20 @@ class Deck:
     is_forced: tuple = (False, False, False)
     velf: tuple = (0.0, 0.0, 0.0)
     dims: tuple = (1, 1)
+    # run control (param.f90:104-108; consumed by cales_b200/run.py, main.f90:358-369, 512-611)
+    nstep: int = 100
+    time_max: float = 100.0
+    tw_max: float = 0.1
+    stop_type: tuple = (True, False, False)
+    restart: bool = False
+    is_overwrite_save: bool = True
+    nsaves_max: int = 0
+    icheck: int = 10
+    iout0d: int = 10
+    iout1d: int = 0
+    iout2d: int = 0
+    iout3d: int = 0
+    isave: int = 0
     sgstype: str = "none"
     lwm: np.ndarray = field(default_factory=lambda: np.zeros((2, 3), dtype=np.int32))
     hwm: float = 0.1
@@ -200,5 +214,11 @@ def read_input(path):
     d.bforce = tuple(float(x) for x in get("bforce", d.bforce))
     d.is_forced = tuple(bool(x) for x in get("is_forced", d.is_forced)); d.velf = tuple(float(x) for x in get("velf", d.velf))
     d.dims = tuple(int(x) for x in get("dims", d.dims))
+    d.nstep = int(get("nstep", [d.nstep])[0]); d.time_max = float(get("time_max", [d.time_max])[0])
+    d.tw_max = float(get("tw_max", [d.tw_max])[0]); d.stop_type = tuple(bool(x) for x in get("stop_type", d.stop_type))
+    d.restart = bool(get("restart", [d.restart])[0]); d.is_overwrite_save = bool(get("is_overwrite_save", [d.is_overwrite_save])[0])
+    d.nsaves_max = int(get("nsaves_max", [d.nsaves_max])[0])
+    for nm in ("icheck", "iout0d", "iout1d", "iout2d", "iout3d", "isave"):
+        setattr(d, nm, int(get(nm, [getattr(d, nm)])[0]))
     d.sgstype = get("sgstype", [d.sgstype])[0]; d.hwm = float(get("hwm", [d.hwm])[0])
     return d
