@@ -54,6 +54,24 @@ def initgrid(gtype, n, gr, lz):
     return dzc, dzf, zc, zf
 
 
+def add_noise(ng, lo, n, iseed, norm, p):
+    """`add_noise`, initflow.f90:285-315: one random number per GLOBAL cell in i-fastest order, added as 2(rn-.5)norm to the
+    cells this rank owns, so the field does not depend on the decomposition.  The reference draws from the Fortran
+    compiler's `random_number` stream seeded with `iseed`, which cannot be reproduced outside that compiler (SURVEY.md
+    section 8d); here the stream is numpy's PCG64 seeded with `iseed` -- same distribution, same amplitude, same
+    decomposition independence, different numbers."""
+    rng = np.random.Generator(np.random.PCG64(iseed))
+    plane = int(ng[0]) * int(ng[1])
+    i0, j0 = lo[0] - 1, lo[1] - 1
+    for k in range(1, int(ng[2]) + 1):
+        kk = k - (lo[2] - 1)
+        if kk < 1 or kk > n[2]:
+            rng.bit_generator.advance(plane)                 # one 64-bit draw per double
+            continue
+        rn = rng.random(plane).reshape((int(ng[0]), int(ng[1])), order="F")
+        p[1:n[0] + 1, 1:n[1] + 1, kk] += 2. * (rn[i0:i0 + n[0], j0:j0 + n[1]] - .5) * norm
+
+
 def initflow(deck, lo, n, zc, zf, dzc, dzf, mean_allreduce=None):
     """Initial u,v,w,p (haloed, Fortran order) of the rank with 1-based lower corner `lo`
     (initflow.f90:17-283).  `mean_allreduce(partial)` supplies the global sum used by set_mean."""
@@ -68,8 +86,13 @@ def initflow(deck, lo, n, zc, zf, dzc, dzf, mean_allreduce=None):
     uref = 1.0
     ubulk = deck.velf[0] if deck.is_forced[0] else uref
     is_mean = False
+    is_noise = False
     u1d = None
     zcn = zc[kk] / l[2]
+
+    def mirrored():
+        """zc2/(2 l3) of the half-channel cases (initflow.f90:84-88, 96-100); only levels 1..n3 are used afterwards."""
+        return zc[kk] / (2. * l[2])
     if inivel == "poi":
         u1d = 6. * zcn * (1. - zcn) * ubulk; is_mean = True
     elif inivel == "cou":
@@ -82,8 +105,37 @@ def initflow(deck, lo, n, zc, zf, dzc, dzf, mean_allreduce=None):
         u1d = np.zeros(n[2])
     elif inivel == "uni":
         u1d = np.full(n[2], uref)
-    elif inivel == "pdc":
+    elif inivel == "tbl":                                     # initflow.f90:60-62, temporal_bl 375-390
+        theta = 54. * visc / uref
+        u1d = (0.5 + 0.5 * np.tanh((1. / (2. * theta)) * (1. - zc[kk] / 1.))) * uref
+        is_noise = True
+    elif inivel in ("log", "hcl"):                            # initflow.f90:76-92, log_profile 392-407
+        half = inivel == "hcl"
+        reb = ubulk * ((2. * l[2]) if half else l[2]) / visc
+        retau = 0.09 * reb ** 0.88
+        z = (mirrored() if half else zcn) * 2. * retau
+        z = np.where(z >= retau, 2. * retau - z, z)
+        u1d = np.where(z <= 11.6, z, 2.5 * np.log(z) + 5.5)
+        is_noise = True; is_mean = True
+    elif inivel == "hcp":                                     # initflow.f90:93-102
+        zz = mirrored()
+        u1d = 6. * zz * (1. - zz) * ubulk; is_mean = True
+    elif inivel == "ant":                                     # initflow.f90:134-156 (Antuono, JFM 890, A23)
+        a = 4. * np.sqrt(2.) / 3. / np.sqrt(3.)
+        zcc = (zc[kk] / l[2] * 2. * pi + 0.5 * pi)[None, None, :]; zff = (zf[kk] / l[2] * 2. * pi + 0.5 * pi)[None, None, :]
+        yc = (j + lo[1] - 1 - .5) * dl[1] / l[1] * 2. * pi + 0.5 * pi; yf = (j + lo[1] - 1 - .0) * dl[1] / l[1] * 2. * pi + 0.5 * pi
+        xc = (i + lo[0] - 1 - .5) * dl[0] / l[0] * 2. * pi + 0.5 * pi; xf = (i + lo[0] - 1 - .0) * dl[0] / l[0] * 2. * pi + 0.5 * pi
+        u[I] = a * (np.sin(xf - 5. * pi / 6.) * np.cos(yc - 1. * pi / 6.) * np.sin(zcc) -
+                    np.sin(xf - 1. * pi / 6.) * np.sin(yc) * np.cos(zcc - 5. * pi / 6.)) * uref
+        v[I] = a * (np.sin(xc) * np.sin(yf - 5. * pi / 6.) * np.sin(zcc - 1. * pi / 6.) -
+                    np.cos(xc - 5. * pi / 6.) * np.sin(yf - 1. * pi / 6.) * np.sin(zcc)) * uref
+        w[I] = a * (np.cos(xc - 1. * pi / 6.) * np.sin(yc) * np.sin(zff - 5. * pi / 6.) -
+                    np.sin(xc) * np.cos(yc - 5. * pi / 6.) * np.sin(zff - 1. * pi / 6.)) * uref
+        p[I] = -(u[I] ** 2 + v[I] ** 2 + w[I] ** 2) / 2.
+    elif inivel in ("pdc", "hdc"):
         lref = l[2] / 2.
+        if inivel != "pdc":
+            lref = 2. * lref
         if deck.is_wallturb:
             uref = (deck.bforce[0] * lref) ** 0.5
             retau = uref * lref / visc
@@ -91,7 +143,8 @@ def initflow(deck, lo, n, zc, zf, dzc, dzf, mean_allreduce=None):
             ubulk = reb * visc / (2 * lref)
         else:
             ubulk = deck.bforce[0] * lref ** 2 / (3. * visc)
-        u1d = 6. * zcn * (1. - zcn) * ubulk; is_mean = True
+        zz = zcn if inivel == "pdc" else mirrored()
+        u1d = 6. * zz * (1. - zz) * ubulk; is_mean = True
     elif inivel == "tgv":
         zcc = (zc[kk] / l[2] * 2. * pi)[None, None, :]
         yc = (j + lo[1] - 1 - .5) * dl[1] / l[1] * 2. * pi; yf = (j + lo[1] - 1 - .0) * dl[1] / l[1] * 2. * pi
@@ -117,9 +170,12 @@ def initflow(deck, lo, n, zc, zf, dzc, dzf, mean_allreduce=None):
         u[:, 1:n[1] + 1, 1:n[2] + 1] = (.5 * lz ** 2 * (1. - eta ** 2 - 4. * (2. / pi) ** 3 * sum_term))[None, :, :]
         is_mean = True
     else:
-        raise ValueError("inivel '%s' needs the compiler-specific random_number stream (add_noise) or is unknown" % inivel)
+        raise ValueError("invalid name for initial velocity field: '%s'" % inivel)      # initflow.f90:202-209
     if u1d is not None:
         u[I] = u1d[None, None, :]
+    if is_noise:                                             # initflow.f90:223-227
+        for fld, seed in ((u, 123), (v, 456), (w, 789)):
+            add_noise(deck.ng, lo, n, seed, .05, fld)
     if is_mean and inivel != "iop":
         gvr = dzf / l[2] * (dl[0] / l[0]) * (dl[1] / l[1])
         part = float(np.cumsum((u[I] * gvr[None, None, 1:n[2] + 1]).ravel(order="F"))[-1])

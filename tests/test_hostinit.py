@@ -51,6 +51,53 @@ def test_initflow_and_initbc(name, kw):
             assert np.array_equal(x[ax], y[ax])
 
 
+@pytest.mark.parametrize("inivel", ["cou", "iop", "zer", "uni", "pdc", "hdc", "hcp", "ant", "tgw", "log", "hcl", "tbl"])
+@pytest.mark.parametrize("turb", [False, True])
+def test_every_initial_condition_of_the_reference(inivel, turb):
+    """All `inivel` values of initflow.f90:51-209 on the product side against the oracle's separate restatement, on a
+    2 x 2 decomposition; the noisy ones ('log', 'hcl', 'tbl') use the documented stand-in for the compiler's random_number
+    stream and must not depend on the decomposition."""
+    from oracle import decomp as odec
+    kw = dict(ng=(10, 8, 12))
+    dd, od = pd.deck_channel(**kw), op.deck_channel(**kw)
+    for d in (dd, od):
+        d.inivel = inivel; d.is_wallturb = turb
+        d.bforce = (0.3, 0., 0.)
+        d.bcvel = d.bcvel.copy(); d.bcvel[0, 2, 0] = 1.0; d.bcvel[1, 2, 0] = -0.5
+    ng = list(dd.ng)
+    dzc, dzf, zc, zf = hostinit.initgrid(dd.gtype, ng[2], dd.gr, dd.l[2])
+    glob = [np.zeros(ng, order="F") for _ in range(4)]
+    dims = (2, 2)
+    parts = []
+    for r in range(4):
+        lo, hi, n = odec.partition(ng, (1, 2, 3), dims, (r // 2, r % 2))
+        ksl = slice(lo[2] - 1, hi[2] + 2)
+        parts.append((lo, hi, n, ksl))
+    def allsum_factory(fn, deck):
+        # set_mean needs the global sum: first pass collects the partial sums, second pass uses their total
+        tot = []
+        for lo, hi, n, ksl in parts:
+            fn(deck, lo, n, zc[ksl], zf[ksl], dzc[ksl], dzf[ksl], lambda x: tot.append(x) or x)
+        return float(np.sum(tot))
+    tp, to = allsum_factory(hostinit.initflow, dd), allsum_factory(o_initflow, od)
+    for lo, hi, n, ksl in parts:
+        a = hostinit.initflow(dd, lo, n, zc[ksl], zf[ksl], dzc[ksl], dzf[ksl], lambda x: tp)
+        b = o_initflow(od, lo, n, zc[ksl], zf[ksl], dzc[ksl], dzf[ksl], lambda x: to)
+        for q, (x, y) in enumerate(zip(a, b)):
+            assert np.abs(x - y).max() <= 4e-15 * max(np.abs(y).max(), 1e-30), (inivel, q)
+            glob[q][lo[0] - 1:hi[0], lo[1] - 1:hi[1], lo[2] - 1:hi[2]] = x[1:-1, 1:-1, 1:-1]
+    # decomposition independence: one rank gives the same field (up to the rounding of the set_mean sum)
+    one = hostinit.initflow(dd, [1, 1, 1], ng, zc, zf, dzc, dzf)
+    for q in range(4):
+        assert np.abs(one[q][1:-1, 1:-1, 1:-1] - glob[q]).max() <= 1e-13 * max(np.abs(glob[q]).max(), 1e-30), (inivel, q)
+    if inivel in ("log", "hcl", "tbl"):
+        noise = one[1][1:-1, 1:-1, 1:-1]                                   # without the vortex pair v carries only the noise
+        if not turb:
+            assert 0.03 < np.abs(noise).max() <= 0.05 and abs(noise.mean()) < 0.01          # 2(rn-.5)*0.05
+    with pytest.raises(ValueError):
+        hostinit.initflow(dd.copy(inivel="xyz"), [1, 1, 1], ng, zc, zf, dzc, dzf)
+
+
 def test_deck_reader_on_reference_style_deck(tmp_path):
     txt = """&dns
 ng(1:3) = 192, 72, 48
