@@ -15,6 +15,7 @@ import time as _time
 import numpy as np
 
 from . import checkpoint
+from . import sanity
 
 SMALL = float(np.finfo(np.float64).eps) * 10 ** (15 // 2)      # epsilon(1._rp)*10**(precision(1._rp)/2), param.f90:24
 
@@ -147,6 +148,7 @@ def main(argv=None):
             dist.all_reduce(t)
             return float(t.item())
     sim = Simulation(deck, rank=rank, nranks=world, uid=uid, device=local)
+    sanity.test_sanity_input(deck, sim.n, sim.is_bound, sim.h["zc"])         # main.f90:284-286
     if not deck.restart and mean_allreduce is not None:
         init = sim.init_flow
         sim.init_flow = lambda: init(mean_allreduce)
