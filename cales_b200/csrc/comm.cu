@@ -545,5 +545,24 @@ int k_transpose_p2p(cales_ctx* ctx, int which, const double* src, PeerBuf* dst) 
 
 extern "C" int cales_transpose(cales_ctx* ctx, int which, const double* src, double* dst) {
   CHECK_CTX(ctx);
+  // a destination obtained from cales_peer_alloc takes the solver's own exchange (NVLink stores into the owners' pencils)
+  for (auto& kv : ctx->peerbufs)
+    if (kv.second.local == (void*)dst && ctx->nranks > 1) {
+      const bool colcomm = (which == 0 || which == 3);
+      if ((colcomm ? ctx->dims[0] : ctx->dims[1]) == 1) break;
+      int rc = k_barrier(ctx);                       // every rank is done reading the destination of the previous call
+      return rc ? rc : k_transpose_p2p(ctx, which, src, &kv.second);
+    }
   return k_transpose(ctx, which, src, dst);
+}
+
+extern "C" int cales_peer_alloc(cales_ctx* ctx, const char* name, long bytes, void** ptr) {
+  CHECK_CTX(ctx);
+  if (!name || !ptr || bytes <= 0) return cales_fail(ctx, CALES_ERR_INVALID, "peer_alloc: bad arguments");
+  *ptr = nullptr;
+  PeerBuf* pb = k_peer_buffer(ctx, (std::string("user_") + name).c_str(), (size_t)bytes);
+  if (pb) { *ptr = pb->local; return CALES_OK; }
+  if (ctx->nranks > 1 && ctx->p2p != 0) return ctx->err[0] ? CALES_ERR_NOMEM : cales_fail(ctx, CALES_ERR_CUDA, "peer_alloc failed");
+  *ptr = cales_scratch(ctx, (std::string("user_") + name).c_str(), (size_t)bytes, true);    // single rank / no peer access: plain device memory
+  return *ptr ? CALES_OK : CALES_ERR_NOMEM;
 }

@@ -36,10 +36,11 @@ class DevBound:
 
 
 class Simulation:
-    def __init__(self, deck, rank=0, nranks=1, uid=None, device=None, ave="channel"):
+    def __init__(self, deck, rank=0, nranks=1, uid=None, device=None, ave="channel", arith=None):
+        """arith: "fma" (the product build, libcales_b200.so) | "strict" (the bit-exact -fmad=false build) | None = lib.DEFAULT_ARITH"""
         if not torch.cuda.is_available():
             raise L.CalesError("no CUDA device: cales_b200 has no CPU fallback")
-        self.lib = L.load()
+        self.lib = L.load(arith)
         self.deck = deck
         self.rank, self.nranks = rank, nranks
         dev_index = device if device is not None else rank % torch.cuda.device_count()
@@ -50,7 +51,7 @@ class Simulation:
         diff = _DIFF[(bool(deck.impdiff), bool(deck.impdiff_1d))]
         rc = self.lib.cales_init(C.byref(self.ctx), L._ia(deck.ng), L._ia(deck.dims), deck.ipencil, L._ca(deck.cbcpre), rank,
                                  nranks, uid, dev_index, C.c_void_p(self.stream.cuda_stream), diff)
-        L.check(None, rc)
+        L.check(None, rc, self.lib)
         arrs = [np.zeros(3, dtype=np.int32) for _ in range(8)] + [np.zeros(6, dtype=np.int32) for _ in range(2)]
         self.chk(self.lib.cales_get_decomp(self.ctx, *[a.ctypes.data_as(L.c_int_p) for a in arrs]))
         (self.lo, self.hi, self.n, self.n_x_fft, self.n_y_fft, self.lo_z, self.hi_z, self.n_z, self.nb, self.is_bound_flat) = arrs
@@ -99,7 +100,7 @@ class Simulation:
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def chk(self, rc):
-        L.check(self.ctx, rc)
+        L.check(self.ctx, rc, self.lib)
 
     def ptr(self, nm):
         return C.c_void_p(self.fields[nm].data_ptr())

@@ -7,8 +7,13 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# CALES_B200_FMAD=1 selects the contraction-enabled build (make FMAD=true); the default is the parity build (-fmad=false)
-LIB_PATH = os.path.join(_HERE, "libcales_b200_fma.so" if os.environ.get("CALES_B200_FMAD") == "1" else "libcales_b200.so")
+# Two arithmetic variants of the same sources (cales_b200/csrc/Makefile):
+#   "fma"    libcales_b200.so         the product: fp64 contraction on (what the reference's own GPU build does)
+#   "strict" libcales_b200_strict.so  -fmad=false, bit-identical to a non-contracting CPU build (test build)
+# CALES_B200_ARITH=strict|fma picks the default of load(); both can live in one process (linked -Bsymbolic, RTLD_LOCAL).
+LIB_PATHS = {"fma": os.path.join(_HERE, "libcales_b200.so"), "strict": os.path.join(_HERE, "libcales_b200_strict.so")}
+DEFAULT_ARITH = os.environ.get("CALES_B200_ARITH", "fma")
+LIB_PATH = LIB_PATHS["fma"]
 
 c_int_p = C.POINTER(C.c_int)
 c_dbl_p = C.POINTER(C.c_double)
@@ -24,7 +29,7 @@ class CalesError(RuntimeError):
     pass
 
 
-_lib = None
+_libs = {}
 
 
 def _ia(a):
@@ -90,27 +95,32 @@ SIGNATURES = {
     "cales_gaussel": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     "cales_transpose": (C.c_int, [vp, C.c_int, vp, vp]),
     "cales_updthalo": (C.c_int, [vp, c_int_p, c_int_p, vp]),
+    "cales_peer_alloc": (C.c_int, [vp, C.c_char_p, C.c_long, C.POINTER(vp)]),
 }
 
 
-def load():
-    """Load libcales_b200.so and attach the signatures.  Fails loudly when it is absent."""
-    global _lib
-    if _lib is not None:
-        return _lib
-    if not os.path.exists(LIB_PATH):
-        raise CalesError("libcales_b200.so not found at %s: build it with `make -C cales_b200/csrc` "
-                         "(there is no CPU fallback)" % LIB_PATH)
-    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+def load(arith=None):
+    """Load one variant of the library ("fma" = libcales_b200.so, "strict" = libcales_b200_strict.so; None = the
+    default, DEFAULT_ARITH) and attach the signatures.  Fails loudly when it is absent."""
+    arith = arith or DEFAULT_ARITH
+    if arith in _libs:
+        return _libs[arith]
+    if arith not in LIB_PATHS:
+        raise CalesError("unknown arithmetic variant %r (fma | strict)" % (arith,))
+    path = LIB_PATHS[arith]
+    if not os.path.exists(path):
+        raise CalesError("%s not found: build it with `make -C cales_b200/csrc` (there is no CPU fallback)" % path)
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     for name, (res, args) in SIGNATURES.items():
         f = getattr(lib, name)
         f.restype = res
         f.argtypes = args
-    _lib = lib
+    lib.arith = arith
+    _libs[arith] = lib
     return lib
 
 
-def check(ctx, rc):
+def check(ctx, rc, lib=None):
     if rc != 0:
-        msg = load().cales_last_error(ctx)
+        msg = (lib or load()).cales_last_error(ctx)
         raise CalesError("libcales_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

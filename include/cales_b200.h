@@ -196,6 +196,11 @@ int cales_gaussel(cales_ctx* ctx, int nx, int ny, int n, int periodic, const dou
                   const double* c, const double* lambdaxy, double* p);
 /* pencil transposes (2decomp transpose_x_to_y etc. / cudecompTranspose*): which = 0 x->y, 1 y->z, 2 z->y, 3 y->x */
 int cales_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
+/* work array the library owns, zero-filled, mapped into every rank of the node (CUDA IPC over NVLink; the role of cuDecomp's
+ * cudecompMalloc, dependencies/cuDecomp/src/cudecomp.cc:913): a cales_transpose whose dst came from here stores each
+ * sub-box straight into its owner's pencil over NVLink (the solver's own exchange) instead of pack + NCCL send/recv + unpack.
+ * Collective over all ranks; plain device memory when peer access is unavailable.  Freed by cales_finalize. */
+int cales_peer_alloc(cales_ctx* ctx, const char* name, long bytes, void** ptr);
 /* halo exchange alone (src/bound.f90:619-723) */
 int cales_updthalo(cales_ctx* ctx, const int n[3], const int nb[6], double* p);
 

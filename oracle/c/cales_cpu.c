@@ -559,6 +559,15 @@ int cales_cpu_threads(void) {
 #endif
 }
 
+/* bench.py sets the thread count explicitly (torchrun exports OMP_NUM_THREADS=1 to its workers) */
+void cales_cpu_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 void cales_cpu_free(void *h) {
   cpu_t *s = (cpu_t *)h;
   if (!s) return;

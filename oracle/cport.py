@@ -35,6 +35,7 @@ def load():
         lib.cales_cpu_divmax.argtypes = [C.c_void_p]; lib.cales_cpu_divmax.restype = C.c_double
         lib.cales_cpu_chkdt.argtypes = [C.c_void_p]; lib.cales_cpu_chkdt.restype = C.c_double
         lib.cales_cpu_threads.restype = C.c_int
+        lib.cales_cpu_set_threads.argtypes = [C.c_int]; lib.cales_cpu_set_threads.restype = None
         _LIB = lib
     return _LIB
 
@@ -46,11 +47,14 @@ def _dp(a):
 class CSim:
     """Mirror of oracle.main.Sim for an all-periodic 'smag' deck on one rank, backed by the C library."""
 
-    def __init__(self, deck):
+    def __init__(self, deck, threads=None):
+        """threads: OpenMP threads to use (None = the OpenMP default, i.e. OMP_NUM_THREADS or all cores)."""
         from .initflow import initflow
         from .initgrid import initgrid
         assert (deck.cbcvel == "P").all() and deck.sgstype == "smag" and not deck.impdiff and tuple(deck.dims) == (1, 1)
         self.lib = load()
+        if threads:
+            self.lib.cales_cpu_set_threads(int(threads))
         self.deck = deck
         n = self.n = tuple(int(x) for x in deck.ng)
         dzc, dzf, zc, zf = initgrid(deck.gtype, n[2], deck.gr, deck.l[2])

@@ -21,10 +21,9 @@ def test_oracle_reproduces_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(GOLDEN))
-def test_cuda_reproduces_golden(name):
-    import torch
-    if not torch.cuda.is_available():
-        pytest.fail("no CUDA device visible")
+def test_cuda_reproduces_golden(name, arith):
+    from conftest import need_gpu
+    need_gpu()
     import cales_b200.deck as pd
     from cales_b200.driver import Simulation
     deck, kw, nsteps = GOLDEN[name]

@@ -13,14 +13,14 @@ torch = pytest.importorskip("torch")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(case, prow, pcol, nsteps, port):
+def run(case, prow, pcol, nsteps, port, arith="-", impdiff=None):
     n = prow * pcol
-    if not torch.cuda.is_available():
-        pytest.fail("no CUDA device visible")
+    from conftest import need_gpu
+    need_gpu()
     if torch.cuda.device_count() < n:
         pytest.skip("needs %d GPUs, box has %d" % (n, torch.cuda.device_count()))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
-           "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), case, str(prow), str(pcol), str(nsteps)]
+           "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), case, str(prow), str(pcol), str(nsteps), arith] + ([impdiff] if impdiff else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-3000:])
