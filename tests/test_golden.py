@@ -32,10 +32,14 @@ def test_cuda_reproduces_golden(name, arith):
     s.init_flow(); s.start()
     for _ in range(nsteps):
         res = s.step(icheck=1)
+    # velocities are normalised by the largest velocity component (a component that is identically zero in the fixture,
+    # e.g. v of the duct, carries x*y - x*y = O(1e-19) contraction residue in the fma build)
+    vscale = max(np.abs(g[k]).max() for k in ("u", "v", "w"))
     for k in ("u", "v", "w", "p", "visct"):
         a = s.get(k)[1:-1, 1:-1, 1:-1]
         if k == "p":
             a = a - a.mean()
-        assert np.abs(a - g[k]).max() <= 1e-10 * max(np.abs(g[k]).max(), 1e-30), k
+        scale = vscale if k in ("u", "v", "w") else np.abs(g[k]).max()
+        assert np.abs(a - g[k]).max() <= 1e-10 * max(scale, 1e-30), k
     assert abs(s.dt - float(g["dt"])) <= 1e-10 * float(g["dt"]) and res[1] < 1e-11
     s.close()

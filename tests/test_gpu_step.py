@@ -20,11 +20,17 @@ def _gpu(arith):
     need_gpu()
 
 
-def relerr(a, b, demean=False):
+def relerr(a, b, demean=False, scale=None):
     a = a[1:-1, 1:-1, 1:-1]; b = b[1:-1, 1:-1, 1:-1]
     if demean:
         a = a - a.mean(); b = b - b.mean()
-    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+    return float(np.abs(a - b).max() / max(np.abs(b).max() if scale is None else scale, 1e-300))
+
+
+def vel_scale(ref):
+    """velocity components are normalised by the largest of the three (a component that is identically zero in the
+    reference, e.g. v of the laminar duct, carries O(1e-19) contraction residue x*y - x*y in the fma build)"""
+    return max(float(np.abs(ref[k][1:-1, 1:-1, 1:-1]).max()) for k in ("u", "v", "w"))
 
 
 def make_pair(name, ng=None, **kw):
@@ -66,8 +72,9 @@ def run_pair(case, nsteps, impdiff=None):
 
 def compare(o, g, tol):
     errs = {}
+    vs = vel_scale({"u": o.U[0], "v": o.V[0], "w": o.W[0]})
     for nm, on in (("u", "U"), ("v", "V"), ("w", "W"), ("p", "P"), ("visct", "VISCT")):
-        errs[nm] = relerr(g.get(nm), getattr(o, on)[0], demean=(nm == "p"))
+        errs[nm] = relerr(g.get(nm), getattr(o, on)[0], demean=(nm == "p"), scale=vs if nm in "uvw" else None)
     bad = {k: v for k, v in errs.items() if not v <= tol}
     assert not bad, errs
     return errs
@@ -217,8 +224,9 @@ def test_full_size_properties():
 # ---- BASELINE-size parity: the CUDA path against the CPU restatements at the sizes the metric is quoted on ----
 def _errs(g, ref, names=("u", "v", "w", "p", "visct")):
     out = {}
+    vs = vel_scale(ref)
     for nm in names:
-        out[nm] = relerr(g.get(nm), ref[nm], demean=(nm == "p"))
+        out[nm] = relerr(g.get(nm), ref[nm], demean=(nm == "p"), scale=vs if nm in "uvw" else None)
     return out
 
 
@@ -243,14 +251,16 @@ def test_fullsize_tgv256_vs_c_port(arith):
     assert all(v <= 1e-10 for v in errs.values()), errs
     assert dmg < 1e-11 and abs(dmg - dmo) <= 1e-12 * float(np.abs(o.f["u"]).max()) * max(g.deck.dli), (dmg, dmo)
     assert abs(g.dt - o.dt) <= 1e-10 * o.dt
-    # one solver call on the same right-hand side: the fillps output of the restatement
-    o.lib.cales_cpu_fillps(o.h, 1. / o.dt)
-    rhs = o.f["pp"].copy(order="F")
+    # one solver call on the same right-hand side on both sides: a seeded random field with zero mean (the compatibility
+    # condition of the singular all-periodic problem; the fillps output of a projected field would be pure round-off)
+    rng = np.random.default_rng(3)
+    rhs = np.asfortranarray(rng.standard_normal(o.f["pp"].shape))
+    rhs[1:-1, 1:-1, 1:-1] -= rhs[1:-1, 1:-1, 1:-1].mean()
     g.set_fields(pp=rhs)
     g.solver(g.poi, "pp")
+    o.f["pp"][...] = rhs
     o.lib.cales_cpu_solver(o.h)
     ref = o.f["pp"].copy(order="F")
-    rng = np.random.default_rng(3)
     o.f["pp"][...] = rhs * (1. + 1.1e-16 * np.sign(rng.standard_normal(rhs.shape)))
     o.lib.cales_cpu_solver(o.h)
     floor = relerr(o.f["pp"], ref, demean=True)
