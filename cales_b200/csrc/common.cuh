@@ -66,6 +66,7 @@ struct cales_ctx {
   int rk_swap = 0;                      // which of the two RHS sets is "old" (rk.f90:98-100)
   bool rk_first = true;
   bool sgs_first = true;
+  long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;
   std::map<int, FftTables> tables;
   long launches = 0;                    // kernels launched by this library (bench.py gpu_launches)

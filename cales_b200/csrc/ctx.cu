@@ -137,12 +137,14 @@ extern "C" int cales_init(cales_ctx** out, const int ng[3], const int dims[2], i
 }
 
 void k_gaussel_tab_free(cales_ctx* ctx);
+void k_step_graphs_free(cales_ctx* ctx);
 
 extern "C" int cales_finalize(cales_ctx* ctx) {
   CHECK_CTX(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   comm_finalize(ctx);
+  k_step_graphs_free(ctx);
   k_gaussel_tab_free(ctx);
   for (auto& kv : ctx->scratch) cudaFree(kv.second.first);
   for (auto& kv : ctx->tables) { cudaFree(kv.second.w); cudaFree(kv.second.h); }

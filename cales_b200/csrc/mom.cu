@@ -20,17 +20,31 @@
 //     it commutes with rounding, so it is folded into the metric factor of the difference, 0.25*dxi etc. (exact unless a
 //     flux underflows, |flux| < 2^-1020).
 // The association order of everything else is the reference's; the library is built with -fmad=false.
-template <int MODE, bool V16>  // MODE 0 explicit, 1 _IMPDIFF, 2 _IMPDIFF + _IMPDIFF_1D; V16: 16-byte plane staging (tile.cuh)
+// Fused RK update (RK > 0, explicit diffusion): the low-storage update of rk.f90:77-94 is applied to the right-hand side
+// while it is still in registers -- the pressure is staged as a fifth tile field, the old right-hand side (RK == 2:
+// rkpar(2) /= 0) is read once, and the new velocity goes to a SECOND set of arrays (un,vn,wn: the stencil of the
+// neighbouring tiles still reads the old one), so that rk = mom + update moves 112 instead of 160 B/cell.  Same
+// operations in the same order as mom_k + rk_update_k: identical bits.
+struct RkFuse {
+  double f1, f2, f12, bfx, bfy, bfz;
+  const double* p;                       // pressure (haloed)
+  const double *duo, *dvo, *dwo;         // old right-hand side (halo-free)
+  double *un, *vn, *wn;                  // updated velocity (haloed; interior written)
+};
+
+template <int MODE, bool V16, int RK>  // MODE 0 explicit, 1 _IMPDIFF, 2 _IMPDIFF + _IMPDIFF_1D; V16: 16-byte plane staging (tile.cuh)
 __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci, const double* __restrict__ dzfi,
                                                     double visc, const double* __restrict__ u, const double* __restrict__ v,
                                                     const double* __restrict__ w, const double* __restrict__ s,
                                                     double* __restrict__ dudt, double* __restrict__ dvdt, double* __restrict__ dwdt,
-                                                    double* __restrict__ dudtd, double* __restrict__ dvdtd, double* __restrict__ dwdtd, int kc) {
-  extern __shared__ __align__(16) double smem[];   // [4 slots][4 fields][PLANE]: planes k, k+1 in use, k+2 and k+3 in flight
+                                                    double* __restrict__ dudtd, double* __restrict__ dvdtd, double* __restrict__ dwdtd, int kc,
+                                                    const __grid_constant__ RkFuse R) {
+  constexpr int NF = RK ? 5 : 4;
+  extern __shared__ __align__(16) double smem[];   // [4 slots][NF fields][PLANE]: planes k, k+1 in use, k+2 and k+3 in flight
   const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
-  Stager<4, V16> st(d, i0, j0, u, v, w, s, smem, k0 - 1, k1 + 1);
+  Stager<NF, V16> st(d, i0, j0, u, v, w, s, smem, k0 - 1, k1 + 1, R.p);
   st.template issue<0>();
   st.template issue<1>();
   st.template issue<2>();
@@ -39,7 +53,7 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
   __syncthreads();
   const bool active = i <= d.n1 && j <= d.n2;
   const double* const sm = smem + (threadIdx.x + 1) + PX * (threadIdx.y + 1);     // my cell in field 0 of slot 0
-  constexpr int SL = 4 * PLANE;
+  constexpr int SL = NF * PLANE;
   const long n12 = (long)d.n1 * d.n2;
   const double qdxi = 0.25 * dxi, qdyi = 0.25 * dyi;
   // k-1/2 quantities of level k0 = k+1/2 quantities of level k0-1 (planes k0-1, k0 = slots 0, 1)
@@ -62,6 +76,7 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
   }
   __syncthreads();                   // slot 0 (plane k0-1) may now be overwritten
   long o = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k0 - 1);   // dudt(n1,n2,n3): no halo
+  long ch = RK ? d.idx(i, j, k0) : 0;                          // the same cell in a haloed array
   int k = k0;
   // one level: planes k, k+1 in slots SC, SP; plane k+3 goes into slot SN (which held plane k-1).  Threads outside the
   // array compute on whatever their tile cells hold and store nothing.
@@ -146,9 +161,25 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
                             (fzz_kp - fzz_km) * dzci_k;
       if (active) {
         if (MODE == 0) {                                                    // mom.f90:296-302
-          dudt[o] = dudt_s + dudtd_xy_s + dudtd_z_s;
-          dvdt[o] = dvdt_s + dvdtd_xy_s + dvdtd_z_s;
-          dwdt[o] = dwdt_s + dwdtd_xy_s + dwdtd_z_s;
+          const double du_ = dudt_s + dudtd_xy_s + dudtd_z_s;
+          const double dv_ = dvdt_s + dvdtd_xy_s + dvdtd_z_s;
+          const double dw_ = dwdt_s + dwdtd_xy_s + dwdtd_z_s;
+          dudt[o] = du_; dvdt[o] = dv_; dwdt[o] = dw_;
+          if (RK) {                                                         // rk.f90:77-86
+            const double* pc_ = uc + 4 * PLANE;
+            const double p_ccc = pc_[0];
+            double un_, vn_, wn_;
+            if (RK == 2) {
+              un_ = u_ccc + R.f1 * du_ + R.f2 * R.duo[o] + R.f12 * (R.bfx - dxi * (pc_[1] - p_ccc));
+              vn_ = v_ccc + R.f1 * dv_ + R.f2 * R.dvo[o] + R.f12 * (R.bfy - dyi * (pc_[PX] - p_ccc));
+              wn_ = w_ccc + R.f1 * dw_ + R.f2 * R.dwo[o] + R.f12 * (R.bfz - dzci_k * (up[4 * PLANE] - p_ccc));
+            } else {
+              un_ = u_ccc + R.f1 * du_ + R.f12 * (R.bfx - dxi * (pc_[1] - p_ccc));
+              vn_ = v_ccc + R.f1 * dv_ + R.f12 * (R.bfy - dyi * (pc_[PX] - p_ccc));
+              wn_ = w_ccc + R.f1 * dw_ + R.f12 * (R.bfz - dzci_k * (up[4 * PLANE] - p_ccc));
+            }
+            R.un[ch] = un_; R.vn[ch] = vn_; R.wn[ch] = wn_;
+          }
         } else if (MODE == 1) {                                             // mom.f90:286-295
           dudt[o] = dudt_s; dvdt[o] = dvdt_s; dwdt[o] = dwdt_s;
           dudtd[o] = dudtd_xy_s + dudtd_z_s;
@@ -167,6 +198,7 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
     tile_wait_1();                   // plane k+2 has landed (k+3 may still be in flight)
     __syncthreads();                 // ... for everyone, and everyone is done reading plane k
     o += n12;
+    if (RK) ch += d.s2;
     return ++k <= k1;
   };
   while (step(Slot<1>{}, Slot<2>{}, Slot<0>{}) && step(Slot<2>{}, Slot<3>{}, Slot<1>{}) && step(Slot<3>{}, Slot<0>{}, Slot<2>{}) &&
@@ -175,17 +207,29 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
 
 static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, const double* dzci, const double* dzfi, double visc,
                       const double* u, const double* v, const double* w, const double* visct, double* dudt, double* dvdt,
-                      double* dwdt, double* dudtd, double* dvdtd, double* dwdtd) {
+                      double* dwdt, double* dudtd, double* dvdtd, double* dwdtd, const RkFuse* rk = nullptr) {
   Dims d(n);
   long cols = (long)cdiv(n[0], TX) * cdiv(n[1], TY);
   const int kc = pick_chunk(cols, n[2], 148 * 2, 12, 2);
   dim3 g(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc)), b(TX, TY);
-  const size_t sh = TSLOTS * 4 * PLANE * sizeof(double);
-  const bool v16 = tile_v16(n[0], u, v, w, visct);
-#define MOM_GO(M_, V_) mom_k<M_, V_><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc)
-  if (ctx->diffusion == CALES_DIFF_EXPLICIT) { if (v16) MOM_GO(0, true); else MOM_GO(0, false); }
-  else if (ctx->diffusion == CALES_DIFF_IMPLICIT_3D) { if (v16) MOM_GO(1, true); else MOM_GO(1, false); }
-  else { if (v16) MOM_GO(2, true); else MOM_GO(2, false); }
+  const size_t sh = TSLOTS * (rk ? 5 : 4) * PLANE * sizeof(double);
+  const bool v16 = tile_v16(n[0], u, v, w, visct) && (!rk || ((uintptr_t)rk->p & 15) == 0);
+  RkFuse R;
+  memset(&R, 0, sizeof R);
+  if (rk) R = *rk;
+#define MOM_GO(M_, V_, R_)                                                                                           \
+  {                                                                                                                  \
+    static bool attr = false;                                                                                        \
+    if (!attr) { attr = true; cudaFuncSetAttribute(mom_k<M_, V_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSLOTS * 5 * PLANE * sizeof(double))); } \
+    mom_k<M_, V_, R_><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc, R); \
+  }
+  if (rk) {
+    if (ctx->diffusion != CALES_DIFF_EXPLICIT) return cales_fail(ctx, CALES_ERR_INVALID, "fused mom+rk update needs explicit diffusion");
+    if (rk->f2 != 0.) { if (v16) MOM_GO(0, true, 2) else MOM_GO(0, false, 2) }
+    else { if (v16) MOM_GO(0, true, 1) else MOM_GO(0, false, 1) }
+  } else if (ctx->diffusion == CALES_DIFF_EXPLICIT) { if (v16) MOM_GO(0, true, 0) else MOM_GO(0, false, 0) }
+  else if (ctx->diffusion == CALES_DIFF_IMPLICIT_3D) { if (v16) MOM_GO(1, true, 0) else MOM_GO(1, false, 0) }
+  else { if (v16) MOM_GO(2, true, 0) else MOM_GO(2, false, 0) }
 #undef MOM_GO
   KERNEL_CHECK(ctx);
   return CALES_OK;
@@ -290,13 +334,17 @@ __global__ void bulkf_k(const double* __restrict__ mean, int is_u, int is_v, int
 
 int k_bulk_mean_dev(cales_ctx* ctx, const int n[3], const double* gvr, const double* p, double* out);
 
-// device-resident rk: leaves f(3) in ctx->fdev, no host synchronisation
+// device-resident rk: leaves f(3) in ctx->fdev, no host synchronisation.  With un/vn/wn (explicit diffusion only) the
+// update is fused into the momentum kernel and the new velocity is written THERE instead of in place (see RkFuse).
 int k_rk_dev(cales_ctx* ctx, const double rkpar[2], const int n[3], const double dli[3], const double* dzci, const double* dzfi,
              const double* gvr_c, const double* gvr_f, double visc, double dt, const double* p, const int is_forced[3],
-             const double velf[3], const double bforce[3], const double* visct, double* u, double* v, double* w) {
+             const double velf[3], const double bforce[3], const double* visct, double* u, double* v, double* w,
+             double* un = nullptr, double* vn = nullptr, double* wn = nullptr) {
   const double factor1 = rkpar[0] * dt, factor2 = rkpar[1] * dt, factor12 = factor1 + factor2;
   const size_t nb = (size_t)n[0] * n[1] * n[2] * sizeof(double);
   const bool imp = ctx->diffusion != CALES_DIFF_EXPLICIT;
+  const bool fused = un != nullptr;
+  if (fused && imp) return cales_fail(ctx, CALES_ERR_INVALID, "fused rk needs explicit diffusion");
   double* r[9];
   static const char* names[9] = {"rk_du0", "rk_dv0", "rk_dw0", "rk_du1", "rk_dv1", "rk_dw1", "rk_dud", "rk_dvd", "rk_dwd"};
   for (int q = 0; q < (imp ? 9 : 6); ++q) {
@@ -311,25 +359,33 @@ int k_rk_dev(cales_ctx* ctx, const double rkpar[2], const int n[3], const double
   }
   double** nw = ctx->rk_swap ? r + 3 : r;            // dudtrk
   double** ol = ctx->rk_swap ? r : r + 3;            // dudtrko
-  int rc = mom_launch(ctx, n, dli[0], dli[1], dzci, dzfi, visc, u, v, w, visct, nw[0], nw[1], nw[2], r[6], r[7], r[8]);
-  if (rc) return rc;
+  int rc;
   Dims d(n);
   long cols = (long)cdiv(n[0], BX) * cdiv(n[1], BY);
   const int kc = pick_chunk(cols, n[2], 148 * 4, 8, 1);
   dim3 g(cdiv(n[0], BX), cdiv(n[1], BY), cdiv(n[2], kc)), b(BX, BY);
+  if (fused) {
+    RkFuse R;
+    R.f1 = factor1; R.f2 = factor2; R.f12 = factor12; R.bfx = bforce[0]; R.bfy = bforce[1]; R.bfz = bforce[2];
+    R.p = p; R.duo = ol[0]; R.dvo = ol[1]; R.dwo = ol[2]; R.un = un; R.vn = vn; R.wn = wn;
+    if ((rc = mom_launch(ctx, n, dli[0], dli[1], dzci, dzfi, visc, u, v, w, visct, nw[0], nw[1], nw[2], nullptr, nullptr, nullptr, &R))) return rc;
+  } else {
+    if ((rc = mom_launch(ctx, n, dli[0], dli[1], dzci, dzfi, visc, u, v, w, visct, nw[0], nw[1], nw[2], r[6], r[7], r[8]))) return rc;
 #define RKU(IMP_, F2_) rk_update_k<IMP_, F2_><<<g, b, 0, ctx->stream>>>(d, factor1, factor2, factor12, dli[0], dli[1], dzci, bforce[0], bforce[1], \
                                                                          bforce[2], p, nw[0], nw[1], nw[2], ol[0], ol[1], ol[2], r[6], r[7], r[8], u, v, w, kc)
-  if (imp) { if (factor2 != 0.) RKU(1, 1); else RKU(1, 0); }
-  else { if (factor2 != 0.) RKU(0, 1); else RKU(0, 0); }
+    if (imp) { if (factor2 != 0.) RKU(1, 1); else RKU(1, 0); }
+    else { if (factor2 != 0.) RKU(0, 1); else RKU(0, 0); }
 #undef RKU
-  KERNEL_CHECK(ctx);
+    KERNEL_CHECK(ctx);
+  }
   ctx->rk_swap ^= 1;                                 // rk.f90:98-100
   // cmpt_bulk_forcing (rk.f90:197-222)
+  double* uo = fused ? un : u; double* vo = fused ? vn : v; double* wo = fused ? wn : w;
   double* mean = ctx->red + 8;
   CUDA_TRY(ctx, cudaMemsetAsync(mean, 0, 3 * sizeof(double), ctx->stream));
-  if (is_forced[0] && (rc = k_bulk_mean_dev(ctx, n, gvr_f, u, mean + 0))) return rc;
-  if (is_forced[1] && (rc = k_bulk_mean_dev(ctx, n, gvr_f, v, mean + 1))) return rc;
-  if (is_forced[2] && (rc = k_bulk_mean_dev(ctx, n, gvr_c, w, mean + 2))) return rc;
+  if (is_forced[0] && (rc = k_bulk_mean_dev(ctx, n, gvr_f, uo, mean + 0))) return rc;
+  if (is_forced[1] && (rc = k_bulk_mean_dev(ctx, n, gvr_f, vo, mean + 1))) return rc;
+  if (is_forced[2] && (rc = k_bulk_mean_dev(ctx, n, gvr_c, wo, mean + 2))) return rc;
   bulkf_k<<<1, 1, 0, ctx->stream>>>(mean, is_forced[0], is_forced[1], is_forced[2], velf[0], velf[1], velf[2], ctx->fdev);
   KERNEL_CHECK(ctx);
   if (imp) {

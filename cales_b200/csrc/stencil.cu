@@ -50,13 +50,18 @@ extern "C" int cales_fillps(cales_ctx* ctx, const int n[3], const double dli[3],
 // The update covers whole haloed planes, so threads are laid over the linear plane index q = i + (n1+2) j (no partial
 // tiles, perfectly coalesced); CU levels are loaded together before any store.
 #define CU 2
+// FUSED (the fused substep, substep.cu): the corrected velocity is written to OTHER arrays than the ones read (uo,vo,wo:
+// the caller's fields; u,v,w: the library's intermediate velocity), rows the correction leaves alone are copied, and the
+// explicit pressure update p = p + pp (updatep.f90:45-47) of the interior rides along -- one pass instead of two.
+template <bool FUSED>
 __global__ void __launch_bounds__(256) correc_k(Dims d, double factori, double factorj, double dt, const double* __restrict__ dzci,
-                                                const double* __restrict__ p, double* __restrict__ u,
-                                                double* __restrict__ v, double* __restrict__ w, int kc) {
+                                                const double* __restrict__ p, const double* u, const double* v, const double* w,
+                                                double* uo, double* vo, double* wo, double* __restrict__ pres, int kc) {
   const long q = blockIdx.x * 256L + threadIdx.x;
   if (q >= d.s2) return;
   const int j = (int)(q / d.s1), i = (int)(q - j * d.s1);
   const bool du = i <= d.n1, dv = j <= d.n2;
+  const bool inner = FUSED && i >= 1 && i <= d.n1 && j >= 1 && j <= d.n2;
   const int k0 = blockIdx.y * kc, k1 = min(k0 + kc - 1, d.n3 + 1);
   const long s1 = d.s1, s2 = d.s2;
   long c = q + s2 * k0;
@@ -65,27 +70,30 @@ __global__ void __launch_bounds__(256) correc_k(Dims d, double factori, double f
   double pc = p[c];
   int k = k0;
   for (; k + CU - 1 <= k1 && k + CU - 1 <= d.n3; k += CU, c += CU * s2) {
-    double pk[CU], pi[CU], pj[CU], uu[CU], vv[CU], ww[CU], dz[CU];
+    double pk[CU], pi[CU], pj[CU], uu[CU], vv[CU], ww[CU], dz[CU], pr[CU];
 #pragma unroll
     for (int r = 0; r < CU; ++r) {
       const long cr = c + r * s2;
       pk[r] = p[cr + s2]; pi[r] = p[cr + oi]; pj[r] = p[cr + oj];
       uu[r] = u[cr]; vv[r] = v[cr]; ww[r] = w[cr]; dz[r] = dzci[k + r];
+      if (FUSED) pr[r] = (inner && k + r >= 1) ? pres[cr] : 0.;
     }
 #pragma unroll
     for (int r = 0; r < CU; ++r) {
       const long cr = c + r * s2;
-      if (du) u[cr] = uu[r] - factori * (pi[r] - pc);
-      if (dv) v[cr] = vv[r] - factorj * (pj[r] - pc);
-      w[cr] = ww[r] - dt * dz[r] * (pk[r] - pc);
+      if (du) uo[cr] = uu[r] - factori * (pi[r] - pc); else if (FUSED) uo[cr] = uu[r];
+      if (dv) vo[cr] = vv[r] - factorj * (pj[r] - pc); else if (FUSED) vo[cr] = vv[r];
+      wo[cr] = ww[r] - dt * dz[r] * (pk[r] - pc);
+      if (FUSED && inner && k + r >= 1) pres[cr] = pr[r] + pc;
       pc = pk[r];
     }
   }
   for (; k <= k1; ++k, c += s2) {
     const double pk = k <= d.n3 ? p[c + s2] : 0.0;
-    if (du) u[c] = u[c] - factori * (p[c + oi] - pc);
-    if (dv) v[c] = v[c] - factorj * (p[c + oj] - pc);
-    if (k <= d.n3) w[c] = w[c] - dt * dzci[k] * (pk - pc);
+    if (du) uo[c] = u[c] - factori * (p[c + oi] - pc); else if (FUSED) uo[c] = u[c];
+    if (dv) vo[c] = v[c] - factorj * (p[c + oj] - pc); else if (FUSED) vo[c] = v[c];
+    if (k <= d.n3) wo[c] = w[c] - dt * dzci[k] * (pk - pc); else if (FUSED) wo[c] = w[c];
+    if (FUSED && inner && k >= 1 && k <= d.n3) pres[c] = pres[c] + pc;
     pc = pk;
   }
 }
@@ -96,7 +104,18 @@ extern "C" int cales_correc(cales_ctx* ctx, const int n[3], const double dli[3],
   Dims d(n);
   const int cols = cdiv(d.s2, 256);
   const int kc = pick_chunk(cols, n[2] + 2, 148 * 8, 8, 1);
-  correc_k<<<dim3(cols, cdiv(n[2] + 2, kc)), 256, 0, ctx->stream>>>(d, dt * dli[0], dt * dli[1], dt, dzci, p, u, v, w, kc);
+  correc_k<false><<<dim3(cols, cdiv(n[2] + 2, kc)), 256, 0, ctx->stream>>>(d, dt * dli[0], dt * dli[1], dt, dzci, p, u, v, w, u, v, w, nullptr, kc);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
+// correc from (us,vs,ws) into (u,v,w) + explicit updatep, one pass (fused substep)
+int k_correc_updatep(cales_ctx* ctx, const int n[3], const double dli[3], const double* dzci, double dt, const double* pp,
+                     const double* us, const double* vs, const double* ws, double* u, double* v, double* w, double* p) {
+  Dims d(n);
+  const int cols = cdiv(d.s2, 256);
+  const int kc = pick_chunk(cols, n[2] + 2, 148 * 8, 8, 1);
+  correc_k<true><<<dim3(cols, cdiv(n[2] + 2, kc)), 256, 0, ctx->stream>>>(d, dt * dli[0], dt * dli[1], dt, dzci, pp, us, vs, ws, u, v, w, p, kc);
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }

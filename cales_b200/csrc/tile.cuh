@@ -34,7 +34,7 @@ struct Stager {
   int knext, klast;         // next plane to issue, last plane this CTA needs
 
   __device__ __forceinline__ Stager(const Dims& d, int i0, int j0, const double* f0, const double* f1, const double* f2,
-                                    const double* f3, const double* smem, int kfirst, int klast_) {
+                                    const double* f3, const double* smem, int kfirst, int klast_, const double* f4 = nullptr) {
     const int t = threadIdx.x + TX * threadIdx.y;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
     s2 = d.s2; knext = kfirst; klast = klast_;
@@ -44,7 +44,7 @@ struct Stager {
       const int f = q / CPP, rem = q - f * CPP;
       const int lj = rem / CPR, li = (rem - lj * CPR) * CE;
       const int i = i0 - 1 + li, j = j0 - 1 + lj;
-      const double* fb = f == 0 ? f0 : f == 1 ? f1 : f == 2 ? f2 : f3;
+      const double* fb = f == 0 ? f0 : f == 1 ? f1 : f == 2 ? f2 : f == 3 ? f3 : f4;
       const bool ok = q < NCH && i + CE - 1 <= d.n1 + 1 && j <= d.n2 + 1;
       src[r] = ok ? fb + i + d.s1 * j + d.s2 * (long)kfirst : nullptr;
       dst[r] = sbase + 8u * (unsigned)(f * PLANE + lj * PX + li);

@@ -36,8 +36,11 @@ class DevBound:
 
 
 class Simulation:
-    def __init__(self, deck, rank=0, nranks=1, uid=None, device=None, ave="channel", arith=None):
-        """arith: "fma" (the product build, libcales_b200.so) | "strict" (the bit-exact -fmad=false build) | None = lib.DEFAULT_ARITH"""
+    def __init__(self, deck, rank=0, nranks=1, uid=None, device=None, ave="channel", arith=None, fused=None, graph=None):
+        """arith: "fma" (the product build, libcales_b200.so) | "strict" (the bit-exact -fmad=false build) | None = lib.DEFAULT_ARITH
+        fused: drive the time loop through the fused entries cales_substep / cales_step (explicit diffusion; identical results)
+               instead of the per-procedure sequence; None = CALES_B200_FUSED (default on)
+        graph: replay each step from a CUDA graph (single rank, fused); None = CALES_B200_GRAPH (default on)"""
         if not torch.cuda.is_available():
             raise L.CalesError("no CUDA device: cales_b200 has no CPU fallback")
         self.lib = L.load(arith)
@@ -46,7 +49,19 @@ class Simulation:
         dev_index = device if device is not None else rank % torch.cuda.device_count()
         self.device = torch.device("cuda", dev_index)
         torch.cuda.set_device(self.device)
-        self.stream = torch.cuda.current_stream(self.device)
+        env = lambda k, dflt: os.environ.get(k, dflt) not in ("0", "")
+        self.fused = (env("CALES_B200_FUSED", "1") if fused is None else bool(fused)) and not deck.impdiff
+        self.graph = (env("CALES_B200_GRAPH", "1") if graph is None else bool(graph)) and self.fused and nranks == 1
+        # the library's stream (the reference's OpenACC queue 1).  A CUDA graph cannot be captured on the legacy default
+        # stream, so graph replay gets a stream of its own, made current for torch as well (copies, fills, event records).
+        self._prev_stream = None
+        if self.graph:
+            self._prev_stream = torch.cuda.current_stream(self.device)
+            self.stream = torch.cuda.Stream(self.device)
+            self.stream.wait_stream(self._prev_stream)
+            torch.cuda.set_stream(self.stream)
+        else:
+            self.stream = torch.cuda.current_stream(self.device)
         self.ctx = C.c_void_p()
         diff = _DIFF[(bool(deck.impdiff), bool(deck.impdiff_1d))]
         rc = self.lib.cales_init(C.byref(self.ctx), L._ia(deck.ng), L._ia(deck.dims), deck.ipencil, L._ca(deck.cbcpre), rank,
@@ -97,6 +112,30 @@ class Simulation:
         self.f = np.zeros(3)
         self.want_f = False
         self.dt = self.dti = self.dt_cfl = 0.0
+        self._step_args = None
+
+    def step_args(self):
+        """cales_step_args for this simulation (built once; every pointer in it is owned by self and stays alive)."""
+        if self._step_args is None:
+            d, D, a = self.deck, self.d, L.StepArgs()
+            for nm, val in (("n", self.n), ("ng", d.ng), ("lo", self.lo), ("hi", self.hi), ("nb", self.nb), ("is_bound", self.is_bound_flat),
+                            ("lwm", L._tab(d.lwm)), ("index_wm", L._tab(self.index_wm)), ("is_forced", [int(bool(x)) for x in d.is_forced])):
+                setattr(a, nm, (C.c_int * len(val))(*[int(x) for x in val]))
+            for nm, val in (("dl", d.dl), ("dli", d.dli), ("l", d.l), ("velf", d.velf), ("bforce", d.bforce)):
+                setattr(a, nm, (C.c_double * 3)(*[float(x) for x in val]))
+            a.plan, a.visc, a.hwm, a.normfft = self.poi["plan"], d.visc, d.hwm, self.poi["normfft"]
+            a.cbcvel, a.cbcpre, a.cbcsgs, a.sgstype = L._ca(self.cbcvel), L._ca(d.cbcpre), L._ca(d.cbcsgs), d.sgstype.strip().encode()
+            for nm, key in (("zc", "zc"), ("zf", "zf"), ("dzc", "dzc"), ("dzf", "dzf"), ("dzci", "dzci"), ("dzfi", "dzfi"),
+                            ("grid_vol_ratio_c", "gvr_c"), ("grid_vol_ratio_f", "gvr_f")):
+                setattr(a, nm, D[key].data_ptr())
+            a.lambdaxy, a.a, a.b, a.c = (self.poi[k].data_ptr() for k in ("lam", "a", "b", "c"))
+            a.rhsbx, a.rhsby, a.rhsbz = (self.rhsbp[k].data_ptr() for k in "xyz")
+            for nm in ("bcu", "bcv", "bcw", "bcp", "bcs", "bcu_mag", "bcv_mag", "bcw_mag", "bcuf", "bcvf", "bcwf"):
+                setattr(a, nm, getattr(self, nm).c)
+            for nm in ("u", "v", "w", "p", "pp", "visct"):
+                setattr(a, nm, self.fields[nm].data_ptr())
+            self._step_args = a
+        return self._step_args
 
     # ---- helpers -------------------------------------------------------------------------------------------
     def chk(self, rc):
@@ -124,11 +163,13 @@ class Simulation:
 
     def set_fields(self, **kw):
         """Upload haloed Fortran-ordered host arrays."""
-        for nm, a in kw.items():
-            self.fields[nm].copy_(torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))))
+        with torch.cuda.stream(self.stream):
+            for nm, a in kw.items():
+                self.fields[nm].copy_(torch.from_numpy(np.ascontiguousarray(a.ravel(order="F"))))
 
     def get(self, nm):
-        return self.fields[nm].cpu().numpy().reshape(self.shape, order="F")
+        with torch.cuda.stream(self.stream):
+            return self.fields[nm].cpu().numpy().reshape(self.shape, order="F")
 
     def init_flow(self, mean_allreduce=None):
         u, v, w, p = hostinit.initflow(self.deck, self.lo, self.n, self.h["zc"], self.h["zf"], self.h["dzc"], self.h["dzf"], mean_allreduce)
@@ -279,8 +320,11 @@ class Simulation:
         """main.f90:405-544 for one time step; returns (divtot, divmax) when checked."""
         self.istep += 1
         self.time += self.dt
-        for irk in range(3):
-            self.substep(irk)
+        if self.fused:
+            self.chk(self.lib.cales_step(self.ctx, C.byref(self.step_args()), self.dt, int(self.graph)))
+        else:
+            for irk in range(3):
+                self.substep(irk)
         if icheck > 0 and self.istep % icheck == 0:
             d = self.deck
             self.dt_cfl = self.chkdt()
@@ -307,3 +351,8 @@ class Simulation:
         if self.ctx:
             self.lib.cales_finalize(self.ctx)
             self.ctx = C.c_void_p()
+            if self._prev_stream is not None:
+                self._prev_stream.wait_stream(self.stream)
+                if torch.cuda.current_stream(self.device) == self.stream:
+                    torch.cuda.set_stream(self._prev_stream)
+                self._prev_stream = None

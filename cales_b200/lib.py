@@ -25,6 +25,19 @@ class Bound(C.Structure):
     _fields_ = [("x", vp), ("y", vp), ("z", vp)]
 
 
+class StepArgs(C.Structure):
+    """cales_step_args (include/cales_b200.h): what the callees of one RK3 substep take, gathered once."""
+    _fields_ = ([(nm, C.c_int * 3) for nm in ("n", "ng", "lo", "hi")] + [(nm, C.c_int * 6) for nm in ("nb", "is_bound", "lwm", "index_wm")] +
+                [("is_forced", C.c_int * 3), ("plan", C.c_int)] +
+                [(nm, C.c_double * 3) for nm in ("dl", "dli", "l", "velf", "bforce")] +
+                [("visc", C.c_double), ("hwm", C.c_double), ("normfft", C.c_double),
+                 ("cbcvel", C.c_char * 18), ("cbcpre", C.c_char * 6), ("cbcsgs", C.c_char * 6), ("sgstype", C.c_char * 8)] +
+                [(nm, vp) for nm in ("zc", "zf", "dzc", "dzf", "dzci", "dzfi", "grid_vol_ratio_c", "grid_vol_ratio_f",
+                                     "lambdaxy", "a", "b", "c", "rhsbx", "rhsby", "rhsbz")] +
+                [(nm, Bound) for nm in ("bcu", "bcv", "bcw", "bcp", "bcs", "bcu_mag", "bcv_mag", "bcw_mag", "bcuf", "bcvf", "bcwf")] +
+                [(nm, vp) for nm in ("u", "v", "w", "p", "pp", "visct")])
+
+
 class CalesError(RuntimeError):
     pass
 
@@ -96,6 +109,9 @@ SIGNATURES = {
     "cales_transpose": (C.c_int, [vp, C.c_int, vp, vp]),
     "cales_updthalo": (C.c_int, [vp, c_int_p, c_int_p, vp]),
     "cales_peer_alloc": (C.c_int, [vp, C.c_char_p, C.c_long, C.POINTER(vp)]),
+    "cales_substep": (C.c_int, [vp, C.POINTER(StepArgs), C.c_int, C.c_double]),
+    "cales_step": (C.c_int, [vp, C.POINTER(StepArgs), C.c_double, C.c_int]),
+    "cales_step_args_layout": (C.c_int, [C.POINTER(C.c_long)]),
 }
 
 

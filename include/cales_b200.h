@@ -187,6 +187,31 @@ int cales_chkdt(cales_ctx* ctx, const int n[3], const double dl[3], const double
 int cales_chkdiv(cales_ctx* ctx, const int lo[3], const int hi[3], const double dli[3], const double* dzfi,
                  const double* u, const double* v, const double* w, double* divtot, double* divmax);
 
+/* ---- fused entries of the time loop (optional): identical results to the per-procedure sequence ------------
+ * Everything the callees of one RK3 substep take (src/main.f90:418-506), gathered once.  HOST struct; its pointer members are
+ * DEVICE arrays exactly as in the per-procedure exports above, the small descriptor vectors are held by value. */
+typedef struct cales_step_args {
+  int n[3], ng[3], lo[3], hi[3], nb[6], is_bound[6], lwm[6], index_wm[6], is_forced[3];
+  int plan;                                     /* Poisson plan handle of cales_initsolver */
+  double dl[3], dli[3], l[3], velf[3], bforce[3];
+  double visc, hwm, normfft;
+  char cbcvel[18], cbcpre[6], cbcsgs[6], sgstype[8];   /* sgstype NUL-terminated: "none" | "smag" | "dsmag" */
+  const double *zc, *zf, *dzc, *dzf, *dzci, *dzfi, *grid_vol_ratio_c, *grid_vol_ratio_f;
+  const double *lambdaxy, *a, *b, *c;           /* Poisson coefficients (cales_initsolver, uploaded) */
+  const double *rhsbx, *rhsby, *rhsbz;          /* rhsbp planes of cales_cmpt_rhs_b (src/main.f90:317) */
+  cales_bound bcu, bcv, bcw, bcp, bcs, bcu_mag, bcv_mag, bcw_mag, bcuf, bcvf, bcwf;
+  double *u, *v, *w, *p, *pp, *visct;           /* the caller's fields */
+} cales_step_args;
+/* one RK3 substep irk = 1,2,3 of src/main.f90:418-506 (explicit diffusion): rk (update fused into the momentum kernel) ->
+ * bulk_forcing -> bounduvw -> fillps -> updt_rhs_b -> solver -> boundp -> correc (+ updatep) -> bounduvw -> boundp ->
+ * cmpt_sgs -> boundp; no host synchronisation; f(3) stays on the device */
+int cales_substep(cales_ctx* ctx, const cales_step_args* a, int irk, double dt);
+/* the three substeps of one time step; use_graph != 0 replays them from a CUDA graph captured per (dt, history parity)
+ * on single-rank contexts with a non-default stream (falls back to the eager sequence otherwise) */
+int cales_step(cales_ctx* ctx, const cales_step_args* a, double dt, int use_graph);
+/* out = {sizeof(cales_step_args), offsetof cbcvel, offsetof zc, offsetof visct}: lets a binding verify its struct layout */
+int cales_step_args_layout(long out[4]);
+
 /* ---- building blocks exported for parity tests and benchmarks ---------------------------------------------- */
 /* one batched 1-D transform pass of the solver on a halo-free array a(n1,n2,n3) in place:
  * dir 0 = along x, 1 = along y; bc = "PP","NN","DD",...; c_or_f 'c'|'f'; backward!=0 = inverse kind */

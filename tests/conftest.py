@@ -39,3 +39,20 @@ def arith(request):
     L.DEFAULT_ARITH = request.param
     yield request.param
     L.DEFAULT_ARITH = old
+
+
+@pytest.fixture(autouse=True)
+def _default_torch_stream(request):
+    """A Simulation with graph replay makes its own stream torch's current stream until close(); a test that fails before
+    close() must not leak that (non-blocking) stream into the next test, whose uploads would then race the library's work."""
+    if request.node.get_closest_marker("gpu") is None:
+        yield
+        return
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.default_stream())
+    yield
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+        torch.cuda.set_stream(torch.cuda.default_stream())

@@ -93,7 +93,7 @@ def case_vs_oracle(name, kw, dims, nsteps, rank, world, local, uid, arith=None, 
             a, b = out[nm], ref[nm]
             if nm == "p":
                 a = a - a.mean(); b = b - b.mean()
-            errs[nm] = float(np.abs(a - b).max() / max(vscale if nm in "uvw" else np.abs(b).max(), 1e-300))
+            errs[nm] = float(np.abs(a - b).max() / max(vscale if nm in "uvw" else max(np.abs(b).max(), vscale ** 2) if nm == "p" else np.abs(b).max(), 1e-300))
         ok = all(v <= tol for v in errs.values()) and abs(res[1] - ro[1]) < 1e-11 and abs(sim.dt - o.dt) <= 1e-10 * o.dt
         rec = {"case": name + ":" + kw.get("sgstype", "smag") + (":impdiff_" + impdiff if impdiff else ""), "ng": list(deck.ng), "dims": list(dims),
                "steps": nsteps, "errs": errs, "divmax": [res[1], ro[1]], "tol": tol, "ok": bool(ok)}

@@ -124,3 +124,14 @@ def test_transpose_plan_moves_global_index_exactly(lib, ng, dims):
         for a, b in zip(new, ref):
             assert np.array_equal(a, b)
         cur = new
+
+
+def test_step_args_layout_matches_the_library(lib):
+    """the ctypes mirror of cales_step_args has the layout the library was compiled with (both variants)"""
+    import ctypes as C
+    from cales_b200 import lib as L
+    for arith in ("fma", "strict"):
+        out = (C.c_long * 4)()
+        assert L.load(arith).cales_step_args_layout(out) == 0
+        S = L.StepArgs
+        assert list(out) == [C.sizeof(S), S.cbcvel.offset, S.zc.offset, S.visct.offset]

@@ -38,7 +38,9 @@ class Ctx:
     def __init__(self, L, lib, ng, cbcpre="PPPPPP", diffusion=0):
         self.L, self.lib = L, lib
         self.ctx = C.c_void_p()
-        L.check(None, lib.cales_init(C.byref(self.ctx), L._ia(ng), L._ia([1, 1]), 1, cbcpre.encode(), 0, 1, None, 0, None, diffusion))
+        # the library works on torch's current stream, like the uploads of the test
+        L.check(None, lib.cales_init(C.byref(self.ctx), L._ia(ng), L._ia([1, 1]), 1, cbcpre.encode(), 0, 1, None, 0,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream), diffusion), lib)
 
     def __enter__(self):
         return self
@@ -47,7 +49,7 @@ class Ctx:
         self.lib.cales_finalize(self.ctx)
 
     def chk(self, rc):
-        self.L.check(self.ctx, rc)
+        self.L.check(self.ctx, rc, self.lib)
 
 
 _KEEP = []
