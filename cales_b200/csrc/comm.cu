@@ -259,6 +259,65 @@ __global__ void __launch_bounds__(256) halo_unpack_k(Dims d, int idir, FieldList
   if (has_hi) p[face_idx(d, idir, n + 1, a, c)] = buf[(fl.nf + f) * m + a + (long)m1 * c];
 }
 
+// One-launch peer exchange of one direction: a persistent grid (every CTA resident) pushes its tiles of the boundary planes
+// into the neighbours' receive buffers, the last CTA to finish raises the neighbours' arrival flags (st.release.sys after
+// every CTA's system-scope fence), then every CTA waits for MY arrival flags (ld.acquire.sys) and unpacks its tiles of the
+// ghost planes: what used to be push kernel + barrier kernel + unpack kernel, with only the two neighbours involved.
+struct HaloX {
+  double *to_lo, *to_hi;                 // receive regions in nb(0) / nb(1) (nullptr: no neighbour)
+  const double* mine;                    // my receive buffer (lower ghosts first, then upper)
+  unsigned long long *sig_lo, *sig_hi;   // flag words in nb(0) / nb(1) to raise
+  const unsigned long long *wait_lo, *wait_hi;   // my flag words raised by nb(0) / nb(1)
+  unsigned* counter;                     // CTAs done pushing (reset by the last one)
+  unsigned long long seq;
+};
+
+__global__ void __launch_bounds__(256) halo_fused_k(Dims d, int idir, FieldList fl, HaloX X, int gx, int gy) {
+  const int m1 = idir == 0 ? d.n2 + 2 : d.n1 + 2, m2 = idir == 2 ? d.n2 + 2 : d.n3 + 2;
+  const int n = idir == 0 ? d.n1 : idir == 1 ? d.n2 : d.n3;
+  const long m = (long)m1 * m2;
+  const int ntile = gx * gy * fl.nf;
+  for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const int f = t / (gx * gy), r = t - f * gx * gy;
+    const int a = (r % gx) * 64 + threadIdx.x, c = (r / gx) * 4 + threadIdx.y;
+    if (a >= m1 || c >= m2) continue;
+    const double* p = fl.p[f];
+    if (X.to_lo) X.to_lo[f * m + a + (long)m1 * c] = p[face_idx(d, idir, 1, a, c)];
+    if (X.to_hi) X.to_hi[f * m + a + (long)m1 * c] = p[face_idx(d, idir, n, a, c)];
+  }
+  __threadfence_system();
+  __syncthreads();
+  const bool lead = threadIdx.x == 0 && threadIdx.y == 0;
+  if (lead) {
+    const unsigned old = atomicAdd(X.counter, 1u);
+    if (old == gridDim.x - 1) {
+      *X.counter = 0;
+      __threadfence_system();
+      if (X.sig_lo) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(X.sig_lo), "l"(X.seq) : "memory");
+      if (X.sig_hi) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(X.sig_hi), "l"(X.seq) : "memory");
+    }
+    const long long t0 = clock64();
+    for (int side = 0; side < 2; ++side) {
+      const unsigned long long* w = side == 0 ? X.wait_lo : X.wait_hi;
+      if (!w) continue;
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w) : "memory");
+      } while (v < X.seq && clock64() - t0 < 60000000000LL);
+      if (v < X.seq) __trap();              // a neighbour died: fail loudly instead of hanging
+    }
+  }
+  __syncthreads();
+  for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+    const int f = t / (gx * gy), r = t - f * gx * gy;
+    const int a = (r % gx) * 64 + threadIdx.x, c = (r / gx) * 4 + threadIdx.y;
+    if (a >= m1 || c >= m2) continue;
+    double* p = fl.p[f];
+    if (X.wait_lo) p[face_idx(d, idir, 0, a, c)] = __ldcv(X.mine + f * m + a + (long)m1 * c);
+    if (X.wait_hi) p[face_idx(d, idir, n + 1, a, c)] = __ldcv(X.mine + (fl.nf + f) * m + a + (long)m1 * c);
+  }
+}
+
 int k_halo_exchange_dirs(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields, int dirmask);
 
 int k_halo_exchange(cales_ctx* ctx, const int n[3], const int nb[6], double* const* fields, int nfields) {
@@ -300,6 +359,27 @@ int k_halo_exchange_dirs(cales_ctx* ctx, const int n[3], const int nb[6], double
       }
       const size_t half = (size_t)2 * 12 * fglob;
       PeerBuf* hb = nccl_halo || (size_t)fmax_ > fglob ? nullptr : k_peer_buffer(ctx, "halo_peer", 2 * half * sizeof(double));
+      static const bool fused_halo = !(getenv("CALES_HALO_FUSED") && atoi(getenv("CALES_HALO_FUSED")) == 0);
+      PeerBuf* hf = hb && fused_halo ? k_peer_buffer(ctx, "halo_flags", 64 * sizeof(unsigned long long)) : nullptr;
+      if (hb && hf) {
+        if (!ctx->halo_counter) { CUDA_TRY(ctx, cudaMalloc(&ctx->halo_counter, 4 * sizeof(unsigned))); CUDA_TRY(ctx, cudaMemsetAsync(ctx->halo_counter, 0, 4 * sizeof(unsigned), ctx->stream)); }
+        const size_t off = (ctx->halo_seq++ & 1u) * half;
+        HaloX X;
+        X.to_lo = nb0 >= 0 ? (double*)hb->ptr[nb0] + off + cnt : nullptr;      // my plane 1 = nb(0)'s upper ghost
+        X.to_hi = nb1 >= 0 ? (double*)hb->ptr[nb1] + off : nullptr;            // my plane n = nb(1)'s lower ghost
+        X.mine = (const double*)hb->local + off;
+        X.sig_lo = nb0 >= 0 ? (unsigned long long*)hf->ptr[nb0] + 2 * idir + 1 : nullptr;
+        X.sig_hi = nb1 >= 0 ? (unsigned long long*)hf->ptr[nb1] + 2 * idir + 0 : nullptr;
+        X.wait_lo = nb0 >= 0 ? (const unsigned long long*)hf->local + 2 * idir + 0 : nullptr;
+        X.wait_hi = nb1 >= 0 ? (const unsigned long long*)hf->local + 2 * idir + 1 : nullptr;
+        X.counter = ctx->halo_counter + idir;
+        X.seq = ++ctx->halo_dir_seq[idir];
+        const int gx = cdiv(m1, 64), gy = cdiv(m2, 4);
+        const int ntile = gx * gy * fl.nf;
+        halo_fused_k<<<std::min(ntile, 148 * 4), b, 0, ctx->stream>>>(d, idir, fl, X, gx, gy);
+        KERNEL_CHECK(ctx);
+        continue;
+      }
       if (hb) {
         const size_t off = (ctx->halo_seq++ & 1u) * half;
         double* to_lo = nb0 >= 0 ? (double*)hb->ptr[nb0] + off + cnt : nullptr;

@@ -58,6 +58,8 @@ struct cales_ctx {
   double* bar = nullptr;                // barrier token (NCCL all-reduce barrier)
   unsigned long long bar_seq = 0;       // sequence number of the peer-memory flag barrier
   unsigned halo_seq = 0;                // parity of the double-buffered peer halo buffers
+  unsigned long long halo_dir_seq[3] = {0, 0, 0};   // exchange count per direction (arrival flags of halo_fused_k)
+  unsigned* halo_counter = nullptr;     // per direction: CTAs of halo_fused_k done pushing
   // scratch owned by the callee (the reference's `save`d allocatables and module buffers)
   std::map<std::string, std::pair<void*, size_t>> scratch;
   double* red = nullptr;                // device reduction slots
@@ -66,6 +68,8 @@ struct cales_ctx {
   int rk_swap = 0;                      // which of the two RHS sets is "old" (rk.f90:98-100)
   bool rk_first = true;
   bool sgs_first = true;
+  cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // copy streams of the pipelined solver exchange (solver.cu)
+  cudaEvent_t side_ev[8] = {nullptr};   // [0..3] chunk ready (main -> side), [4..7] chunk pushed (side -> main)
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;
   std::map<int, FftTables> tables;

@@ -144,11 +144,13 @@ extern "C" int cales_finalize(cales_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   comm_finalize(ctx);
+  for (auto& st_ : ctx->side) if (st_) cudaStreamDestroy(st_);
+  for (auto& e_ : ctx->side_ev) if (e_) cudaEventDestroy(e_);
   k_step_graphs_free(ctx);
   k_gaussel_tab_free(ctx);
   for (auto& kv : ctx->scratch) cudaFree(kv.second.first);
   for (auto& kv : ctx->tables) { cudaFree(kv.second.w); cudaFree(kv.second.h); }
-  cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->fdev); cudaFree(ctx->bar);
+  cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->fdev); cudaFree(ctx->bar); cudaFree(ctx->halo_counter);
   delete ctx;
   return CALES_OK;
 }

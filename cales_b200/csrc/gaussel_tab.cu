@@ -507,7 +507,7 @@ static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const do
   for (auto& t : v)
     if (t.nxy == nxy && t.n == n && t.periodic == periodic && t.key[0] == a && t.key[1] == b && t.key[2] == c && t.key[3] == lam) return &t;
   GaussTab* t = nullptr;
-  if (v.size() < 8) { v.emplace_back(); t = &v.back(); }
+  if (v.size() < 32) { v.emplace_back(); t = &v.back(); }
   else {
     t = &v[0];
     for (auto& u : v) if (u.last_use < t->last_use) t = &u;

@@ -8,6 +8,7 @@
 // (i,j) column (coalesced in i) running the reference's Thomas recurrence in its exact operation order
 // (pivot regularisation `+eps` included), and the backward x pass writes the haloed field scaled by
 // normfft: five sweeps, 16 B/cell each, no transposes and no copy-in/out passes.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -388,6 +389,101 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   double* w0 = p2p ? (double*)pb0->local : (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
   double* w1 = p2p ? (double*)pb1->local : (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
   if (!w0 || !w1) return CALES_ERR_NOMEM;
+  // ---- pipelined exchange (default with peer memory): the y <-> z transposes are done by the COPY ENGINES, chunk by chunk,
+  // while the SMs work on the next chunk.  y -> z: the local z range is cut into chunks; as soon as the x and y transforms of
+  // a chunk are done, one strided 2-D DMA per peer pushes its [all x, y of that peer, chunk] box straight into the peer's
+  // Z-pencil (contiguous there) over NVLink.  z -> y: the columns of my Z-pencil are cut into y chunks; each chunk is
+  // solved and then pushed into the peers' Y-pencils the same way.  One flag barrier per direction.  Peer writes run at the
+  // link rate whatever the producing kernel looks like (tools/p2pbench: 650-700 GB/s per direction), every transform kind
+  // and process grid takes this path, and no kernel stores across NVLink.  CALES_SOLVER_PIPE=0 restores the older paths.
+  // Selection (measured, profiles/r2h_*): where the kernel-fused exchange below exists (1 x P grids, transform with a peer
+  // post-stage, column short enough for the TMA z solve) it wins at 256^3 per GPU (0.70 vs 0.78 ms at 2 GPUs: the chunks
+  // cost wave quantisation); everywhere else the pipeline replaces the unfused chain.  CALES_SOLVER_PIPE=0/1 forces a path.
+  static const int pipe_env = getenv("CALES_SOLVER_PIPE") ? atoi(getenv("CALES_SOLVER_PIPE")) : -1;
+  static const int nchunk_env = getenv("CALES_SOLVER_CHUNKS") ? atoi(getenv("CALES_SOLVER_CHUNKS")) : 2;
+  const bool fused_ok = ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fft_peer_capable(pl.bc[1], pl.c_or_f[1], ys[1]) && q == 0 &&
+                        k_gauss_tma_fits(zs[0] * zs[1], zs[2], zper);
+  const bool pipe = pipe_env >= 0 ? pipe_env != 0 : !fused_ok;
+  if (p2p && pipe && ctx->dims[1] > 1 && ctx->dims[1] <= 16 && lambdaxy) {
+    const int P = ctx->dims[1], me = ctx->coord[1];
+    if (!ctx->side[0]) {
+      for (auto& st_ : ctx->side) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
+      for (auto& sev : ctx->side_ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&sev, cudaEventDisableTiming));
+    }
+    std::vector<int> yst(P), yen(P), yszq(P), zst(P), zen(P), zszq(P);
+    cales_distribute(ctx->ng[1], P, yst.data(), yen.data(), yszq.data());
+    cales_distribute(ctx->ng[2], P, zst.data(), zen.data(), zszq.data());
+    const long nxl = ys[0], ny = ys[1], nzl = ys[2], nyl = zs[1];
+    const size_t E = sizeof(double);
+    auto rankof = [&](int q) { return ctx->coord[0] * ctx->dims[1] + q; };
+    double *cur = w0, *oth = w1;
+    PeerBuf *pcur = pb0, *poth = pb1;
+    const bool xy = ctx->dims[0] > 1;
+    if (xy) {                                               // x transform + x -> y transpose first (not pipelined)
+      if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, cur, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+      if ((rc = k_transpose_p2p(ctx, 0, cur, poth))) return rc;
+      std::swap(cur, oth); std::swap(pcur, poth);
+    }
+    // ---- forward: [x transform,] y transform and push, chunk by chunk over my z planes.  Streams side[0..2]: NVLink pushes
+    // (chunks round-robin), side[3]: the local boxes (another copy engine).
+    auto join_side = [&]() -> int {                          // the compute stream waits for every copy issued so far
+      for (int q4 = 0; q4 < 4; ++q4) {
+        CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[4 + q4], ctx->side[q4]));
+        CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[4 + q4], 0));
+      }
+      return CALES_OK;
+    };
+    const int nck = std::max(1, std::min(std::min(nchunk_env, 4), (int)nzl));
+    for (int ch = 0; ch < nck; ++ch) {
+      const int k0 = (int)((long)nzl * ch / nck), k1 = (int)((long)nzl * (ch + 1) / nck);
+      if (k1 <= k0) continue;
+      if (!xy && (rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], k1 - k0, p + d.idx(1, 1, 1 + k0), d.s1, d.s2,
+                                  cur + (long)xs[0] * xs[1] * k0, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+      double* yc = cur + nxl * ny * k0;
+      if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], k1 - k0, yc, ys[0], nxl * ny, yc, ys[0], nxl * ny, 1.0))) return rc;
+      CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[ch % 4], ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side[ch % 3], ctx->side_ev[ch % 4], 0));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side[3], ctx->side_ev[ch % 4], 0));
+      for (int dq = 0; dq < P; ++dq) {
+        const int pq = (me + 1 + dq) % P;
+        const double* src = cur + nxl * (yst[pq] - 1) + nxl * ny * k0;
+        double* dst = (double*)poth->ptr[rankof(pq)] + nxl * yszq[pq] * (long)(zst[me] - 1 + k0);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)nxl * yszq[pq] * E, src, (size_t)nxl * ny * E, (size_t)nxl * yszq[pq] * E, (size_t)(k1 - k0),
+                                        cudaMemcpyDeviceToDevice, pq == me ? ctx->side[3] : ctx->side[ch % 3]));
+      }
+      ctx->launches += P;
+    }
+    if ((rc = join_side())) return rc;
+    if ((rc = k_barrier(ctx))) return rc;
+    // ---- z solve and push, chunk by chunk over my y columns
+    const int ncj = std::max(1, std::min(std::min(nchunk_env, 4), (int)nyl / 2));
+    for (int ch = 0; ch < ncj; ++ch) {
+      int j0 = (int)((long)nyl * ch / ncj), j1 = (int)((long)nyl * (ch + 1) / ncj);
+      j0 -= j0 & 1; if (ch + 1 < ncj) j1 -= j1 & 1;          // even boundaries keep the 16-byte alignment of the TMA kernel
+      if (j1 <= j0) continue;
+      if ((rc = k_gaussel(ctx, zs[0], j1 - j0, zs[2] - q, nxl * nyl, zper, a, b, c, lambdaxy + nxl * j0, oth + nxl * j0))) return rc;
+      CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[ch % 4], ctx->stream));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side[ch % 3], ctx->side_ev[ch % 4], 0));
+      CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side[3], ctx->side_ev[ch % 4], 0));
+      for (int dq = 0; dq < P; ++dq) {
+        const int qq = (me + 1 + dq) % P;
+        const double* src = oth + nxl * j0 + nxl * nyl * (long)(zst[qq] - 1);
+        double* dst = (double*)pcur->ptr[rankof(qq)] + nxl * (long)(yst[me] - 1 + j0);
+        CUDA_TRY(ctx, cudaMemcpy2DAsync(dst, (size_t)nxl * ny * E, src, (size_t)nxl * nyl * E, (size_t)nxl * (j1 - j0) * E, (size_t)zszq[qq],
+                                        cudaMemcpyDeviceToDevice, qq == me ? ctx->side[3] : ctx->side[ch % 3]));
+      }
+      ctx->launches += P;
+    }
+    if ((rc = join_side())) return rc;
+    if ((rc = k_barrier(ctx))) return rc;
+    // ---- backward: y transform, [y -> x transpose,] x transform
+    if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, ys[0], ys[1], ys[2], cur, ys[0], nxl * ny, cur, ys[0], nxl * ny, 1.0))) return rc;
+    if (xy) {
+      if ((rc = k_transpose_p2p(ctx, 3, cur, poth))) return rc;
+      std::swap(cur, oth); std::swap(pcur, poth);
+    }
+    return k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, xs[0], xs[1], xs[2], cur, xs[0], (long)xs[0] * xs[1], p + d.idx(1, 1, 1), d.s1, d.s2, normfft);
+  }
   // ---- peer-fused path (process grid 1 x P: x->y is the identity): the forward y pass scatters its spectrum straight
   // into the Z-pencils of the owning ranks and the z solve scatters its solution straight into their Y-pencils, so the
   // two transposes cost no pass over memory at all -- only the NVLink stores inside the producing kernels and one

@@ -13,7 +13,7 @@ torch = pytest.importorskip("torch")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(case, prow, pcol, nsteps, port, arith="-", impdiff=None):
+def run(case, prow, pcol, nsteps, port, arith="-", impdiff=None, env=None):
     n = prow * pcol
     from conftest import need_gpu
     need_gpu()
@@ -21,7 +21,9 @@ def run(case, prow, pcol, nsteps, port, arith="-", impdiff=None):
         pytest.skip("needs %d GPUs, box has %d" % (n, torch.cuda.device_count()))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mgpu_worker.py"), case, str(prow), str(pcol), str(nsteps), arith] + ([impdiff] if impdiff else [])
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=e)
     lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
     assert r.returncode == 0 and lines, (r.stdout[-2000:], r.stderr[-3000:])
     assert json.loads(lines[-1])["ok"], lines[-1]
@@ -36,3 +38,17 @@ def test_two_gpus(case, prow, pcol):
 @pytest.mark.parametrize("case,prow,pcol", [("channel_dsmag", 2, 2), ("tgv_smag", 1, 4), ("channel_wm_dsmag", 4, 1)])
 def test_four_gpus(case, prow, pcol):
     run(case, prow, pcol, 5, 29512)
+
+
+@pytest.mark.parametrize("case,prow,pcol", [("channel_dsmag", 1, 8), ("channel_dsmag", 2, 4), ("channel_wm_smag", 4, 2), ("tgv_smag", 1, 8)])
+def test_eight_gpus(case, prow, pcol):
+    run(case, prow, pcol, 5, 29513)
+
+
+@pytest.mark.parametrize("case,prow,pcol,env", [("tgv_smag", 1, 2, {"CALES_SOLVER_PIPE": "1"}), ("channel_dsmag", 1, 2, {"CALES_SOLVER_PIPE": "1", "CALES_SOLVER_CHUNKS": "3"}),
+                                                ("channel_smag", 1, 2, {"CALES_SOLVER_PIPE": "0"}), ("duct_smag", 1, 2, {"CALES_HALO_FUSED": "0"}),
+                                                ("channel_dsmag", 1, 2, {"CALES_NO_P2P": "1"}), ("tgv_smag", 1, 2, {"CALES_B200_ARITH": "strict"})])
+def test_two_gpus_exchange_variants(case, prow, pcol, env):
+    """every exchange mechanism on the same cases: copy-engine pipeline, kernel-fused transposes, separate-kernel halo
+    exchange, NCCL send/recv without peer memory, and the strict arithmetic build"""
+    run(case, prow, pcol, 5, 29514, env=env)
