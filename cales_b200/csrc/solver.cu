@@ -581,5 +581,37 @@ extern "C" int cales_solver_gaussel_z(cales_ctx* ctx, const int n[3], const doub
     KERNEL_CHECK(ctx);
     return CALES_OK;
   }
-  return cales_fail(ctx, CALES_ERR_INVALID, "solver_gaussel_z with z decomposed across ranks is not implemented yet");
+  // z is decomposed: transpose to Z-pencils, solve, transpose back (src/solver.f90:199-231)
+  const int* xs = ctx->xsz; const int* zs = ctx->zsz;
+  size_t bmax = 0;
+  for (int r = 0; r < ctx->nranks; ++r)
+    for (int ax = 1; ax <= 3; ++ax) {
+      int lo[3], hi[3], sz[3];
+      cales_pencil(ctx->ng, ctx->dims, r, ax, lo, hi, sz);
+      bmax = std::max(bmax, (size_t)sz[0] * sz[1] * sz[2]);
+    }
+  PeerBuf* pb0 = k_peer_buffer(ctx, "solver_wk", bmax * sizeof(double));
+  PeerBuf* pb1 = pb0 ? k_peer_buffer(ctx, "solver_wk1", bmax * sizeof(double)) : nullptr;
+  const bool p2p = pb0 && pb1;
+  double* cur = p2p ? (double*)pb0->local : (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
+  double* oth = p2p ? (double*)pb1->local : (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
+  if (!cur || !oth) return CALES_ERR_NOMEM;
+  PeerBuf *pcur = pb0, *poth = pb1;
+  if (xs[0] != n[0] || xs[1] != n[1] || xs[2] != n[2]) return cales_fail(ctx, CALES_ERR_INVALID, "solver_gaussel_z: n does not match the X-pencil of this rank");
+  strip_k<<<dim3(cdiv(n[0], 128), n[1], n[2]), 128, 0, ctx->stream>>>(d, p, cur, 1);
+  KERNEL_CHECK(ctx);
+#define TRANSPOSE(which, P)                                                                       \
+  if ((P) > 1) {                                                                                  \
+    if ((rc = p2p ? k_transpose_p2p(ctx, which, cur, poth) : k_transpose(ctx, which, cur, oth))) return rc; \
+    std::swap(cur, oth); std::swap(pcur, poth);                                                   \
+  }
+  TRANSPOSE(0, ctx->dims[0])
+  TRANSPOSE(1, ctx->dims[1])
+  if ((rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, nullptr, cur))) return rc;
+  TRANSPOSE(2, ctx->dims[1])
+  TRANSPOSE(3, ctx->dims[0])
+#undef TRANSPOSE
+  strip_k<<<dim3(cdiv(n[0], 128), n[1], n[2]), 128, 0, ctx->stream>>>(d, p, cur, 0);
+  KERNEL_CHECK(ctx);
+  return CALES_OK;
 }

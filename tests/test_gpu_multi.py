@@ -52,3 +52,10 @@ def test_two_gpus_exchange_variants(case, prow, pcol, env):
     """every exchange mechanism on the same cases: copy-engine pipeline, kernel-fused transposes, separate-kernel halo
     exchange, NCCL send/recv without peer memory, and the strict arithmetic build"""
     run(case, prow, pcol, 5, 29514, env=env)
+
+
+@pytest.mark.parametrize("case,prow,pcol,mode", [("channel_smag", 1, 2, "1d"), ("channel_wm_smag", 2, 1, "1d"), ("tgv_smag", 1, 2, "1d"), ("channel_smag", 1, 2, "3d")])
+def test_two_gpus_implicit_diffusion(case, prow, pcol, mode):
+    """Crank-Nicolson across ranks: _IMPDIFF_1D with z decomposed runs solver_gaussel_z through the pencil transposes
+    (src/solver.f90:199-231); _IMPDIFF runs three Helmholtz solves per substep through the distributed solver"""
+    run(case, prow, pcol, 5, 29515, impdiff=mode)
