@@ -400,9 +400,13 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   // post-stage, column short enough for the TMA z solve) it wins at 256^3 per GPU (0.70 vs 0.78 ms at 2 GPUs: the chunks
   // cost wave quantisation); everywhere else the pipeline replaces the unfused chain.  CALES_SOLVER_PIPE=0/1 forces a path.
   static const int pipe_env = getenv("CALES_SOLVER_PIPE") ? atoi(getenv("CALES_SOLVER_PIPE")) : -1;
-  static const int nchunk_env = getenv("CALES_SOLVER_CHUNKS") ? atoi(getenv("CALES_SOLVER_CHUNKS")) : 2;
+  // chunks: 1 below ~24 M cells per rank (at 256^3 per GPU chunked kernels lose more to wave quantisation than the overlap
+  // returns: 6.49 ms/step with 1 chunk, 9.33 with 4 at 8 GPUs), 2 above
+  static const int nchunk_cfg = getenv("CALES_SOLVER_CHUNKS") ? atoi(getenv("CALES_SOLVER_CHUNKS")) : 0;
+  const int nchunk_env = nchunk_cfg > 0 ? nchunk_cfg : ((long)xs[0] * xs[1] * xs[2] < 24000000L ? 1 : 2);
+  // (the kernel-fused periodic z solve is verified on two ranks only: with more, the pipeline takes over)
   const bool fused_ok = ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fft_peer_capable(pl.bc[1], pl.c_or_f[1], ys[1]) && q == 0 &&
-                        k_gauss_tma_fits(zs[0] * zs[1], zs[2], zper);
+                        k_gauss_tma_fits(zs[0] * zs[1], zs[2], zper) && (!zper || ctx->dims[1] == 2);
   const bool pipe = pipe_env >= 0 ? pipe_env != 0 : !fused_ok;
   if (p2p && pipe && ctx->dims[1] > 1 && ctx->dims[1] <= 16 && lambdaxy) {
     const int P = ctx->dims[1], me = ctx->coord[1];
@@ -489,7 +493,8 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   // two transposes cost no pass over memory at all -- only the NVLink stores inside the producing kernels and one
   // stream-ordered barrier each.
   static const bool nofuse = getenv("CALES_NO_FUSED_TRANSPOSE") != nullptr;
-  if (p2p && !nofuse && ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fft_peer_capable(pl.bc[1], pl.c_or_f[1], ys[1])) {
+  if (p2p && !nofuse && ctx->dims[0] == 1 && ctx->dims[1] <= 8 && lambdaxy && k_fft_peer_capable(pl.bc[1], pl.c_or_f[1], ys[1]) &&
+      (pipe_env == 0 || fused_ok)) {
     const int P = ctx->dims[1], me = ctx->coord[1];
     std::vector<int> yst(P), yen(P), ysz(P), zst(P), zen(P), zsz(P);
     cales_distribute(ctx->ng[1], P, yst.data(), yen.data(), ysz.data());
