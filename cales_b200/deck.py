@@ -148,77 +148,176 @@ def deck_cavity(ng=(512, 256, 256), sgstype="smag", visci=1000.0, dims=(1, 1)):
 
 
 # ---------------------------------------------------------------------------
-# minimal namelist reader for the reference's input.nml decks (param.f90:88-152)
+# namelist reader for the reference's input.nml decks (read_input, src/param.f90:88-152)
 # ---------------------------------------------------------------------------
-def _parse_values(s):
-    out = []
-    for tok in re.split(r"[,\s]+", s.strip()):
-        if not tok:
-            continue
-        t = tok.strip()
-        if t.startswith(("'", '"')):
-            out.append(t.strip("'\""))
-        elif t.upper() in ("T", ".TRUE.", "TRUE"):
-            out.append(True)
-        elif t.upper() in ("F", ".FALSE.", "FALSE"):
-            out.append(False)
-        else:
-            try:
-                out.append(int(t))
-            except ValueError:
-                out.append(float(t.replace("d", "e").replace("D", "e")))
+class DeckError(ValueError):
+    """an input deck the reference would not have accepted (or that this reader cannot interpret unambiguously)"""
+
+
+_TOKEN = re.compile(r"""\s*(?:
+      (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")      # quoted string
+    | (?P<amp>&\w+)                               # group start
+    | (?P<end>/|\\)                              # group terminator: '/' (or a backslash, as in some DNS decks) anywhere outside quotes
+    | (?P<eq>=)
+    | (?P<comma>,)
+    | (?P<sub>\([^)]*\))                          # array section, e.g. (0:1,1:3,2)
+    | (?P<word>[^\s,=/\\()'"!]+)                  # name, number, logical, repeat count n*value
+    | (?P<comment>![^\n]*)
+    )""", re.X)
+
+
+def _tokens(txt):
+    pos, out = 0, []
+    while pos < len(txt):
+        m = _TOKEN.match(txt, pos)
+        if m is None or m.end() == pos:
+            if txt[pos:].strip() == "":
+                break
+            raise DeckError("cannot tokenise the deck at: %r" % txt[pos:pos + 30])
+        pos = m.end()
+        kind = m.lastgroup
+        if kind != "comment":
+            out.append((kind, m.group(kind)))
     return out
 
 
-def read_input(path):
-    """Read &dns and &les of an input.nml into a Deck (param.f90:88-152).  Groups may be terminated by '/' or,
-    as in some DNS decks, by a backslash."""
-    txt = "\n".join(line.split("!")[0] for line in open(path).read().splitlines())
-    d = Deck()
-    arrays = {"cbcvel": d.cbcvel, "bcvel": d.bcvel, "cbcpre": d.cbcpre, "cbcsgs": d.cbcsgs, "bcpre": d.bcpre, "bcsgs": d.bcsgs,
-              "lwm": d.lwm}
-    scal = {}
-    for gm in re.finditer(r"&(\w+)(.*?)^\s*[/\\]\s*$", txt, re.S | re.M):
-        if gm.group(1).lower() not in ("dns", "les"):
+def _value(word):
+    u = word.upper()
+    if u in ("T", ".T.", ".TRUE.", "TRUE"):
+        return True
+    if u in ("F", ".F.", ".FALSE.", "FALSE"):
+        return False
+    try:
+        return int(word)
+    except ValueError:
+        pass
+    try:
+        return float(u.replace("D", "E"))
+    except ValueError:
+        raise DeckError("cannot interpret the value %r" % word)
+
+
+def _groups(txt):
+    """{group: [(name, section or None, [values])]} of a namelist file: values may be separated by commas and/or blanks, run
+    over several lines, carry repeat counts (3*0.), and the group ends at the first '/' outside quotes."""
+    toks = _tokens(txt)
+    groups, i = {}, 0
+    while i < len(toks):
+        kind, tok = toks[i]
+        if kind != "amp":
+            i += 1
             continue
-        body = gm.group(2)
-        ms = list(re.finditer(r"([A-Za-z_]\w*)\s*(\([^)]*\))?\s*=", body))
-        for i, m in enumerate(ms):
-            name = m.group(1).lower()
-            vals = _parse_values(body[m.end():ms[i + 1].start() if i + 1 < len(ms) else len(body)])
-            if name in arrays:
-                arr = arrays[name]
-                spec = (m.group(2) or "").strip("()").split(",")
-                if arr.ndim == 3:
-                    k = int(spec[2]) - 1 if len(spec) == 3 and ":" not in spec[2] else None
-                    ks = [k] if k is not None else range(3)
+        gname = tok[1:].lower()
+        entries, i = [], i + 1
+        cur = None
+        closed = False
+        rep = 1
+        while i < len(toks):
+            kind, tok = toks[i]
+            if kind == "end":
+                closed = True
+                i += 1
+                break
+            if kind == "amp":
+                raise DeckError("group &%s is not terminated by '/'" % gname)
+            if kind == "word" and i + 1 < len(toks) and (toks[i + 1][0] == "eq" or (toks[i + 1][0] == "sub" and i + 2 < len(toks) and toks[i + 2][0] == "eq")):
+                sub = toks[i + 1][1] if toks[i + 1][0] == "sub" else None
+                cur = (tok.lower(), sub, [])
+                entries.append(cur)
+                i += 3 if sub else 2
+                continue
+            if cur is None:
+                raise DeckError("value %r before any name in group &%s" % (tok, gname))
+            if kind == "str":
+                q = tok[0]
+                cur[2].extend([tok[1:-1].replace(q + q, q)] * rep)
+                rep = 1
+            elif kind == "word":
+                if "*" in tok:                                  # repeat count r*value (the value may be a quoted string: next token)
+                    r, _, v = tok.partition("*")
+                    if not r.isdigit() or rep != 1:
+                        raise DeckError("bad repeat count in %r" % tok)
+                    if v == "":
+                        rep = int(r)
+                    else:
+                        cur[2].extend([_value(v)] * int(r))
+                else:
+                    cur[2].extend([_value(tok)] * rep)
+                    rep = 1
+            elif kind != "comma":
+                raise DeckError("unexpected %r in group &%s" % (tok, gname))
+            i += 1
+        if not closed:
+            raise DeckError("group &%s is not terminated by '/'" % gname)
+        groups.setdefault(gname, []).extend(entries)
+    return groups
+
+
+# name -> (type, count) of the scalar / vector entries of &dns and &les (param.f90:95-120); tables are handled separately
+_DNS = {"ng": (int, 3), "l": (float, 3), "gtype": (int, 1), "gr": (float, 1), "cfl": (float, 1), "dtmax": (float, 1), "dt_f": (float, 1),
+        "visci": (float, 1), "inivel": (str, 1), "is_wallturb": (bool, 1), "nstep": (int, 1), "time_max": (float, 1), "tw_max": (float, 1),
+        "stop_type": (bool, 3), "restart": (bool, 1), "is_overwrite_save": (bool, 1), "nsaves_max": (int, 1), "icheck": (int, 1),
+        "iout0d": (int, 1), "iout1d": (int, 1), "iout2d": (int, 1), "iout3d": (int, 1), "isave": (int, 1), "bforce": (float, 3),
+        "is_forced": (bool, 3), "velf": (float, 3), "dims": (int, 2)}
+_LES = {"sgstype": (str, 1), "hwm": (float, 1)}
+_DNS_TABLES = ("cbcvel", "cbcpre", "cbcsgs", "bcvel", "bcpre", "bcsgs")    # namelist /dns/, param.f90:95-111
+_LES_TABLES = ("lwm",)                                                      # namelist /les/, param.f90:112-115
+_REQUIRED = ("ng", "l", "visci", "cbcvel", "cbcpre")
+
+
+def _conv(name, typ, v):
+    if typ is float and isinstance(v, (int, float)) and not isinstance(v, bool):
+        return float(v)
+    if typ is int and isinstance(v, int) and not isinstance(v, bool):
+        return v
+    if typ is bool and isinstance(v, bool):
+        return v
+    if typ is str and isinstance(v, str):
+        return v
+    raise DeckError("entry %s: value %r is not of type %s" % (name, v, typ.__name__))
+
+
+def read_input(path):
+    """Read &dns and &les of an input.nml into a Deck (read_input, src/param.f90:88-152).  Raises DeckError when there is no
+    &dns group, a required entry (ng, l, visci, cbcvel, cbcpre) is missing, a name is unknown to the group, a group is
+    not terminated, or a value has the wrong type or count -- where the Fortran runtime would stop with an I/O error."""
+    groups = _groups(open(path).read())
+    if "dns" not in groups:
+        raise DeckError("%s: no &dns group found" % path)
+    d = Deck()
+    seen = set()
+    for gname, scalars, tables in (("dns", _DNS, _DNS_TABLES), ("les", _LES, _LES_TABLES)):
+        for name, sub, vals in groups.get(gname, []):
+            seen.add(name)
+            if name in tables:
+                arr = getattr(d, name)
+                typ = str if arr.dtype.kind == "U" else (int if arr.dtype.kind == "i" else float)
+                if arr.ndim == 3:                                   # (0:1,1:3,1:3): Fortran order, optionally one velocity component
+                    spec = [x.strip() for x in sub.strip("()").split(",")] if sub else []
+                    comps = [int(spec[2]) - 1] if len(spec) == 3 and ":" not in spec[2] else [0, 1, 2]
+                    if len(vals) != 6 * len(comps):
+                        raise DeckError("entry %s%s: %d values, expected %d" % (name, sub or "", len(vals), 6 * len(comps)))
                     it = iter(vals)
-                    for kk in ks:
+                    for kk in comps:
                         for idir in range(3):
                             for ib in range(2):
-                                arr[ib, idir, kk] = next(it)
+                                arr[ib, idir, kk] = _conv(name, typ, next(it))
                 else:
+                    if len(vals) != 6:
+                        raise DeckError("entry %s: %d values, expected 6" % (name, len(vals)))
                     it = iter(vals)
                     for idir in range(3):
                         for ib in range(2):
-                            arr[ib, idir] = next(it)
+                            arr[ib, idir] = _conv(name, typ, next(it))
+            elif name in scalars:
+                typ, cnt = scalars[name]
+                if len(vals) != cnt:
+                    raise DeckError("entry %s: %d values, expected %d" % (name, len(vals), cnt))
+                conv = [_conv(name, typ, v) for v in vals]
+                setattr(d, name, conv[0] if cnt == 1 else tuple(conv))
             else:
-                scal[name] = vals
-    def get(name, default):
-        return scal.get(name, default)
-    d.ng = tuple(int(x) for x in get("ng", d.ng)); d.l = tuple(float(x) for x in get("l", d.l))
-    d.gtype = int(get("gtype", [d.gtype])[0]); d.gr = float(get("gr", [d.gr])[0])
-    d.cfl = float(get("cfl", [d.cfl])[0]); d.dtmax = float(get("dtmax", [d.dtmax])[0])
-    d.dt_f = float(get("dt_f", [d.dt_f])[0]); d.visci = float(get("visci", [d.visci])[0])
-    d.inivel = get("inivel", [d.inivel])[0]; d.is_wallturb = bool(get("is_wallturb", [d.is_wallturb])[0])
-    d.bforce = tuple(float(x) for x in get("bforce", d.bforce))
-    d.is_forced = tuple(bool(x) for x in get("is_forced", d.is_forced)); d.velf = tuple(float(x) for x in get("velf", d.velf))
-    d.dims = tuple(int(x) for x in get("dims", d.dims))
-    d.nstep = int(get("nstep", [d.nstep])[0]); d.time_max = float(get("time_max", [d.time_max])[0])
-    d.tw_max = float(get("tw_max", [d.tw_max])[0]); d.stop_type = tuple(bool(x) for x in get("stop_type", d.stop_type))
-    d.restart = bool(get("restart", [d.restart])[0]); d.is_overwrite_save = bool(get("is_overwrite_save", [d.is_overwrite_save])[0])
-    d.nsaves_max = int(get("nsaves_max", [d.nsaves_max])[0])
-    for nm in ("icheck", "iout0d", "iout1d", "iout2d", "iout3d", "isave"):
-        setattr(d, nm, int(get(nm, [getattr(d, nm)])[0]))
-    d.sgstype = get("sgstype", [d.sgstype])[0]; d.hwm = float(get("hwm", [d.hwm])[0])
+                raise DeckError("unknown entry %r in group &%s" % (name, gname))
+    missing = [k for k in _REQUIRED if k not in seen]
+    if missing:
+        raise DeckError("%s: required entries missing from &dns: %s" % (path, ", ".join(missing)))
     return d

@@ -113,6 +113,11 @@ def test_deck_reader_run_control(tmp_path):
     p.write_text("""&dns
 ng(1:3) = 16, 16, 16
 l(1:3) = 1., 1., 1.
+visci = 100.
+cbcvel(0:1,1:3,1) = 6*'P'
+cbcvel(0:1,1:3,2) = 6*'P'
+cbcvel(0:1,1:3,3) = 6*'P'
+cbcpre(0:1,1:3) = 6*'P'
 nstep = 250, time_max = 12.5, tw_max = 0.2
 stop_type(1:3) = F, T, T
 restart = T, is_overwrite_save = F, nsaves_max = 3

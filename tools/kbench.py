@@ -43,6 +43,9 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--deck", default="tgv", choices=["tgv", "channel"])
     ap.add_argument("--warm", type=int, default=3)
+    ap.add_argument("--sgs", default="smag", choices=["smag", "dsmag", "none"])
+    ap.add_argument("--impdiff", default="", choices=["", "3d", "1d"], help="Crank-Nicolson diffusion (_IMPDIFF / _IMPDIFF_1D): times the per-procedure substep")
+    ap.add_argument("--wall-model", action="store_true")
     args = ap.parse_args()
     global WARM
     WARM = args.warm
@@ -51,8 +54,16 @@ def main():
     from cales_b200.driver import Simulation
     only = set(x for x in args.only.split(",") if x)
     ng = tuple(args.ng)
-    deck = pd.deck_tgv(ng=ng) if args.deck == "tgv" else pd.deck_channel(ng=ng, sgstype="smag")
+    if args.deck == "tgv":
+        deck = pd.deck_tgv(ng=ng, sgstype=args.sgs)
+    elif args.wall_model:
+        deck = pd.deck_channel(ng=ng, sgstype=args.sgs, wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.)
+    else:
+        deck = pd.deck_channel(ng=ng, sgstype=args.sgs)
+    if args.impdiff:
+        deck.impdiff = True; deck.impdiff_1d = args.impdiff == "1d"
     sim = Simulation(deck)
+    print("# %s %s sgs=%s impdiff=%s arith=%s fused=%s graph=%s" % (args.deck, ng, args.sgs, args.impdiff or "no", sim.lib.arith, sim.fused, sim.graph))
     sim.init_flow(); sim.start()
     sim.step()
     n = sim.n; nn = L._ia(n); D = sim.d; d = deck
@@ -79,6 +90,14 @@ def main():
             for bw in (0, 1):
                 add("fft_%s_%s_%s" % (bc.decode(), "xy"[dir_], "bwd" if bw else "fwd"), 16,
                     lambda: sim.chk(lib.cales_fft_lines(sim.ctx, nn, dir_, bc, b"c", bw, wk.data_ptr())))
+    # cuFFT as the comparison point (north star; what src/fft.f90:86-97,247-272 calls): batched D2Z / Z2D over the same lines of
+    # the same array through torch.fft (out of place: 8 B/cell read + ~8 B/cell written, like the hand-written passes)
+    a3 = wk.view(int(n[2]), int(n[1]), int(n[0]))                 # C order (k, j, i) == Fortran (i, j, k)
+    for dname, dim in (("x", 2), ("y", 1)):
+        spec = torch.fft.rfft(a3, dim=dim)
+        add("cufft_D2Z_%s" % dname, 16, lambda: torch.fft.rfft(a3, dim=dim))
+        add("cufft_Z2D_%s" % dname, 16, lambda: torch.fft.irfft(spec, n=a3.shape[dim], dim=dim))
+        del spec
     for per in (1, 0):
         wk.normal_()
         add("gaussel_%s" % ("periodic" if per else "nonper"), 16, lambda: sim.chk(lib.cales_gaussel(
@@ -93,6 +112,8 @@ def main():
     add("bounduvw", 0, lambda: sim.bounduvw(True, False))
     add("boundp", 0, lambda: sim.boundp(d.cbcpre, sim.bcp, "p"))
     add("chkdt", 32, lambda: sim.chkdt())
+    if args.impdiff:
+        add("substep(per-procedure)", 0, lambda: sim.substep(1))
     add("step/3", 0, lambda: sim.step())
     sim.close()
 
