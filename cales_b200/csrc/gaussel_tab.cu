@@ -182,8 +182,15 @@ __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, l
     if (g < nfull) {
 #pragma unroll
       for (int q = 0; q < GU; ++q) { z[q] = zs[q * GC]; r[q] = ps[q * GC]; aa[q] = as[q]; }
+#ifdef CALES_FMA
+#pragma unroll
+      for (int q = 0; q < GU; ++q) { r[q] = r[q] * z[q]; aa[q] = aa[q] * z[q]; }
+#pragma unroll
+      for (int q = 0; q < GU; ++q) { pl = fma(-aa[q], pl, r[q]); r[q] = pl; }
+#else
 #pragma unroll
       for (int q = 0; q < GU; ++q) { pl = (r[q] - aa[q] * pl) * z[q]; r[q] = pl; }
+#endif
       if (kept) {
 #pragma unroll
         for (int q = 0; q < GU; ++q) ps[q * GC] = r[q];
@@ -399,8 +406,17 @@ __global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtens
       double r[TGU], z[TGU], aa[TGU];
 #pragma unroll
       for (int q = 0; q < TGU; ++q) { z[q] = zs[q * CW]; r[q] = ks[q * CW]; aa[q] = __ldg(as + q); }
+#ifdef CALES_FMA
+      // contraction build: (r - a pl) z re-associated as r z - (a z) pl -- the two products leave the dependent chain,
+      // which is then ONE fused multiply-add per level (tolerance parity, tests/; the strict build keeps the reference order)
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { r[q] = r[q] * z[q]; aa[q] = aa[q] * z[q]; }
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { pl = fma(-aa[q], pl, r[q]); ks[q * CW] = pl; }
+#else
 #pragma unroll
       for (int q = 0; q < TGU; ++q) { pl = (r[q] - aa[q] * pl) * z[q]; ks[q * CW] = pl; }
+#endif
     } else {
       for (int q = 0; q < ntail; ++q) { pl = (ks[q * CW] - as[q] * pl) * zs[q * CW]; ks[q * CW] = pl; }
     }

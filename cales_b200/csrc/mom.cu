@@ -408,3 +408,15 @@ extern "C" int cales_rk(cales_ctx* ctx, const double rkpar[2], const int n[3], c
   for (int c = 0; c < 3; ++c) f[c] = ctx->red_host[8 + c];
   return CALES_OK;
 }
+
+// rk with the update fused into the momentum kernel (explicit diffusion): u,v,w are read only, the updated velocity goes to
+// un,vn,wn (haloed arrays; interior written).  f(3) stays on the device (cales_bulk_forcing(f = NULL) consumes it).
+extern "C" int cales_rk_fused(cales_ctx* ctx, const double rkpar[2], const int n[3], const double dli[3], const double* dzci,
+                              const double* dzfi, const double* grid_vol_ratio_c, const double* grid_vol_ratio_f, double visc,
+                              double dt, const double* p, const int is_forced[3], const double velf[3], const double bforce[3],
+                              const double* visct, const double* u, const double* v, const double* w, double* un, double* vn, double* wn) {
+  CHECK_CTX(ctx);
+  if (!un || !vn || !wn || un == u || vn == v || wn == w) return cales_fail(ctx, CALES_ERR_INVALID, "rk_fused: un,vn,wn must be arrays other than u,v,w");
+  return k_rk_dev(ctx, rkpar, n, dli, dzci, dzfi, grid_vol_ratio_c, grid_vol_ratio_f, visc, dt, p, is_forced, velf, bforce, visct,
+                  (double*)u, (double*)v, (double*)w, un, vn, wn);
+}

@@ -30,6 +30,9 @@ struct SmagArgs {
   const double* zc; const double* dzci0;      // zc(0:n3+1), dzci(0:n3+1)
   const double* delk;                         // (dl(1)*dl(2)*dzf(k))**(1/3), precomputed per k
   const double *u, *v, *w;                    // the UN-extrapolated velocity (wall shear, sgs.f90:117-143)
+  // in-place extrapolation (wall-model faces in z only): the original ghost planes k = 0 / n3+1 of u and v, saved aside
+  // (nullptr: read the arrays)
+  const double *ug0, *vg0, *ug1, *vg1;
 };
 
 // del(k) = (dl(1)*dl(2)*dzf(k))**(1/3)   (sgs.f90:149)
@@ -43,8 +46,11 @@ __global__ void smag_del_k(int n3, double dl0, double dl1, const double* __restr
 __device__ __forceinline__ double wall_sqrt_tau_z(const Dims& d, const SmagArgs& A, int i, int j, int top) {
   const double* __restrict__ u = A.u; const double* __restrict__ v = A.v;
   const int ka = top ? d.n3 : 1, kb = top ? d.n3 + 1 : 0;
-  const double t1 = u[d.idx(i, j, ka)] - u[d.idx(i, j, kb)] + u[d.idx(i - 1, j, ka)] - u[d.idx(i - 1, j, kb)];
-  const double t2 = v[d.idx(i, j, ka)] - v[d.idx(i, j, kb)] + v[d.idx(i, j - 1, ka)] - v[d.idx(i, j - 1, kb)];
+  const double* ug = top ? A.ug1 : A.ug0; const double* vg = top ? A.vg1 : A.vg0;     // ghost plane kb: saved copy or the array itself
+  const long o = i + d.s1 * (long)j;
+  const double* ub = ug ? ug + o : u + d.idx(i, j, kb); const double* vb = vg ? vg + o : v + d.idx(i, j, kb);
+  const double t1 = u[d.idx(i, j, ka)] - ub[0] + u[d.idx(i - 1, j, ka)] - ub[-1];
+  const double t2 = v[d.idx(i, j, ka)] - vb[0] + v[d.idx(i, j - 1, ka)] - vb[-d.s1];
   const double tauw_s = sqrt(t1 * t1 + t2 * t2) * A.dzci0[top ? d.n3 : 0];
   return sqrt(0.5 * A.visc * tauw_s);
 }
@@ -437,7 +443,27 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
   const int gflat = 148 * 8;
   if (!strcmp(sgstype, "smag")) {
     const double *us = u, *vs = v, *ws = w;
-    if (any_wm) {                                            // sgs.f90:84-90: copies only matter where extrapolate acts
+    // Wall-model faces in z only and no x/y walls (the channel): instead of copying u,v,w (sgs.f90:84-90, 48 B/cell) the
+    // extrapolation (which touches the ghost planes k = 0 / n3+1 of u and v only) is done IN PLACE on the caller's arrays
+    // and undone afterwards; the four original planes are saved aside -- the van Driest wall shear reads them there.
+    bool inplace = any_wm;
+    for (int q6 = 0; q6 < 4; ++q6) inplace = inplace && !(is_bound[q6] && lwm[q6] != 0);
+    for (int idir = 0; idir < 2 && inplace; ++idir)
+      for (int ib = 0; ib < 2; ++ib) if (is_bound[tb(ib, idir)] && cbcvel[ib + 2 * idir + 6 * idir] == 'D') inplace = false;
+    static const bool no_inplace = getenv("CALES_SGS_COPY") != nullptr;
+    double* gsave = nullptr;
+    const size_t pb_ = (size_t)d.s2 * sizeof(double);
+    if (inplace && !no_inplace) {
+      gsave = (double*)cales_scratch(ctx, "sgs_gsave", 4 * pb_);
+      if (!gsave) return CALES_ERR_NOMEM;
+      const double* srcs[2] = {u, v};
+      for (int f = 0; f < 2; ++f)
+        for (int ib = 0; ib < 2; ++ib)
+          if (is_bound[tb(ib, 2)] && lwm[tb(ib, 2)] != 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(gsave + (size_t)(2 * f + ib) * d.s2, srcs[f] + (size_t)d.s2 * (ib ? n[2] + 1 : 0), pb_, cudaMemcpyDeviceToDevice, ctx->stream));
+      double* wkp[3] = {(double*)u, (double*)v, (double*)w};
+      if ((rc = extrap_launch(ctx, n, is_bound, dzci, wkp, ifaces3, 3, 1, nullptr, lwm))) return rc;
+    } else if (any_wm) {                                     // sgs.f90:84-90: copies only matter where extrapolate acts
       double* wk[3];
       static const char* nm[3] = {"sgs_wk0", "sgs_wk1", "sgs_wk2"};
       for (int c = 0; c < 3; ++c) if (!(wk[c] = (double*)cales_scratch(ctx, nm[c], fb))) return CALES_ERR_NOMEM;
@@ -460,6 +486,11 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
       }
     A.dl0 = dl[0]; A.dl1 = dl[1]; A.l2 = l[2]; A.dxi = dli[0]; A.dyi = dli[1]; A.visc = visc;
     A.zc = zc; A.dzci0 = dzci; A.delk = delk; A.u = u; A.v = v; A.w = w;
+    A.ug0 = A.vg0 = A.ug1 = A.vg1 = nullptr;
+    if (gsave) {
+      if (is_bound[tb(0, 2)] && lwm[tb(0, 2)] != 0) { A.ug0 = gsave; A.vg0 = gsave + 2 * (size_t)d.s2; }
+      if (is_bound[tb(1, 2)] && lwm[tb(1, 2)] != 0) { A.ug1 = gsave + (size_t)d.s2; A.vg1 = gsave + 3 * (size_t)d.s2; }
+    }
     Ptr6 P{};
     int kcs;
     const dim3 gs = strain_grid(n, kcs);
@@ -468,6 +499,13 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
     else
       strain_k<0, 1, false><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);
     KERNEL_CHECK(ctx);
+    if (gsave) {                                             // undo the in-place extrapolation: the caller's ghost planes return
+      double* dsts[2] = {(double*)u, (double*)v};
+      for (int f = 0; f < 2; ++f)
+        for (int ib = 0; ib < 2; ++ib)
+          if (is_bound[tb(ib, 2)] && lwm[tb(ib, 2)] != 0)
+            CUDA_TRY(ctx, cudaMemcpyAsync(dsts[f] + (size_t)d.s2 * (ib ? n[2] + 1 : 0), gsave + (size_t)(2 * f + ib) * d.s2, pb_, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     return CALES_OK;
   }
   if (strcmp(sgstype, "dsmag")) return cales_fail(ctx, CALES_ERR_INVALID, "unknown SGS model '%s'", sgstype);

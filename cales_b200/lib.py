@@ -84,6 +84,8 @@ SIGNATURES = {
     "cales_solver_gaussel_z": (C.c_int, [vp, c_int_p, vp, vp, vp, C.c_char_p, C.c_char_p, vp]),
     "cales_rk": (C.c_int, [vp, c_dbl_p, c_int_p, c_dbl_p, vp, vp, vp, vp, C.c_double, C.c_double, vp, c_int_p, c_dbl_p, c_dbl_p,
                            vp, vp, vp, vp, c_dbl_p]),
+    "cales_rk_fused": (C.c_int, [vp, c_dbl_p, c_int_p, c_dbl_p, vp, vp, vp, vp, C.c_double, C.c_double, vp, c_int_p, c_dbl_p, c_dbl_p,
+                                 vp, vp, vp, vp, vp, vp, vp]),
     "cales_mom_xyz_ad": (C.c_int, [vp, c_int_p, C.c_double, C.c_double, vp, vp, C.c_double, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cales_bulk_forcing": (C.c_int, [vp, c_int_p, c_int_p, c_dbl_p, vp, vp, vp]),
     "cales_bulk_mean": (C.c_int, [vp, c_int_p, vp, vp, c_dbl_p]),

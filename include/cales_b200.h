@@ -120,6 +120,13 @@ int cales_rk(cales_ctx* ctx, const double rkpar[2], const int n[3], const double
              const double* dzfi, const double* grid_vol_ratio_c, const double* grid_vol_ratio_f, double visc,
              double dt, const double* p, const int is_forced[3], const double velf[3], const double bforce[3],
              const double* visct, double* u, double* v, double* w, double f[3]);
+/* rk with the update applied inside the momentum kernel (explicit diffusion; 112 instead of 160 B/cell): u,v,w are only
+ * read, the updated velocity is written to the interior of un,vn,wn (other haloed arrays); same results as cales_rk,
+ * bit for bit in the strict build; f(3) stays on the device.  cales_substep is built on it. */
+int cales_rk_fused(cales_ctx* ctx, const double rkpar[2], const int n[3], const double dli[3], const double* dzci,
+                   const double* dzfi, const double* grid_vol_ratio_c, const double* grid_vol_ratio_f, double visc,
+                   double dt, const double* p, const int is_forced[3], const double velf[3], const double bforce[3],
+                   const double* visct, const double* u, const double* v, const double* w, double* un, double* vn, double* wn);
 /* mom_xyz_ad alone (src/mom.f90:17-309); dudtd.. may be NULL unless diffusion is implicit */
 int cales_mom_xyz_ad(cales_ctx* ctx, const int n[3], double dxi, double dyi, const double* dzci, const double* dzfi,
                      double visc, const double* u, const double* v, const double* w, const double* visct,

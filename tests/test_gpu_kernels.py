@@ -309,3 +309,100 @@ def test_gaussel_bitexact(env, n, periodic):
             A = np.diag(b + lam[i, j]) + np.diag(a[1:], -1) + np.diag(c_[:-1], 1)
             x = np.linalg.solve(A, p[i, j, :])
             assert np.allclose(ref[i, j, :], x, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [(16, 12, 10), (67, 9, 33), (64, 64, 64)])
+def test_rk_update_direct(env, n):
+    """rk (src/rk.f90:17-121) kernel by kernel: two consecutive calls (the second reads the old right-hand side the first
+    one left: rkpar(2) /= 0 and the new<->old swap, rk.f90:98-100), through cales_rk (mom_k + rk_update_k) and through
+    cales_rk_fused (update inside the momentum kernel), each against the oracle's rk_update: identical bits (strict)."""
+    from oracle import rk as ork
+    from cales_b200.deck import rkcoeff
+    L, lib = env
+    u0, v0, w0, p, s = rnd_fields(n, 21, 5)
+    s = np.abs(s)
+    dzc, dzf, dzci, dzfi = grid(n[2])
+    dli = np.array([3.3, 2.1, 1.7]); visc, dt = 1e-2, 3e-3
+    bforce = (0.3, -0.2, 0.1)
+    gvr = dzf / dzf[1:-1].sum() / (n[0] * n[1])
+    noforce = L._ia(np.zeros(3, dtype=np.int32))
+    # oracle: two substeps
+    st = ork.RkState(n)
+    ur, vr, wr = u0.copy(order="F"), v0.copy(order="F"), w0.copy(order="F")
+    refs = []
+    for irk in (0, 1):
+        ork.rk_update(rkcoeff[irk], n, dli, dzci, dzfi, visc, dt, p, bforce, s, ur, vr, wr, st)
+        refs.append((ur.copy(order="F"), vr.copy(order="F"), wr.copy(order="F")))
+    I = (slice(1, -1),) * 3
+    for fused in (False, True):
+        with Ctx(L, lib, n) as c:
+            du, dv, dw, dp, ds = map(dev, (u0, v0, w0, p, s))
+            outs = [dev(np.zeros_like(u0)) for _ in range(3)]
+            ddzci, ddzfi, dg = dev(dzci), dev(dzfi), dev(gvr)
+            cur = [du, dv, dw]
+            for irk in (0, 1):
+                if fused:
+                    c.chk(lib.cales_rk_fused(c.ctx, L._da(rkcoeff[irk]), L._ia(n), L._da(dli), ddzci.data_ptr(), ddzfi.data_ptr(), dg.data_ptr(), dg.data_ptr(),
+                                             visc, dt, dp.data_ptr(), noforce, L._da(np.zeros(3)), L._da(bforce), ds.data_ptr(),
+                                             cur[0].data_ptr(), cur[1].data_ptr(), cur[2].data_ptr(), outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr()))
+                    # the fused kernel writes the interior only: carry the (unchanged) ghost cells over for the next call
+                    for a, b in zip(cur, outs):
+                        full = host(a, u0.shape); new = host(b, u0.shape); full[I] = new[I]
+                        b.copy_(torch.from_numpy(np.ascontiguousarray(full.ravel(order="F"))))
+                    cur, outs = outs, cur
+                else:
+                    c.chk(lib.cales_rk(c.ctx, L._da(rkcoeff[irk]), L._ia(n), L._da(dli), ddzci.data_ptr(), ddzfi.data_ptr(), dg.data_ptr(), dg.data_ptr(),
+                                       visc, dt, dp.data_ptr(), noforce, L._da(np.zeros(3)), L._da(bforce), ds.data_ptr(),
+                                       cur[0].data_ptr(), cur[1].data_ptr(), cur[2].data_ptr(), None))
+                for t, r in zip(cur, refs[irk]):
+                    assert same(host(t, u0.shape)[I], r[I]), (fused, irk)
+
+
+WM_CASES = {
+    "channel_log": ("deck_channel", dict(ng=(24, 16, 20), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.), 1),
+    "channel_lam": ("deck_channel", dict(ng=(24, 16, 20), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.), -1),
+    "duct_log": ("deck_duct", dict(ng=(16, 20, 24), wall_model=True), 1),
+    "duct_lam": ("deck_duct", dict(ng=(16, 20, 24), wall_model=True), -1),
+    "cavity": ("deck_cavity", dict(ng=(20, 16, 12)), 0),
+    "tgv": ("deck_tgv", dict(ng=(16, 16, 16)), 0),
+}
+
+
+@pytest.mark.parametrize("case", list(WM_CASES))
+@pytest.mark.parametrize("is_correc", [False, True])
+def test_bounduvw_setbc_wallmodel_direct(arith, case, is_correc):
+    """bounduvw (src/bound.f90:18-154) on its own: set_bc for every BC kind of the decks (P, D, N; cell- and face-centred), the
+    wall-model update of the BC planes (log law WM_LOG = 1 and the parabolic WM_LAM = -1, src/wmodel.f90:288-335) and the
+    `is_correc` variant that leaves the wall-normal component alone -- random interior fields, every cell of the haloed
+    arrays and every wall-model BC plane compared with the oracle (the Newton iteration and pow/log: 1e-13)."""
+    from conftest import need_gpu
+    need_gpu()
+    import oracle.param as op
+    import cales_b200.deck as pd
+    from oracle import bound as ob
+    from oracle.main import Sim
+    from cales_b200.driver import Simulation
+    name, kw, mtype = WM_CASES[case]
+    od, dd = getattr(op, name)(**kw), getattr(pd, name)(**kw)
+    if mtype:
+        od.lwm[od.lwm != 0] = mtype; dd.lwm[dd.lwm != 0] = mtype
+    o = Sim(od)
+    g = Simulation(dd, graph=False)
+    rng = np.random.default_rng(31)
+    shp = g.shape
+    f = [np.asfortranarray(0.5 + 0.3 * rng.standard_normal(shp)) for _ in range(3)]
+    g.set_fields(u=f[0], v=f[1], w=f[2])
+    U, V, W = [f[0].copy(order="F")], [f[1].copy(order="F")], [f[2].copy(order="F")]
+    g.bounduvw(True, is_correc)
+    ob.bounduvw(o.world, o.cbcvel if hasattr(o, "cbcvel") else od.cbcvel, o.st, True, is_correc, U, V, W)
+    tol = 0. if (arith == "strict" and not mtype) else 1e-13
+    for nm, ref in (("u", U[0]), ("v", V[0]), ("w", W[0])):
+        got = g.get(nm)
+        assert np.abs(got - ref).max() <= tol * max(1., np.abs(ref).max()), (nm, np.abs(got - ref).max())
+    if mtype:
+        for bname in ("bcu", "bcv", "bcw"):
+            hb = getattr(g, bname).host()
+            rb = getattr(o.st[0], bname)
+            for ax in "xyz":
+                assert np.abs(hb[ax] - rb[ax]).max() <= 1e-12 * max(1., np.abs(rb[ax]).max()), (bname, ax)
+    g.close()
