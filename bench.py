@@ -382,6 +382,12 @@ def run_ours(args):
     kern["mom_xyz_ad"] = (56, time_kernel(lambda: sim.chk(sim.lib.cales_mom_xyz_ad(
         sim.ctx, L._ia(n), d.dli[0], d.dli[1], D["dzci"].data_ptr(), D["dzfi"].data_ptr(), d.visc, sim.ptr("u"), sim.ptr("v"), sim.ptr("w"),
         sim.ptr("visct"), scr[0].data_ptr(), scr[1].data_ptr(), scr[2].data_ptr(), None, None, None))))
+    if not deck.impdiff:
+        hs = [torch.zeros(sim.ncell, dtype=torch.float64, device="cuda") for _ in range(3)]
+        kern["mom_rk_fused"] = (112, time_kernel(lambda: sim.chk(sim.lib.cales_rk_fused(
+            sim.ctx, L._da(rkcoeff[1]), L._ia(n), L._da(d.dli), D["dzci"].data_ptr(), D["dzfi"].data_ptr(), D["gvr_c"].data_ptr(), D["gvr_f"].data_ptr(),
+            d.visc, sim.dt, sim.ptr("p"), L._ia(np.zeros(3, dtype=np.int32)), L._da(d.velf), L._da(d.bforce), sim.ptr("visct"),
+            sim.ptr("u"), sim.ptr("v"), sim.ptr("w"), hs[0].data_ptr(), hs[1].data_ptr(), hs[2].data_ptr()))))
     if world == 1:
         wk = torch.zeros(int(ncell_loc), dtype=torch.float64, device="cuda")
         nn = L._ia(n)

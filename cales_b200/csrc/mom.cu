@@ -45,16 +45,33 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
   const int i = i0 + threadIdx.x, j = j0 + threadIdx.y;
   const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
   Stager<NF, V16> st(d, i0, j0, u, v, w, s, smem, k0 - 1, k1 + 1, R.p);
-  st.template issue<0>();
-  st.template issue<1>();
-  st.template issue<2>();
-  st.template issue<3>();
+  const bool active = i <= d.n1 && j <= d.n2;
+  const long n12 = (long)d.n1 * d.n2;
+  // RK == 2: the old right-hand side of my cell rides the same ring (thread-private 8-byte copies issued with the plane
+  // of its level, two levels ahead of its use), so its HBM latency is hidden like that of the tiles
+  double* const fl = smem + TSLOTS * NF * PLANE + (threadIdx.x + TX * threadIdx.y);      // [slot][3][TX*TY], my element
+  long ofl = (i - 1) + (long)d.n1 * (j - 1) + n12 * (k0 - 2);                            // my cell at plane st.knext (= k0-1 now)
+  auto flat = [&](auto sl_) {
+    constexpr int SLT = decltype(sl_)::v;
+    if (RK == 2) {
+      const int kp = st.knext - 1;                                                       // the plane just issued
+      if (active && kp >= k0 && kp <= k1) {
+        tile_cp8(fl + (SLT * 3 + 0) * (TX * TY), R.duo + ofl);
+        tile_cp8(fl + (SLT * 3 + 1) * (TX * TY), R.dvo + ofl);
+        tile_cp8(fl + (SLT * 3 + 2) * (TX * TY), R.dwo + ofl);
+      }
+      ofl += n12;
+    }
+    tile_commit();
+  };
+  st.template issue<0, false>(); flat(Slot<0>{});
+  st.template issue<1, false>(); flat(Slot<1>{});
+  st.template issue<2, false>(); flat(Slot<2>{});
+  st.template issue<3, false>(); flat(Slot<3>{});
   tile_wait_1();
   __syncthreads();
-  const bool active = i <= d.n1 && j <= d.n2;
   const double* const sm = smem + (threadIdx.x + 1) + PX * (threadIdx.y + 1);     // my cell in field 0 of slot 0
   constexpr int SL = NF * PLANE;
-  const long n12 = (long)d.n1 * d.n2;
   const double qdxi = 0.25 * dxi, qdyi = 0.25 * dyi;
   // k-1/2 quantities of level k0 = k+1/2 quantities of level k0-1 (planes k0-1, k0 = slots 0, 1)
   double wu_km, dudz_km, sxz_km, wv_km, dvdz_km, syz_km, ww_km, dwdz_km, fzz_km, s_ccm, s_pcm, s_cpm;
@@ -82,7 +99,7 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
   // array compute on whatever their tile cells hold and store nothing.
   auto step = [&](auto sc_, auto sp_, auto sn_) {
     constexpr int SC = decltype(sc_)::v, SP = decltype(sp_)::v, SN = decltype(sn_)::v;
-    st.template issue<SN>();
+    st.template issue<SN, false>(); flat(Slot<SN>{});
     {
       const double* uc = sm + SC * SL; const double* up = sm + SP * SL;
       const double* vc = uc + PLANE; const double* vp = up + PLANE;
@@ -170,9 +187,10 @@ __global__ void __launch_bounds__(TX* TY, 2) mom_k(Dims d, double dxi, double dy
             const double p_ccc = pc_[0];
             double un_, vn_, wn_;
             if (RK == 2) {
-              un_ = u_ccc + R.f1 * du_ + R.f2 * R.duo[o] + R.f12 * (R.bfx - dxi * (pc_[1] - p_ccc));
-              vn_ = v_ccc + R.f1 * dv_ + R.f2 * R.dvo[o] + R.f12 * (R.bfy - dyi * (pc_[PX] - p_ccc));
-              wn_ = w_ccc + R.f1 * dw_ + R.f2 * R.dwo[o] + R.f12 * (R.bfz - dzci_k * (up[4 * PLANE] - p_ccc));
+              const double* fo = fl + SC * 3 * (TX * TY);
+              un_ = u_ccc + R.f1 * du_ + R.f2 * fo[0] + R.f12 * (R.bfx - dxi * (pc_[1] - p_ccc));
+              vn_ = v_ccc + R.f1 * dv_ + R.f2 * fo[TX * TY] + R.f12 * (R.bfy - dyi * (pc_[PX] - p_ccc));
+              wn_ = w_ccc + R.f1 * dw_ + R.f2 * fo[2 * TX * TY] + R.f12 * (R.bfz - dzci_k * (up[4 * PLANE] - p_ccc));
             } else {
               un_ = u_ccc + R.f1 * du_ + R.f12 * (R.bfx - dxi * (pc_[1] - p_ccc));
               vn_ = v_ccc + R.f1 * dv_ + R.f12 * (R.bfy - dyi * (pc_[PX] - p_ccc));
@@ -212,7 +230,7 @@ static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, co
   long cols = (long)cdiv(n[0], TX) * cdiv(n[1], TY);
   const int kc = pick_chunk(cols, n[2], 148 * 2, 12, 2);
   dim3 g(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc)), b(TX, TY);
-  const size_t sh = TSLOTS * (rk ? 5 : 4) * PLANE * sizeof(double);
+  const size_t sh = (TSLOTS * (rk ? 5 : 4) * PLANE + (rk && rk->f2 != 0. ? TSLOTS * 3 * TX * TY : 0)) * sizeof(double);
   const bool v16 = tile_v16(n[0], u, v, w, visct) && (!rk || ((uintptr_t)rk->p & 15) == 0);
   RkFuse R;
   memset(&R, 0, sizeof R);
@@ -220,7 +238,7 @@ static int mom_launch(cales_ctx* ctx, const int n[3], double dxi, double dyi, co
 #define MOM_GO(M_, V_, R_)                                                                                           \
   {                                                                                                                  \
     static bool attr = false;                                                                                        \
-    if (!attr) { attr = true; cudaFuncSetAttribute(mom_k<M_, V_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TSLOTS * 5 * PLANE * sizeof(double))); } \
+    if (!attr) { attr = true; cudaFuncSetAttribute(mom_k<M_, V_, R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((TSLOTS * 5 * PLANE + TSLOTS * 3 * TX * TY) * sizeof(double))); } \
     mom_k<M_, V_, R_><<<g, b, sh, ctx->stream>>>(d, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, dudt, dvdt, dwdt, dudtd, dvdtd, dwdtd, kc, R); \
   }
   if (rk) {

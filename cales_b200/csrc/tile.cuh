@@ -51,8 +51,9 @@ struct Stager {
     }
   }
 
-  // stage plane `knext` into slot S (nothing if the CTA does not need it); always one commit group
-  template <int S>
+  // stage plane `knext` into slot S (nothing if the CTA does not need it); always one commit group (COMMIT = false: the
+  // caller adds copies of its own to the group and commits it with tile_commit())
+  template <int S, bool COMMIT = true>
   __device__ __forceinline__ void issue() {
     if (knext <= klast) {
 #pragma unroll
@@ -64,9 +65,14 @@ struct Stager {
         }
     }
     ++knext;
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (COMMIT) asm volatile("cp.async.commit_group;" ::: "memory");
   }
 };
+
+__device__ __forceinline__ void tile_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tile_cp8(const double* smem_dst, const double* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(src) : "memory");
+}
 
 // all but the most recent commit group have landed
 __device__ __forceinline__ void tile_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
