@@ -68,6 +68,7 @@ struct cales_ctx {
   int rk_swap = 0;                      // which of the two RHS sets is "old" (rk.f90:98-100)
   bool rk_first = true;
   bool sgs_first = true;
+  int sgs_ave = 1, sgs_filter2d = 0;    // dsmag averaging geometry / test filter (cales_set_sgs_options)
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // copy streams of the pipelined solver exchange (solver.cu)
   cudaEvent_t side_ev[8] = {nullptr};   // [0..3] chunk ready (main -> side), [4..7] chunk pushed (side -> main)
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)

@@ -228,6 +228,9 @@ extern "C" int cales_strain_rate(cales_ctx* ctx, const int n[3], const double dl
 }
 
 // ---- filter3d (sgs.f90:616-680), NF arrays per launch (blockIdx.z / nkb selects the array) ---------------------------
+// z-march with the 3 x 3 x 3 neighbourhood held in registers: 9 loads per cell instead of 27; the sum keeps the reference's
+// association order (same bits).  F2D: filter2d (sgs.f90:824-848, the -D_FILTER_2D variant): 9 points of the plane, /16.
+template <bool F2D>
 __global__ void __launch_bounds__(BX* BY) filter3d_k(Dims d, CPtr6 in, Ptr6 out, int kc, int nkb) {
   const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
   if (i > d.n1 || j > d.n2) return;
@@ -237,24 +240,46 @@ __global__ void __launch_bounds__(BX* BY) filter3d_k(Dims d, CPtr6 in, Ptr6 out,
   double* __restrict__ pf = out.p[f];
   const long s1 = d.s1, s2 = d.s2;
   long c = d.idx(i, j, k0);
+  if (F2D) {
+    for (int k = k0; k <= k1; ++k, c += s2) {
+#define Q(di, dj) p[c + (di) + (dj) * s1]
+      pf[c] = (4. * Q(0, 0) + 2. * (Q(-1, 0) + Q(0, -1) + Q(1, 0) + Q(0, 1)) + 1. * (Q(-1, -1) + Q(1, -1) + Q(-1, 1) + Q(1, 1))) / 16.;
+#undef Q
+    }
+    return;
+  }
+  double m[3][3], q0[3][3], pl[3][3];      // planes k-1, k, k+1: [dj+1][di+1]
+#pragma unroll
+  for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+    for (int di = 0; di < 3; ++di) { m[dj][di] = p[c - s2 + (di - 1) + (dj - 1) * s1]; q0[dj][di] = p[c + (di - 1) + (dj - 1) * s1]; }
   for (int k = k0; k <= k1; ++k, c += s2) {
-#define Q(di, dj, dk) p[c + (di) + (dj) * s1 + (dk) * s2]
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+      for (int di = 0; di < 3; ++di) pl[dj][di] = p[c + s2 + (di - 1) + (dj - 1) * s1];
+#define Q(di, dj, dk) ((dk) < 0 ? m[(dj) + 1][(di) + 1] : (dk) == 0 ? q0[(dj) + 1][(di) + 1] : pl[(dj) + 1][(di) + 1])
     pf[c] = (8. * Q(0, 0, 0) +
              4. * (Q(-1, 0, 0) + Q(0, -1, 0) + Q(0, 0, -1) + Q(1, 0, 0) + Q(0, 1, 0) + Q(0, 0, 1)) +
              2. * (Q(0, -1, -1) + Q(-1, 0, -1) + Q(-1, -1, 0) + Q(0, 1, -1) + Q(1, 0, -1) + Q(1, -1, 0) +
                    Q(0, -1, 1) + Q(-1, 0, 1) + Q(-1, 1, 0) + Q(0, 1, 1) + Q(1, 0, 1) + Q(1, 1, 0)) +
              1. * (Q(-1, -1, -1) + Q(1, -1, -1) + Q(-1, 1, -1) + Q(1, 1, -1) + Q(-1, -1, 1) + Q(1, -1, 1) + Q(-1, 1, 1) + Q(1, 1, 1))) / 64.;
 #undef Q
+#pragma unroll
+    for (int dj = 0; dj < 3; ++dj)
+#pragma unroll
+      for (int di = 0; di < 3; ++di) { m[dj][di] = q0[dj][di]; q0[dj][di] = pl[dj][di]; }
   }
 }
 
-static int filter_launch(cales_ctx* ctx, const int n[3], double* const* in, double* const* out, int nf) {
+static int filter_launch(cales_ctx* ctx, const int n[3], double* const* in, double* const* out, int nf, bool f2d = false) {
   Dims d(n);
   const int kc = pick_kc(n[0], n[1], n[2]);
   const int nkb = cdiv(n[2], kc);
   CPtr6 I; Ptr6 O;
   for (int m = 0; m < nf; ++m) { I.p[m] = in[m]; O.p[m] = out[m]; }
-  filter3d_k<<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), nkb * nf), dim3(BX, BY), 0, ctx->stream>>>(d, I, O, kc, nkb);
+  if (f2d) filter3d_k<true><<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), nkb * nf), dim3(BX, BY), 0, ctx->stream>>>(d, I, O, kc, nkb);
+  else filter3d_k<false><<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), nkb * nf), dim3(BX, BY), 0, ctx->stream>>>(d, I, O, kc, nkb);
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
@@ -341,7 +366,7 @@ __global__ void prod_u_k(long n, const double* __restrict__ uc, const double* __
   }
 }
 
-struct Alph { int wall[6]; };   // is_bound && cbc(ib,idir,idir)=='D' (cmpt_alph2, sgs.f90:783-816)
+struct Alph { int wall[6]; int all; };   // is_bound && cbc(ib,idir,idir)=='D' (cmpt_alph2, sgs.f90:783-816); all: _FILTER_2D (817-821)
 
 // mij = 2*(mij - alph2*s0*sij) interior (sgs.f90:262-272) fused with interpolate (sgs.f90:850-870)
 __global__ void __launch_bounds__(BX* BY) mij_interp_k(Dims d, Alph al, const double* __restrict__ s0, CPtr6 sij, Ptr6 mij,
@@ -354,7 +379,7 @@ __global__ void __launch_bounds__(BX* BY) mij_interp_k(Dims d, Alph al, const do
   long c = d.idx(i, j, k0);
   for (int k = k0; k <= k1; ++k, c += d.s2) {
     double alph2 = 4.00;
-    if ((al.wall[0] && i == 1) || (al.wall[1] && i == d.n1) || (al.wall[2] && j == 1) || (al.wall[3] && j == d.n2) ||
+    if (al.all || (al.wall[0] && i == 1) || (al.wall[1] && i == d.n1) || (al.wall[2] && j == 1) || (al.wall[3] && j == d.n2) ||
         (al.wall[4] && k == 1) || (al.wall[5] && k == d.n3)) alph2 = 2.52;
     const double s = s0[c];
 #pragma unroll
@@ -367,9 +392,10 @@ __global__ void __launch_bounds__(BX* BY) mij_interp_k(Dims d, Alph al, const do
 
 // Germano contraction (sgs.f90:328-358) fused with the x-y plane sums of ave1d_channel (sgs.f90:455-474):
 // one CTA per (k, x-y tile); per-plane partials are folded in a fixed order afterwards.
+// cml/cmm (non-null): the per-cell contractions are stored as well (the _DUCT and _CAVITY averaging variants need them).
 __global__ void __launch_bounds__(BX* BY) contract_k(Dims d, CPtr6 mij, CPtr6 lij, const double* __restrict__ uf,
                                                       const double* __restrict__ vf, const double* __restrict__ wf,
-                                                      double* __restrict__ part, int ntile) {
+                                                      double* __restrict__ part, int ntile, double* __restrict__ cml, double* __restrict__ cmm) {
   const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1, k = blockIdx.z + 1;
   double ml = 0., mm = 0.;
   if (i <= d.n1 && j <= d.n2) {
@@ -382,6 +408,7 @@ __global__ void __launch_bounds__(BX* BY) contract_k(Dims d, CPtr6 mij, CPtr6 li
     L[3] = L[3] - a * b; L[4] = L[4] - a * e; L[5] = L[5] - b * e;
     ml = M[0] * L[0] + M[1] * L[1] + M[2] * L[2] + (M[3] * L[3] + M[4] * L[4] + M[5] * L[5]) * 2.;
     mm = M[0] * M[0] + M[1] * M[1] + M[2] * M[2] + (M[3] * M[3] + M[4] * M[4] + M[5] * M[5]) * 2.;
+    if (cml) { cml[c] = ml; cmm[c] = mm; }
   }
   ml = block_sum<BX * BY>(ml);
   mm = block_sum<BX * BY>(mm);
@@ -401,6 +428,47 @@ __global__ void plane_fold_k(const double* __restrict__ part, int ntile, int n3,
   if (threadIdx.x == 0) {
     const int k = q / 2, which = q % 2;
     p1d[which * ng3 + (lo3 - 1 + k)] = v * gar;
+  }
+}
+
+// ave0d_dit (sgs.f90:388-431): volume average = sum_k plane average(k) dzf(k)/l(3) over the local levels (then all-reduced)
+__global__ void dit_fold_k(const double* __restrict__ p1d, int ng3, int lo3, int n3, const double* __restrict__ dzf, double l3, double* __restrict__ p0d) {
+  const int which = blockIdx.x;
+  double v = 0.;
+  for (int k = threadIdx.x + 1; k <= n3; k += 256) v = v + p1d[which * ng3 + lo3 - 1 + k - 1] * dzf[k] / l3;
+  v = block_sum<256>(v);
+  if (threadIdx.x == 0) p0d[which] = v;
+}
+
+// ave2d_duct (sgs.f90:540-614, streamwise direction x): one warp per (j,k) row sums the per-cell contractions along i
+// (x is never decomposed in X-pencils) and scales by dl(1)/l(1)
+__global__ void __launch_bounds__(256) duct_rows_k(Dims d, const double* __restrict__ cml, const double* __restrict__ cmm, double gar,
+                                                    double* __restrict__ ml2d, double* __restrict__ mm2d) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= d.n2 * d.n3) return;
+  const int j = row % d.n2 + 1, k = row / d.n2 + 1;
+  const long c0 = d.idx(0, j, k);
+  double a = 0., b = 0.;
+  for (int i = lane + 1; i <= d.n1; i += 32) { a = a + cml[c0 + i]; b = b + cmm[c0 + i]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a = a + __shfl_down_sync(0xffffffffu, a, o); b = b + __shfl_down_sync(0xffffffffu, b, o); }
+  if (lane == 0) { ml2d[row] = a * gar; mm2d[row] = b * gar; }
+}
+
+// MODE 0 _DIT (two scalars), 2 _DUCT (per (j,k) row), 3 _CAVITY (no averaging: the cell's own contraction)
+template <int MODE>
+__global__ void __launch_bounds__(BX* BY) dsmag_final_var_k(Dims d, const double* __restrict__ a0, const double* __restrict__ a1,
+                                                            double* __restrict__ visct, int kc) {
+  const int i = blockIdx.x * BX + threadIdx.x + 1, j = blockIdx.y * BY + threadIdx.y + 1;
+  if (i > d.n1 || j > d.n2) return;
+  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  long c = d.idx(i, j, k0);
+  for (int k = k0; k <= k1; ++k, c += d.s2) {
+    double ml, mm;
+    if (MODE == 0) { ml = a0[0]; mm = a0[1]; }
+    else if (MODE == 2) { const long r = (j - 1) + (long)d.n2 * (k - 1); ml = a0[r]; mm = a1[r]; }
+    else { ml = a0[c]; mm = a1[c]; }
+    visct[c] = fmax(visct[c] * ml / mm, 0.);
   }
 }
 
@@ -541,17 +609,22 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
     if ((rc = k_boundp_multi(ctx, cbcsgs, n, bcs, nb, is_bound, dl, dzc, ps, 7))) return rc;
   }
   // (5) Mij first part: filter(s0*sij)                                                   sgs.f90:198-223
+  const bool f2d = ctx->sgs_filter2d != 0;                   // -D_FILTER_2D: filter2d, no extrapolation (sgs.f90:236-247, 316-327)
   prod_s_k<<<gflat, 256, 0, ctx->stream>>>(nflat, s0, Csij, Pwk);
   KERNEL_CHECK(ctx);
-  if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces0, 6, 0, cbcvel, nullptr))) return rc;
-  if ((rc = filter_launch(ctx, n, wk, mij, 6))) return rc;
+  if (!f2d && (rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces0, 6, 0, cbcvel, nullptr))) return rc;
+  if ((rc = filter_launch(ctx, n, wk, mij, 6, f2d))) return rc;
   // (6) filtered velocity                                                                sgs.f90:225-235
-  copy3_k<<<gflat, 256, 0, ctx->stream>>>(nflat, u, v, w, wk[0], wk[1], wk[2]);
-  KERNEL_CHECK(ctx);
-  if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces3, 3, 0, cbcvel, nullptr))) return rc;
-  {
+  if (!f2d) {
+    copy3_k<<<gflat, 256, 0, ctx->stream>>>(nflat, u, v, w, wk[0], wk[1], wk[2]);
+    KERNEL_CHECK(ctx);
+    if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces3, 3, 0, cbcvel, nullptr))) return rc;
     double* out[3] = {uf, vf, wf};
     if ((rc = filter_launch(ctx, n, wk, out, 3))) return rc;
+  } else {
+    double* in3[3] = {(double*)u, (double*)v, (double*)w};
+    double* out[3] = {uf, vf, wf};
+    if ((rc = filter_launch(ctx, n, in3, out, 3, true))) return rc;
   }
   // (7) BCs on the filtered velocity, strain rate of it                                   sgs.f90:256-261
   if ((rc = cales_bounduvw(ctx, cbcvel, n, bcuf, bcvf, bcwf, bcu_mag, bcv_mag, bcw_mag, nb, is_bound, lwm, l, dl, zc, zf, dzc, dzf,
@@ -565,6 +638,7 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
   Alph al;
   for (int idir = 0; idir < 3; ++idir)
     for (int ib = 0; ib < 2; ++ib) al.wall[2 * idir + ib] = is_bound[tb(ib, idir)] && cbcvel[ib + 2 * idir + 6 * idir] == 'D';
+  al.all = f2d ? 1 : 0;
   mij_interp_k<<<g, b, 0, ctx->stream>>>(d, al, s0, Csij, Pmij, u, v, w, uc, vc, wc, kc);
   KERNEL_CHECK(ctx);
   {
@@ -574,28 +648,64 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
   // (9b) Lij (stored in sij)                                                               sgs.f90:283-315
   prod_u_k<<<gflat, 256, 0, ctx->stream>>>(nflat, uc, vc, wc, Pwk);
   KERNEL_CHECK(ctx);
-  if ((rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces0, 6, 0, cbcvel, nullptr))) return rc;
-  if ((rc = filter_launch(ctx, n, wk, sij, 6))) return rc;
+  if (!f2d && (rc = extrap_launch(ctx, n, is_bound, dzci, wk, ifaces0, 6, 0, cbcvel, nullptr))) return rc;
+  if ((rc = filter_launch(ctx, n, wk, sij, 6, f2d))) return rc;
   {
     double* ps[3] = {uc, vc, wc};
     double* out[3] = {uf, vf, wf};
-    if ((rc = extrap_launch(ctx, n, is_bound, dzci, ps, ifaces0, 3, 0, cbcvel, nullptr))) return rc;
-    if ((rc = filter_launch(ctx, n, ps, out, 3))) return rc;
+    if (!f2d && (rc = extrap_launch(ctx, n, is_bound, dzci, ps, ifaces0, 3, 0, cbcvel, nullptr))) return rc;
+    if ((rc = filter_launch(ctx, n, ps, out, 3, f2d))) return rc;
   }
-  // (10)-(11) contraction + x-y plane averages                                             sgs.f90:328-364
+  // (10)-(11) contraction + averaging over the homogeneous directions                       sgs.f90:328-370
+  // ctx->sgs_ave: 1 _CHANNEL (x-y planes; the reference's hard-wired choice, sgs.f90:8), 0 _DIT (whole volume), 2 _DUCT
+  // (streamwise x), 3 _CAVITY (none)
+  const int ave = ctx->sgs_ave;
   const int ntile = cdiv(n[0], BX) * cdiv(n[1], BY);
   double* part = (double*)cales_scratch(ctx, "sgs_part", (size_t)2 * n[2] * ntile * sizeof(double));
-  double* p1d = (double*)cales_scratch(ctx, "sgs_p1d", (size_t)2 * ng[2] * sizeof(double));
+  double* p1d = (double*)cales_scratch(ctx, "sgs_p1d", (size_t)(2 * ng[2] + 2) * sizeof(double));
   if (!part || !p1d) return CALES_ERR_NOMEM;
-  CUDA_TRY(ctx, cudaMemsetAsync(p1d, 0, (size_t)2 * ng[2] * sizeof(double), ctx->stream));
-  contract_k<<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), n[2]), b, 0, ctx->stream>>>(d, Cmij, Csij, uf, vf, wf, part, ntile);
+  CUDA_TRY(ctx, cudaMemsetAsync(p1d, 0, (size_t)(2 * ng[2] + 2) * sizeof(double), ctx->stream));
+  double *cml = nullptr, *cmm = nullptr;
+  if (ave >= 2) { cml = wk[0]; cmm = wk[1]; }               // the reference keeps them in wk(:,:,:,1:2) too (sgs.f90:345-357)
+  contract_k<<<dim3(cdiv(n[0], BX), cdiv(n[1], BY), n[2]), b, 0, ctx->stream>>>(d, Cmij, Csij, uf, vf, wf, part, ntile, cml, cmm);
   KERNEL_CHECK(ctx);
+  if (ave == 2 || ave == 3) {
+    if (ave == 2) {
+      if (ctx->ipencil != 1) return cales_fail(ctx, CALES_ERR_INVALID, "_DUCT averaging needs X-aligned pencils");
+      double* r2 = (double*)cales_scratch(ctx, "sgs_p2d", (size_t)2 * n[1] * n[2] * sizeof(double));
+      if (!r2) return CALES_ERR_NOMEM;
+      duct_rows_k<<<cdiv((long)n[1] * n[2], 8), 256, 0, ctx->stream>>>(d, cml, cmm, dl[0] / l[0], r2, r2 + (size_t)n[1] * n[2]);
+      KERNEL_CHECK(ctx);
+      dsmag_final_var_k<2><<<g, b, 0, ctx->stream>>>(d, r2, r2 + (size_t)n[1] * n[2], visct, kc);
+    } else dsmag_final_var_k<3><<<g, b, 0, ctx->stream>>>(d, cml, cmm, visct, kc);
+    KERNEL_CHECK(ctx);
+    return CALES_OK;
+  }
   const double gar = dl[0] * dl[1] / (l[0] * l[1]);
   plane_fold_k<<<2 * n[2], 256, 0, ctx->stream>>>(part, ntile, n[2], lo[2], ng[2], gar, p1d);
   KERNEL_CHECK(ctx);
+  if (ave == 0) {
+    double* p0d = p1d + 2 * ng[2];
+    dit_fold_k<<<2, 256, 0, ctx->stream>>>(p1d, ng[2], lo[2], n[2], dzf, l[2], p0d);
+    KERNEL_CHECK(ctx);
+    if ((rc = k_allreduce_sum(ctx, p0d, 2))) return rc;                                      // sgs.f90:418
+    dsmag_final_var_k<0><<<g, b, 0, ctx->stream>>>(d, p0d, nullptr, visct, kc);
+    KERNEL_CHECK(ctx);
+    return CALES_OK;
+  }
   if ((rc = k_allreduce_sum(ctx, p1d, 2 * ng[2]))) return rc;                                // sgs.f90:475
   // (12)                                                                                   sgs.f90:372-380
   dsmag_final_k<<<g, b, 0, ctx->stream>>>(d, p1d, ng[2], lo[2], visct, kc);
   KERNEL_CHECK(ctx);
+  return CALES_OK;
+}
+
+// the cpp switches of src/sgs.f90 that pick the dsmag averaging geometry and the test filter, selected at run time:
+// ave 0 _DIT (ave0d_dit, sgs.f90:388-431), 1 _CHANNEL (ave1d_channel 433-538; the reference's hard-wired default, sgs.f90:8),
+// 2 _DUCT (ave2d_duct 540-614, streamwise x), 3 _CAVITY (no averaging); filter_2d != 0: -D_FILTER_2D (filter2d 824-848)
+extern "C" int cales_set_sgs_options(cales_ctx* ctx, int ave, int filter_2d) {
+  CHECK_CTX(ctx);
+  if (ave < 0 || ave > 3) return cales_fail(ctx, CALES_ERR_INVALID, "sgs averaging mode %d: 0 _DIT, 1 _CHANNEL, 2 _DUCT, 3 _CAVITY", ave);
+  ctx->sgs_ave = ave; ctx->sgs_filter2d = filter_2d ? 1 : 0;
   return CALES_OK;
 }

@@ -36,7 +36,7 @@ class DevBound:
 
 
 class Simulation:
-    def __init__(self, deck, rank=0, nranks=1, uid=None, device=None, ave="channel", arith=None, fused=None, graph=None):
+    def __init__(self, deck, rank=0, nranks=1, uid=None, device=None, ave="channel", arith=None, fused=None, graph=None, filter_2d=False):
         """arith: "fma" (the product build, libcales_b200.so) | "strict" (the bit-exact -fmad=false build) | None = lib.DEFAULT_ARITH
         fused: drive the time loop through the fused entries cales_substep / cales_step (explicit diffusion; identical results)
                instead of the per-procedure sequence; None = CALES_B200_FUSED (default on)
@@ -67,6 +67,8 @@ class Simulation:
         rc = self.lib.cales_init(C.byref(self.ctx), L._ia(deck.ng), L._ia(deck.dims), deck.ipencil, L._ca(deck.cbcpre), rank,
                                  nranks, uid, dev_index, C.c_void_p(self.stream.cuda_stream), diff)
         L.check(None, rc, self.lib)
+        # dsmag averaging geometry / test filter: the reference's cpp switches _DIT/_CHANNEL/_DUCT/_CAVITY and _FILTER_2D (sgs.f90:8)
+        self.chk(self.lib.cales_set_sgs_options(self.ctx, {"dit": 0, "channel": 1, "duct": 2, "cavity": 3}[ave], int(bool(filter_2d))))
         arrs = [np.zeros(3, dtype=np.int32) for _ in range(8)] + [np.zeros(6, dtype=np.int32) for _ in range(2)]
         self.chk(self.lib.cales_get_decomp(self.ctx, *[a.ctypes.data_as(L.c_int_p) for a in arrs]))
         (self.lo, self.hi, self.n, self.n_x_fft, self.n_y_fft, self.lo_z, self.hi_z, self.n_z, self.nb, self.is_bound_flat) = arrs
@@ -267,6 +269,11 @@ class Simulation:
         self.chk(self.lib.cales_chkdiv(self.ctx, L._ia(self.lo), L._ia(self.hi), L._da(self.deck.dli), self.d["dzfi"].data_ptr(),
                                        self.ptr("u"), self.ptr("v"), self.ptr("w"), C.byref(tot), C.byref(mx)))
         return tot.value, mx.value
+
+    def out1d_chan(self, fname=None):
+        """on-the-fly channel statistics (out1d_single_point_chan, src/output.f90:509-691): the 27 profiles; see stats.py"""
+        from . import stats
+        return stats.out1d_chan(self, fname)
 
     def synchronize(self):
         self.chk(self.lib.cales_stream_synchronize(self.ctx))

@@ -102,6 +102,7 @@ SIGNATURES = {
     "cales_cmpt_sgs": (C.c_int, [vp, C.c_char_p, c_int_p, c_int_p, c_int_p, c_int_p, C.c_char_p, C.c_char_p, C.POINTER(Bound),
                                  c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, c_dbl_p, vp, vp, vp, vp, vp, vp, C.c_double,
                                  C.c_double, c_int_p, vp, vp, vp] + [C.POINTER(Bound)] * 6 + [vp]),
+    "cales_set_sgs_options": (C.c_int, [vp, C.c_int, C.c_int]),
     "cales_strain_rate": (C.c_int, [vp, c_int_p, c_dbl_p, vp, vp, vp, vp, vp, vp, vp]),
     "cales_filter3d": (C.c_int, [vp, c_int_p, vp, vp]),
     "cales_chkdt": (C.c_int, [vp, c_int_p, c_dbl_p, vp, vp, C.c_double, vp, vp, vp, vp, c_dbl_p]),
@@ -111,6 +112,7 @@ SIGNATURES = {
     "cales_transpose": (C.c_int, [vp, C.c_int, vp, vp]),
     "cales_updthalo": (C.c_int, [vp, c_int_p, c_int_p, vp]),
     "cales_peer_alloc": (C.c_int, [vp, C.c_char_p, C.c_long, C.POINTER(vp)]),
+    "cales_out1d_chan": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, vp, vp, vp, vp, vp, vp, vp, c_dbl_p]),
     "cales_substep": (C.c_int, [vp, C.POINTER(StepArgs), C.c_int, C.c_double]),
     "cales_step": (C.c_int, [vp, C.POINTER(StepArgs), C.c_double, C.c_int]),
     "cales_step_args_layout": (C.c_int, [C.POINTER(C.c_long)]),

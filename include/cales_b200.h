@@ -181,6 +181,11 @@ int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3], const in
                    const double* u, const double* v, const double* w, const cales_bound* bcuf,
                    const cales_bound* bcvf, const cales_bound* bcwf, const cales_bound* bcu_mag,
                    const cales_bound* bcv_mag, const cales_bound* bcw_mag, double* visct);
+/* the build-time switches of src/sgs.f90 for 'dsmag', selected at run time (before the first cales_cmpt_sgs):
+ * ave: 0 _DIT (ave0d_dit, sgs.f90:388-431), 1 _CHANNEL (ave1d_channel, 433-538: the reference's hard-wired `#define`, sgs.f90:8;
+ * the default), 2 _DUCT (ave2d_duct, 540-614, streamwise x), 3 _CAVITY (no averaging); filter_2d != 0: -D_FILTER_2D
+ * (filter2d, sgs.f90:824-848, alph2 = 2.52 everywhere, no extrapolation) */
+int cales_set_sgs_options(cales_ctx* ctx, int ave, int filter_2d);
 /* building blocks exported for parity tests: strain_rate (src/sgs.f90:1019-1110; sij may be NULL,
  * else 6 haloed arrays back to back) and filter3d (src/sgs.f90:616-680) */
 int cales_strain_rate(cales_ctx* ctx, const int n[3], const double dli[3], const double* dzci, const double* dzfi,
@@ -193,6 +198,16 @@ int cales_chkdt(cales_ctx* ctx, const int n[3], const double dl[3], const double
                 double visc, const double* visct, const double* u, const double* v, const double* w, double* dtmax);
 int cales_chkdiv(cales_ctx* ctx, const int lo[3], const int hi[3], const double dli[3], const double* dzfi,
                  const double* u, const double* v, const double* w, double* divtot, double* divmax);
+
+/* ---- on-the-fly statistics -----------------------------------------------------------------------------------
+ * replaces the reductions of out1d_single_point_chan (src/output.f90:509-691, idir = 3; called every iout1d steps through
+ * out1d.h90:35-36): the 27 plane-averaged single-point profiles (mean and moments of u,v,w, <uw>, p, p^2, vorticity,
+ * modelled stresses, <nu_t>, du/dz), summed over ranks.  dzc, dzf: DEVICE, the rank-local slices (0:n3+1) of dzc_g, dzf_g;
+ * u..visct: the rank-local haloed fields; buf: HOST, (27, ng3) in Fortran order.  Writing fname.out / fname.bin stays with
+ * the host (cales_b200/stats.py).  The budget block of the same routine (output.f90:692-920) is not covered. */
+int cales_out1d_chan(cales_ctx* ctx, const int ng[3], const int lo[3], const int hi[3], const double l[3], const double dl[3],
+                     const double* dzc, const double* dzf, const double* u, const double* v, const double* w, const double* p,
+                     const double* visct, double* buf);
 
 /* ---- fused entries of the time loop (optional): identical results to the per-procedure sequence ------------
  * Everything the callees of one RK3 substep take (src/main.f90:418-506), gathered once.  HOST struct; its pointer members are

@@ -16,9 +16,12 @@ class RankState:
 
 
 class Sim:
-    def __init__(self, deck, ave="channel"):
+    def __init__(self, deck, ave="channel", filter_2d=False):
+        """ave / filter_2d: the cpp switches _DIT/_CHANNEL/_DUCT/_CAVITY and _FILTER_2D of src/sgs.f90 (default: the reference's
+        hard-wired `#define _CHANNEL`, sgs.f90:8, with the 3-D test filter)"""
         self.deck = deck
         self.ave = ave
+        self.filter_2d = filter_2d
         ng = deck.ng
         self.world = World(ng, deck.dims, deck.cbcpre, deck.ipencil)
         w = self.world
@@ -111,7 +114,7 @@ class Sim:
         bnd.bounduvw(self.world, self.cbcvel, self.st, is_updt_wm, is_correc, self.U, self.V, self.W)
 
     def cmpt_sgs(self):
-        sgsmod.cmpt_sgs(self.world, self.st, self.deck, self.cbcvel, self.U, self.V, self.W, self.VISCT, ave=self.ave)
+        sgsmod.cmpt_sgs(self.world, self.st, self.deck, self.cbcvel, self.U, self.V, self.W, self.VISCT, ave=self.ave, filter_2d=self.filter_2d)
 
     def chkdt(self):
         d = self.deck

@@ -359,3 +359,29 @@ def test_fused_step_identical_to_per_procedure_sequence(case, arith):
     assert sims[0].dt == sims[1].dt or arith == "fma"
     for s in sims:
         s.close()
+
+
+@pytest.mark.parametrize("case,ave,f2d", [("tgv_smag", "dit", False), ("duct_smag", "duct", False), ("cavity_smag", "cavity", False),
+                                          ("channel_dsmag", "channel", True), ("duct_wm_smag", "duct", True)])
+def test_dsmag_averaging_and_filter_variants(case, ave, f2d):
+    """The build-time variants of the dynamic model: averaging over the whole volume (_DIT, ave0d_dit
+    sgs.f90:388-431), along the streamwise direction (_DUCT, ave2d_duct 540-614), none (_CAVITY), and the 2-D test filter
+    (-D_FILTER_2D, filter2d 824-848), each against the oracle on the matching flow, 5 steps, 1e-10."""
+    import oracle.param as op
+    import cales_b200.deck as pd
+    from oracle.main import Sim
+    from cales_b200.driver import Simulation
+    name, kw = CASES[case]
+    kw = dict(kw); kw["sgstype"] = "dsmag"
+    od, dd = getattr(op, name)(**kw), getattr(pd, name)(**kw)
+    if name == "deck_duct":                 # the laminar duct profile is x-uniform (nu_t = 0): start from an unforced TGV field instead
+        for d in (od, dd):
+            d.inivel = "tgv"; d.is_forced = (False, False, False)
+    o = Sim(od, ave=ave, filter_2d=f2d)
+    g = Simulation(dd, ave=ave, filter_2d=f2d)
+    g.init_flow(); g.start()
+    for _ in range(5):
+        o.step(icheck=1); g.step(icheck=1)
+    compare(o, g, 1e-10)
+    assert float(np.abs(o.VISCT[0]).max()) > 0.
+    g.close()

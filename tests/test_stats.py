@@ -1,0 +1,80 @@
+"""On-the-fly channel statistics: the oracle's restatement of out1d_single_point_chan against closed forms
+(CPU), decomposition independence of the emulated ranks (CPU), the ES24.16E3 writer (CPU) and the device reductions
+against the oracle (GPU)."""
+import numpy as np
+import pytest
+
+
+def test_oracle_profiles_closed_form():
+    """u = z, v = 2, w = x on a uniform grid: <u> = zc, <u^2> = zc^2, <v> = 2, vorticity_y = du/dz - dw/dx = 0, du/dz = 1."""
+    from oracle import output as oo
+    ng = (8, 6, 10); l = (2.0, 3.0, 1.0); dl = [l[q] / ng[q] for q in range(3)]
+    shp = (ng[0] + 2, ng[1] + 2, ng[2] + 2)
+    i = np.arange(shp[0])[:, None, None]; k = np.arange(shp[2])[None, None, :]
+    zc = (k - .5) * dl[2]; xc = (i - .5) * dl[0]
+    u = np.asfortranarray(zc + 0. * i + np.zeros(shp)); v = np.full(shp, 2.0, order="F"); w = np.asfortranarray(xc + np.zeros(shp))
+    p = np.zeros(shp, order="F"); s = np.ones(shp, order="F")
+    dz = np.full(ng[2] + 2, dl[2])
+    buf = oo.out1d_single_point_chan_local(ng, (1, 1, 1), ng, l, dl, dz, dz, u, v, w, p, s)
+    zk = (np.arange(1, ng[2] + 1) - .5) * dl[2]
+    assert np.allclose(buf[0], zk) and np.allclose(buf[3], zk ** 2) and np.allclose(buf[1], 2.0) and np.allclose(buf[25], 1.0)
+    assert np.allclose(buf[16], 0.0, atol=1e-13) and np.allclose(buf[26], 1.0) and np.allclose(buf[24], -0.25 * 4 * 2.0)
+
+
+def test_oracle_profiles_do_not_depend_on_the_decomposition():
+    import oracle.param as op
+    from oracle import output as oo
+    from oracle.main import Sim
+    out = []
+    for dims in ((1, 1), (2, 2)):
+        o = Sim(op.deck_channel(ng=(16, 12, 16), sgstype="smag", dims=dims))
+        o.step(icheck=1)
+        out.append(oo.out1d_single_point_chan(o.world, o.st, o.deck, o.U, o.V, o.W, o.P, o.VISCT))
+    # (<p> and <p^2> carry the additive constant of the pressure, round-off noise of the singular Poisson mode: SURVEY section 7)
+    rows = [m for m in range(27) if m not in (13, 14)]
+    assert np.abs(out[0][rows] - out[1][rows]).max() <= 1e-12 * np.abs(out[0][rows]).max()
+    a, b = out[0][13] - out[0][13].mean(), out[1][13] - out[1][13].mean()
+    assert np.abs(a - b).max() <= 1e-10 * max(np.abs(a).max(), 1.0)
+
+
+@pytest.mark.parametrize("v,s", [(1.0, " 1.0000000000000000E+000"), (-0.5, "-5.0000000000000000E-001"), (0.0, " 0.0000000000000000E+000"),
+                                 (123456.789, " 1.2345678900000000E+005")])
+def test_es24(v, s):
+    from cales_b200.stats import _es24
+    assert _es24(v) == s and len(s) == 24
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["channel_dsmag", "channel_wm_smag"])
+def test_out1d_chan_vs_oracle(case, arith, tmp_path):
+    from conftest import need_gpu
+    need_gpu()
+    import oracle.param as op
+    import cales_b200.deck as pd
+    from oracle import output as oo
+    from oracle.main import Sim
+    from cales_b200.driver import Simulation
+    from parity_mgpu import CASES
+    name, kw = CASES[case]
+    o = Sim(getattr(op, name)(**kw)); g = Simulation(getattr(pd, name)(**kw))
+    g.init_flow(); g.start()
+    for _ in range(3):
+        o.step(icheck=1); g.step(icheck=1)
+    ref = oo.out1d_single_point_chan(o.world, o.st, o.deck, o.U, o.V, o.W, o.P, o.VISCT)
+    fn = str(tmp_path / "stats")
+    got = g.out1d_chan(fn)
+    # p enters through <p> and <p^2>: the additive constant of the pressure is round-off noise of the singular Poisson mode
+    # (SURVEY section 7), so those two profiles are compared after removing it
+    for m in range(27):
+        a, b = got[m].copy(), ref[m].copy()
+        if m == 13:
+            a -= a.mean(); b -= b.mean()
+        if m == 14:
+            continue
+        scale = max(np.abs(ref[m]).max(), 1e-12 * np.abs(ref[:13]).max())
+        assert np.abs(a - b).max() <= 1e-10 * scale, (m, np.abs(a - b).max(), scale)
+    lines = open(fn + ".out").read().splitlines()
+    assert len(lines) == kw["ng"][2] and all(len(x) == 31 * 25 - 1 for x in lines)
+    back = np.fromfile(fn + ".bin").reshape((27, kw["ng"][2]), order="F")
+    assert np.array_equal(back, got)
+    g.close()
