@@ -12,7 +12,9 @@ NVARS = 27
 
 def _es24(v):
     """Fortran ES24.16E3: one digit before the point, 16 after, three exponent digits, width 24."""
-    if v == 0.0:
+    if v != v or v in (float("inf"), float("-inf")):
+        s = "NaN" if v != v else ("Infinity" if v > 0 else "-Infinity")
+    elif v == 0.0:
         s = "0.0000000000000000E+000"
     else:
         m, e = ("%.16E" % v).split("E")

@@ -71,7 +71,7 @@ def test_out1d_chan_vs_oracle(case, arith, tmp_path):
             a -= a.mean(); b -= b.mean()
         if m == 14:
             continue
-        scale = max(np.abs(ref[m]).max(), 1e-12 * np.abs(ref[:13]).max())
+        scale = max(np.abs(ref[m]).max(), 1e-6)          # (a profile that vanishes identically, e.g. <w>, is round-off on both sides)
         assert np.abs(a - b).max() <= 1e-10 * scale, (m, np.abs(a - b).max(), scale)
     lines = open(fn + ".out").read().splitlines()
     assert len(lines) == kw["ng"][2] and all(len(x) == 31 * 25 - 1 for x in lines)
