@@ -173,7 +173,21 @@ class Simulation:
         with torch.cuda.stream(self.stream):
             return self.fields[nm].cpu().numpy().reshape(self.shape, order="F")
 
-    def init_flow(self, mean_allreduce=None):
+    DEVICE_INIVEL = ("zer", "uni", "cou", "poi", "iop", "hcp", "pdc", "hdc", "tgv", "tgw", "ant", "duc")
+
+    def init_flow(self, mean_allreduce=None, device=None):
+        """initflow (main.f90:367).  The deterministic initial conditions are generated directly on the device
+        (cales_initflow); the noisy ones ('log', 'hcl', 'tbl') and device=False go through the host (hostinit.initflow)."""
+        d = self.deck
+        if device is None:
+            device = d.inivel.strip() in self.DEVICE_INIVEL
+        if device:
+            self.chk(self.lib.cales_initflow(self.ctx, d.inivel.strip().encode(), L._da(np.asarray(d.bcvel, dtype=np.float64).ravel(order="F")),
+                                             L._ia(d.ng), L._ia(self.lo), L._ia(self.n), L._da(d.l), L._da(d.dl), self.d["zc"].data_ptr(),
+                                             self.d["zf"].data_ptr(), self.d["dzc"].data_ptr(), self.d["dzf"].data_ptr(), d.visc,
+                                             L._ia([int(bool(x)) for x in d.is_forced]), L._da(d.velf), L._da(d.bforce), int(bool(d.is_wallturb)),
+                                             self.ptr("u"), self.ptr("v"), self.ptr("w"), self.ptr("p")))
+            return
         u, v, w, p = hostinit.initflow(self.deck, self.lo, self.n, self.h["zc"], self.h["zf"], self.h["dzc"], self.h["dzf"], mean_allreduce)
         self.set_fields(u=u, v=v, w=w, p=p)
 

@@ -112,6 +112,8 @@ SIGNATURES = {
     "cales_transpose": (C.c_int, [vp, C.c_int, vp, vp]),
     "cales_updthalo": (C.c_int, [vp, c_int_p, c_int_p, vp]),
     "cales_peer_alloc": (C.c_int, [vp, C.c_char_p, C.c_long, C.POINTER(vp)]),
+    "cales_initflow": (C.c_int, [vp, C.c_char_p, c_dbl_p, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, vp, vp, vp, vp, C.c_double, c_int_p, c_dbl_p,
+                                 c_dbl_p, C.c_int, vp, vp, vp, vp]),
     "cales_out1d_chan": (C.c_int, [vp, c_int_p, c_int_p, c_int_p, c_dbl_p, c_dbl_p, vp, vp, vp, vp, vp, vp, vp, c_dbl_p]),
     "cales_substep": (C.c_int, [vp, C.POINTER(StepArgs), C.c_int, C.c_double]),
     "cales_step": (C.c_int, [vp, C.POINTER(StepArgs), C.c_double, C.c_int]),

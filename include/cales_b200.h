@@ -199,6 +199,17 @@ int cales_chkdt(cales_ctx* ctx, const int n[3], const double dl[3], const double
 int cales_chkdiv(cales_ctx* ctx, const int lo[3], const int hi[3], const double dli[3], const double* dzfi,
                  const double* u, const double* v, const double* w, double* divtot, double* divmax);
 
+/* ---- input synthesis ---------------------------------------------------------------------------------------------
+ * replaces initflow (src/initflow.f90:17-283) for the deterministic initial conditions, generated directly in the caller's
+ * device arrays: inivel 'zer' 'uni' 'cou' 'poi' 'iop' 'hcp' 'pdc' 'hdc' 'tgv' 'tgw' 'ant' 'duc', set_mean (317-338) through
+ * a device reduction (+ all-reduce), and the vortex pair of is_wallturb (233-260).  'log' 'hcl' 'tbl' add noise from the
+ * Fortran compiler's random_number stream (285-315) and are refused (CALES_ERR_INVALID): they stay with the host.
+ * zc,zf,dzc,dzf: DEVICE, rank-local (0:n3+1); bcvel(0:1,3,3) HOST in Fortran order; ghost cells are left zero. */
+int cales_initflow(cales_ctx* ctx, const char* inivel, const double bcvel[18], const int ng[3], const int lo[3], const int n[3],
+                   const double l[3], const double dl[3], const double* zc, const double* zf, const double* dzc,
+                   const double* dzf, double visc, const int is_forced[3], const double velf[3], const double bforce[3],
+                   int is_wallturb, double* u, double* v, double* w, double* p);
+
 /* ---- on-the-fly statistics -----------------------------------------------------------------------------------
  * replaces the reductions of out1d_single_point_chan (src/output.f90:509-691, idir = 3; called every iout1d steps through
  * out1d.h90:35-36): the 27 plane-averaged single-point profiles (mean and moments of u,v,w, <uw>, p, p^2, vorticity,

@@ -142,3 +142,47 @@ hwm = 0.1
         assert "".join(d.cbcvel[:, 2, 0]) == "DD" and "".join(d.cbcpre[:, 2]) == "NN" and "".join(d.cbcsgs[:, 0]) == "PP"
         assert list(d.lwm[:, 2]) == [1, 1] and list(d.lwm[:, 0]) == [0, 0]
         assert d.is_forced == (True, False, False) and d.velf == (1.0, 0.0, 0.0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("inivel", ["zer", "uni", "cou", "poi", "iop", "hcp", "pdc", "hdc", "tgv", "tgw", "ant", "duc"])
+@pytest.mark.parametrize("wallturb", [False, True])
+def test_device_initflow_matches_the_host_path(inivel, wallturb, arith):
+    """the deterministic initial conditions generated directly on the device (cales_initflow) against the host
+    path (hostinit.initflow, itself held against the oracle above): sin/cos/exp/cosh and the set_mean reduction differ by
+    round-off only (1e-13 relative to the largest value of the field)."""
+    from conftest import need_gpu
+    need_gpu()
+    import cales_b200.deck as pd
+    from cales_b200 import hostinit
+    from cales_b200.driver import Simulation
+    d = pd.deck_channel(ng=(20, 12, 16), sgstype="smag", gtype=1, gr=2.0, l=(3.0, 2.0, 1.5))
+    d.inivel = inivel; d.is_wallturb = wallturb
+    d.is_forced = (True, False, False); d.velf = (1.2, 0.0, 0.0); d.bforce = (0.5, 0.0, 0.0)
+    d.bcvel[0, 2, 0] = 1.0; d.bcvel[1, 2, 0] = -0.5
+    g = Simulation(d, graph=False)
+    g.init_flow(device=True)
+    ref = hostinit.initflow(d, g.lo, g.n, g.h["zc"], g.h["zf"], g.h["dzc"], g.h["dzf"])
+    I = (slice(1, -1),) * 3
+    for nm, r in zip(("u", "v", "w", "p"), ref):
+        got = g.get(nm)
+        scale = max(float(np.abs(r[I]).max()), 1e-3)
+        assert np.abs(got[I] - r[I]).max() <= 1e-13 * scale, (nm, np.abs(got[I] - r[I]).max(), scale)
+    g.close()
+
+
+@pytest.mark.gpu
+def test_device_initflow_refuses_the_noisy_cases():
+    from conftest import need_gpu
+    need_gpu()
+    import cales_b200.deck as pd
+    from cales_b200 import lib as L
+    from cales_b200.driver import Simulation
+    d = pd.deck_channel(ng=(16, 12, 16), sgstype="smag")
+    d.inivel = "log"
+    g = Simulation(d, graph=False)
+    with pytest.raises(L.CalesError, match="host"):
+        g.init_flow(device=True)
+    g.init_flow()                                   # default: falls back to the host path for 'log'
+    assert float(np.abs(g.get("u")).max()) > 0.
+    g.close()
