@@ -72,7 +72,7 @@ def run_pair(case, nsteps, impdiff=None):
     g = Simulation(dd)
     g.init_flow()
     g.start()
-    assert abs(g.dt - o.dt) <= 1e-13 * o.dt
+    assert abs(g.dt - o.dt) <= 1e-12 * o.dt      # (the device-generated initial field differs from numpy by round-off)
     out = []
     for _ in range(nsteps):
         ro = o.step(icheck=1)
@@ -254,7 +254,7 @@ def test_fullsize_tgv256_vs_c_port(arith):
     o = CSim(op.deck_tgv(ng=ng))
     g = Simulation(deck_tgv(ng=ng))
     g.init_flow(); g.start()
-    assert abs(g.dt - o.dt) <= 1e-13 * o.dt
+    assert abs(g.dt - o.dt) <= 1e-12 * o.dt      # (the device-generated initial field differs from numpy by round-off)
     for _ in range(5):
         dmo = o.step(icheck=1)
         tot, dmg = g.step(icheck=1)
