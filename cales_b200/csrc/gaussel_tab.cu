@@ -41,6 +41,8 @@ struct GaussTab {
   long last_use = 0;
   CUtensorMap tmZ, tmP2;                                // tensor maps of Z and P2 (valid when has_tmap)
   bool has_tmap = false;
+  int twoway = 0;                                       // tables hold the two-way (twisted) factorisation of gauss2_k
+  double *MW = nullptr, *MDF = nullptr, *MDB = nullptr; // [nxy] meeting row: 1/(1 - db df), df(s-1), db(s)
 };
 
 static std::map<cales_ctx*, std::vector<GaussTab>> g_tabs;
@@ -483,6 +485,198 @@ __global__ void __launch_bounds__(32) gauss_tma_k(const __grid_constant__ CUtens
 #undef CMB_ISSUE
 }
 
+
+// ---- two-way solve (contraction build) --------------------------------------------------------------------------------------
+// gauss_tma_k is bound by the issue latency of its single warp (ncu r2l: 1.2 warps per scheduler, half the lanes idle with 16
+// columns per CTA).  gauss2_k runs the TWISTED factorisation instead: the upper half of every column is eliminated top-down by
+// warp 0 while warp 1 eliminates the lower half bottom-up, the two meet in a 2 x 2 system, and both halves are substituted
+// outwards at the same time -- the same column block in shared memory now keeps two warps busy, every sweep is half as long,
+// and nothing is added to the traffic or to the tables (Z holds forward pivots above the meeting row, backward pivots below).
+// Different operation order than dgtsv_homebrewed (solver.f90:153-179): agreement to round-off (tests: 1e-13 kernel level,
+// 1e-12 / 1e-10 solver and field level), which is why only the contraction build uses it; the strict build keeps gauss_tma_k.
+struct G2Meet { const double *W, *DF, *DB; };
+
+template <int PER>
+__global__ void __launch_bounds__(64) gauss2_build_k(int nxy, int n, const double* __restrict__ a, const double* __restrict__ b,
+                                                      const double* __restrict__ c, const double* __restrict__ lambdaxy, double* __restrict__ Z,
+                                                      double* __restrict__ P2, double* __restrict__ DEN, double* __restrict__ MW,
+                                                      double* __restrict__ MDF, double* __restrict__ MDB, const unsigned* flag, unsigned gen) {
+  if (*flag != gen) return;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= nxy) return;
+  const int nlev = PER ? n - 1 : n;
+  const int s = (((nlev + 15) / 16) / 2) * 16;                   // meeting row: first level of the lower half
+  const double lam = lambdaxy[col];
+  double d = 0.;
+  for (int l = 0; l < s; ++l) { const double z = __drcp_rn((b[l] + lam) - a[l] * d + EPS); d = c[l] * z; Z[(long)l * nxy + col] = z; }
+  const double df = d;                                           // df(s-1)
+  d = 0.;
+  for (int l = nlev - 1; l >= s; --l) { const double z = __drcp_rn((b[l] + lam) - c[l] * d + EPS); d = a[l] * z; Z[(long)l * nxy + col] = z; }
+  const double db = d;                                           // db(s)
+  const double w = 1. / (1. - db * df + EPS);
+  MW[col] = w; MDF[col] = df; MDB[col] = db;
+  if (PER) {                                                     // second system of gaussel_periodic: rhs = [-a(1), 0, ..., 0, -c(n-1)]
+    double y = 0.;
+    for (int l = 0; l < s; ++l) {
+      const double r = (l == 0 ? -a[0] : 0.) + (l == nlev - 1 ? -c[nlev - 1] : 0.);
+      y = (r - a[l] * y) * Z[(long)l * nxy + col];
+      P2[(long)l * nxy + col] = y;
+    }
+    const double yf = y;
+    y = 0.;
+    for (int l = nlev - 1; l >= s; --l) {
+      const double r = (l == 0 ? -a[0] : 0.) + (l == nlev - 1 ? -c[nlev - 1] : 0.);
+      y = (r - c[l] * y) * Z[(long)l * nxy + col];
+      P2[(long)l * nxy + col] = y;
+    }
+    const double yb = y;
+    const double xs = (yb - db * yf) * w;
+    double x = xs;
+    for (int l = s - 1; l >= 0; --l) { x = P2[(long)l * nxy + col] - (c[l] * Z[(long)l * nxy + col]) * x; P2[(long)l * nxy + col] = x; }
+    const double x0 = x;
+    x = yf - df * xs;
+    for (int l = s; l < nlev; ++l) { x = P2[(long)l * nxy + col] - (a[l] * Z[(long)l * nxy + col]) * x; P2[(long)l * nxy + col] = x; }
+    DEN[col] = (b[n - 1] + lam) + c[n - 1] * x0 + a[n - 1] * x + EPS;       // solver.f90:143-144
+  }
+}
+
+template <int PER, int CW>
+__global__ void __launch_bounds__(64) gauss2_k(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmP2,
+                                                const __grid_constant__ CUtensorMap tmP, int nxy, int n, long sz, int tng,
+                                                const double* __restrict__ a, const double* __restrict__ c, const double* __restrict__ DEN,
+                                                G2Meet M, double* __restrict__ p) {
+  extern __shared__ __align__(128) unsigned char shraw[];
+  constexpr int TGU = 16;
+  constexpr unsigned BOX = TGU * CW * sizeof(double);
+  const int nlev = PER ? n - 1 : n;
+  const int ngrp = (nlev + TGU - 1) / TGU, Gt = ngrp / 2, s = Gt * TGU, ntail = nlev - (nlev / TGU) * TGU;
+  const int wid = threadIdx.x >> 5, lid = threadIdx.x & 31;
+  const int lane = lid % CW, col0 = blockIdx.x * CW, col = col0 + lane;
+  double* keep = reinterpret_cast<double*>(shraw);
+  double* zr = keep + (size_t)ngrp * TGU * CW + (size_t)wid * tng * TGU * CW;             // this warp's pivot ring
+  double* xch = keep + (size_t)ngrp * TGU * CW + (size_t)2 * tng * TGU * CW;              // [2][CW]: x(0), x(nlev-1)
+  const unsigned bar0 = smem_u32(xch + 2 * CW) + 8u * wid * tng, keep0 = smem_u32(keep), zr0 = smem_u32(zr);
+  if (lid == 0) {
+    for (int q = 0; q < tng; ++q) mbar_init(bar0 + 8 * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  __syncwarp();
+  const bool valid = col < nxy;
+  double plast = 0., den = 1., mw = 0., mdf = 0., mdb = 0.;
+  if (valid) { mw = M.W[col]; mdf = M.DF[col]; mdb = M.DB[col]; }
+  if (PER && valid) { plast = p[(long)(n - 1) * sz + col]; den = DEN[col]; }
+  unsigned islot = 0, cslot = 0, cpar = 0;
+  double* kl = keep + lane;
+  // this warp's groups: warp 0 the upper half [0, Gt) in increasing order, warp 1 the lower half [Gt, ngrp) in decreasing order
+  const int g_first = wid == 0 ? 0 : ngrp - 1, g_step = wid == 0 ? 1 : -1, g_cnt = wid == 0 ? Gt : ngrp - Gt;
+#define G2_ISSUE(cond_, body_)                                       \
+  {                                                                  \
+    if (cond_) {                                                     \
+      if (lid == 0) {                                                \
+        const unsigned bar = bar0 + 8 * islot;                       \
+        const unsigned zdst = zr0 + islot * BOX;                     \
+        body_                                                        \
+      }                                                              \
+      if (++islot == (unsigned)tng) islot = 0;                       \
+    }                                                                \
+  }
+#define G2_WAIT()                                                    \
+  mbar_wait(bar0 + 8 * cslot, cpar);                                 \
+  const double* zs = zr + cslot * (TGU * CW) + lane;                 \
+  if (++cslot == (unsigned)tng) { cslot = 0; cpar ^= 1u; }
+  // ================= elimination towards the meeting row =================================================================
+#define EL_ISSUE(it_) G2_ISSUE((it_) < g_cnt, { const int gg_ = g_first + (it_) * g_step; mbar_expect_tx(bar, 2 * BOX);     \
+                                                tma_load_2d(zdst, &tmZ, col0, gg_ * TGU, bar); tma_load_2d(keep0 + gg_ * BOX, &tmP, col0, gg_ * TGU, bar); })
+  for (int it = 0; it < tng; ++it) EL_ISSUE(it)
+  double y = 0.;
+  for (int it = 0; it < g_cnt; ++it) {
+    const int g = g_first + it * g_step;
+    G2_WAIT()
+    double* ks = kl + (size_t)g * (TGU * CW);
+    double r[TGU], cz[TGU];
+    if (wid == 0) {
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { const double z = zs[q * CW]; r[q] = ks[q * CW] * z; cz[q] = __ldg(a + g * TGU + q) * z; }
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { y = fma(-cz[q], y, r[q]); ks[q * CW] = y; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { const int l = g * TGU + q; const double z = zs[q * CW]; r[q] = ks[q * CW] * z; cz[q] = (l < nlev ? __ldg(c + l) : 0.) * z; }
+#pragma unroll
+      for (int q = TGU - 1; q >= 0; --q) { y = fma(-cz[q], y, r[q]); ks[q * CW] = y; }
+    }
+    __syncwarp();
+    EL_ISSUE(it + tng)
+  }
+  __syncthreads();
+  // ================= meeting: rows s-1 and s =================================================================================
+  const double yf = kl[(size_t)(s - 1) * CW], yb = kl[(size_t)s * CW];
+  const double xs = (yb - mdb * yf) * mw;                    // x(s)
+  double x = wid == 0 ? xs : fma(-mdf, xs, yf);              // warp 0 continues upwards from x(s), warp 1 downwards from x(s-1)
+  double xend = 0.;                                          // x(0) / x(nlev-1): the periodic closure needs them
+  // ================= substitution away from the meeting row ================================================================
+#define SB_ISSUE(it_) G2_ISSUE((it_) < g_cnt, { const int gg_ = g_first + (g_cnt - 1 - (it_)) * g_step; mbar_expect_tx(bar, BOX); \
+                                                tma_load_2d(zdst, &tmZ, col0, gg_ * TGU, bar); })
+#define G2_STORE(g_) { tma_store_2d(&tmP, col0, (g_) * TGU, keep0 + (g_) * BOX); }
+  for (int it = 0; it < tng; ++it) SB_ISSUE(it)
+  for (int it = 0; it < g_cnt; ++it) {
+    const int g = g_first + (g_cnt - 1 - it) * g_step;       // the elimination order reversed
+    G2_WAIT()
+    double* ks = kl + (size_t)g * (TGU * CW);
+    double yy[TGU], cz[TGU];
+    if (wid == 0) {
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { yy[q] = ks[q * CW]; cz[q] = __ldg(c + g * TGU + q) * zs[q * CW]; }
+#pragma unroll
+      for (int q = TGU - 1; q >= 0; --q) { x = fma(-cz[q], x, yy[q]); ks[q * CW] = x; }
+      xend = x;
+    } else {
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { const int l = g * TGU + q; yy[q] = ks[q * CW]; cz[q] = (l < nlev ? __ldg(a + l) : 0.) * zs[q * CW]; }
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) { x = fma(-cz[q], x, yy[q]); ks[q * CW] = x; if (g * TGU + q == nlev - 1) xend = x; }
+    }
+    if (!PER) fence_async_smem();
+    __syncwarp();
+    if (!PER && lid == 0) G2_STORE(g)
+    SB_ISSUE(it + tng)
+  }
+  if (PER) {
+    // ================= periodic closure (solver.f90:142-145): p(n) and p(1:n-1) = p1 + p2 p(n) =========================
+    if (lid < CW) xch[wid * CW + lane] = xend;
+    __syncthreads();
+    const double pn = (plast - c[n - 1] * xch[lane] - a[n - 1] * xch[CW + lane]) / den;
+    // both warps walk their half in increasing order now
+    const int c_first = wid == 0 ? 0 : Gt;
+#define CB_ISSUE(it_) G2_ISSUE((it_) < g_cnt, { mbar_expect_tx(bar, BOX); tma_load_2d(zdst, &tmP2, col0, (c_first + (it_)) * TGU, bar); })
+    for (int it = 0; it < tng; ++it) CB_ISSUE(it)
+    for (int it = 0; it < g_cnt; ++it) {
+      const int g = c_first + it;
+      G2_WAIT()
+      double* ks = kl + (size_t)g * (TGU * CW);
+      double r[TGU];
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) r[q] = fma(zs[q * CW], pn, ks[q * CW]);
+#pragma unroll
+      for (int q = 0; q < TGU; ++q) ks[q * CW] = r[q];
+      if (g == ngrp - 1 && ntail > 0) ks[ntail * CW] = pn;      // level n-1 shares the last (partial) box (rows past nlev were zero)
+      fence_async_smem();
+      __syncwarp();
+      if (lid == 0) G2_STORE(g)
+      CB_ISSUE(it + tng)
+    }
+    if (wid == 1 && ntail == 0 && valid && lid < CW) p[(long)(n - 1) * sz + col] = pn;
+  }
+  if (lid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");     // shared memory must outlive the bulk stores
+#undef G2_ISSUE
+#undef G2_WAIT
+#undef EL_ISSUE
+#undef SB_ISSUE
+#undef CB_ISSUE
+#undef G2_STORE
+}
+
 static PFN_cuTensorMapEncodeTiled tmap_encoder() {
   static PFN_cuTensorMapEncodeTiled fn = nullptr;
   static bool tried = false;
@@ -518,24 +712,26 @@ static bool make_tmap(CUtensorMap* tm, const double* base, int cols, int rows, l
              CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const double* a, const double* b, const double* c, const double* lam) {
+static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const double* a, const double* b, const double* c, const double* lam, int twoway) {
   std::vector<GaussTab>& v = g_tabs[ctx];
   for (auto& t : v)
-    if (t.nxy == nxy && t.n == n && t.periodic == periodic && t.key[0] == a && t.key[1] == b && t.key[2] == c && t.key[3] == lam) return &t;
+    if (t.nxy == nxy && t.n == n && t.periodic == periodic && t.twoway == twoway && t.key[0] == a && t.key[1] == b && t.key[2] == c && t.key[3] == lam) return &t;
   GaussTab* t = nullptr;
   if (v.size() < 32) { v.emplace_back(); t = &v.back(); }
   else {
     t = &v[0];
     for (auto& u : v) if (u.last_use < t->last_use) t = &u;
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(t->Z); cudaFree(t->P2); cudaFree(t->DEN); cudaFree(t->ca); cudaFree(t->clam); cudaFree(t->flag);
+    cudaFree(t->Z); cudaFree(t->P2); cudaFree(t->DEN); cudaFree(t->ca); cudaFree(t->clam); cudaFree(t->flag); cudaFree(t->MW);
     *t = GaussTab();
   }
+  t->twoway = twoway;
   const size_t cells = (size_t)nxy * n;
   bool ok = cudaMalloc(&t->Z, cells * sizeof(double)) == cudaSuccess;
   if (periodic) ok = ok && cudaMalloc(&t->P2, cells * sizeof(double)) == cudaSuccess && cudaMalloc(&t->DEN, nxy * sizeof(double)) == cudaSuccess;
   ok = ok && cudaMalloc(&t->ca, 3 * (size_t)n * sizeof(double)) == cudaSuccess && cudaMalloc(&t->clam, nxy * sizeof(double)) == cudaSuccess &&
        cudaMalloc(&t->flag, sizeof(unsigned)) == cudaSuccess;
+  if (twoway) { ok = ok && cudaMalloc(&t->MW, 3 * (size_t)nxy * sizeof(double)) == cudaSuccess; t->MDF = t->MW + nxy; t->MDB = t->MDF + nxy; }
   if (!ok) { cales_fail(ctx, CALES_ERR_NOMEM, "tridiagonal pivot tables (%zu bytes) could not be allocated", cells * 8 * (periodic ? 2 : 1)); return nullptr; }
   t->cb = t->ca + n; t->cc = t->cb + n;
   // cached copies start as an all-ones bit pattern (a NaN no caller passes), so the first validation fails
@@ -554,7 +750,7 @@ static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const do
 void k_gaussel_tab_free(cales_ctx* ctx) {
   auto it = g_tabs.find(ctx);
   if (it == g_tabs.end()) return;
-  for (auto& t : it->second) { cudaFree(t.Z); cudaFree(t.P2); cudaFree(t.DEN); cudaFree(t.ca); cudaFree(t.clam); cudaFree(t.flag); }
+  for (auto& t : it->second) { cudaFree(t.Z); cudaFree(t.P2); cudaFree(t.DEN); cudaFree(t.ca); cudaFree(t.clam); cudaFree(t.flag); cudaFree(t.MW); }
   g_tabs.erase(it);
 }
 
@@ -579,7 +775,28 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   const int nxy = nx * ny;
   const int nlev = periodic ? n - 1 : n;
   if (nlev < 1) return 0;
-  GaussTab* t = find_tab(ctx, nxy, n, periodic, a, b, c, lambdaxy);
+  const bool peer = g_gauss_peer_out != nullptr;
+  // contraction build: the two-way kernel (gauss2_k) whenever the solution stays on this rank, the column has at least two
+  // level groups and its block fits in shared memory; CALES_GAUSS_TWOWAY=0 keeps the one-warp Thomas kernel
+  int twoway = 0, cw2 = 16, tng2 = 3;
+  size_t sh2 = 0;
+#ifdef CALES_FMA
+  {
+    static const int tw_env = getenv("CALES_GAUSS_TWOWAY") ? atoi(getenv("CALES_GAUSS_TWOWAY")) : 1;
+    static const int cw_env = getenv("CALES_GAUSS2_CW") ? atoi(getenv("CALES_GAUSS2_CW")) : 0;
+    static const int tng_env2 = getenv("CALES_GAUSS2_TNG") ? atoi(getenv("CALES_GAUSS2_TNG")) : 3;
+    tng2 = std::max(2, std::min(tng_env2, 8));
+    const int ngrp2 = (nlev + 15) / 16;
+    tng2 = std::min(tng2, std::max(1, ngrp2 / 2));
+    auto shbytes = [&](int cw_) { const size_t box_ = (size_t)16 * cw_ * sizeof(double);
+                                  return (size_t)ngrp2 * box_ + (size_t)2 * tng2 * box_ + (size_t)2 * cw_ * sizeof(double) + (size_t)2 * tng2 * 8; };
+    // 32 columns per CTA (256-byte rows: 0.129 vs 0.136 ms at 256^3) while two CTAs still fit per SM, else 16
+    cw2 = cw_env == 32 || cw_env == 16 ? cw_env : (shbytes(32) <= 100 * 1024 && nxy % 32 == 0 ? 32 : 16);
+    sh2 = shbytes(cw2);
+    twoway = tw_env && !peer && ngrp2 >= 2 && tng2 >= 1 && nxy % 2 == 0 && sz % 2 == 0 && ((uintptr_t)p & 15) == 0 && sh2 <= 110 * 1024 && tmap_encoder() != nullptr;
+  }
+#endif
+  GaussTab* t = find_tab(ctx, nxy, n, periodic, a, b, c, lambdaxy, twoway);
   if (!t) return -CALES_ERR_NOMEM;
   t->last_use = ++g_use;
   static unsigned gen = 0;
@@ -587,10 +804,33 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   const long tot = 3L * n + nxy;
   gauss_validate_k<<<(int)std::min<long>((tot + 255) / 256, 592), 256, 0, ctx->stream>>>(n, nxy, a, b, c, lambdaxy, t->ca, t->cb, t->cc, t->clam, t->flag, gen);
   ctx->launches++;
+#ifdef CALES_FMA
+  if (twoway) {
+    if (periodic) gauss2_build_k<1><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->MW, t->MDF, t->MDB, t->flag, gen);
+    else gauss2_build_k<0><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->MW, t->MDF, t->MDB, t->flag, gen);
+    ctx->launches++;
+    CUtensorMap tmZ2, tmP22, tmPp;
+    if (make_tmap(&tmZ2, t->Z, nxy, nlev, nxy, 16, cw2) && make_tmap(&tmP22, periodic ? t->P2 : t->Z, nxy, nlev, nxy, 16, cw2) && make_tmap(&tmPp, p, nxy, n, sz, 16, cw2)) {
+      G2Meet M{t->MW, t->MDF, t->MDB};
+#define G2_GO(PER_, CW_)                                                                                                   \
+  {                                                                                                                        \
+    static bool attr = false;                                                                                              \
+    if (!attr) { attr = true; cudaFuncSetAttribute(gauss2_k<PER_, CW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); } \
+    gauss2_k<PER_, CW_><<<cdiv(nxy, CW_), 64, sh2, ctx->stream>>>(tmZ2, tmP22, tmPp, nxy, n, sz, tng2, a, c, t->DEN, M, p);   \
+  }
+      if (periodic) { if (cw2 == 32) G2_GO(1, 32) else G2_GO(1, 16) }
+      else { if (cw2 == 32) G2_GO(0, 32) else G2_GO(0, 16) }
+#undef G2_GO
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) return -cales_fail(ctx, CALES_ERR_CUDA, "gauss2_k launch failed");
+      return 1;
+    }
+    return -cales_fail(ctx, CALES_ERR_CUDA, "gauss2_k: tensor map creation failed");
+  }
+#endif
   if (periodic) gauss_build_k<1><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->flag, gen);
   else gauss_build_k<0><<<cdiv(nxy, 64), 64, 0, ctx->stream>>>(nxy, n, a, b, c, lambdaxy, t->Z, t->P2, t->DEN, t->flag, gen);
   ctx->launches++;
-  const bool peer = g_gauss_peer_out != nullptr;
   {
     // TMA kernel: whole column block resident, at least two CTAs per SM, 16-byte aligned rows
     static const int use_tma = getenv("CALES_GAUSS_TMA") ? atoi(getenv("CALES_GAUSS_TMA")) : 1;
