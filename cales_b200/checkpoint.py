@@ -69,6 +69,9 @@ def load_all(io, filename, ng, lo, hi, u, v, w, p, time=0.0, istep=0, rank=0, nh
         return time, istep
     if io != "w":
         raise CheckpointError("io must be 'r' or 'w'")
+    if barrier is None and (rank != 0 or any(int(lo[q]) != 1 or int(hi[q]) != ng[q] for q in range(3))):
+        # this rank holds a sub-box: without a barrier nothing orders rank 0's create-and-truncate against the other ranks' writes
+        raise CheckpointError("writing a checkpoint from several ranks needs a barrier (MPI_FILE_OPEN is collective, load.f90:106-109)")
     if rank == 0:
         with open(filename, "wb") as f:                                    # MPI_MODE_CREATE + set size 0 (load.f90:106-109)
             f.truncate(good)

@@ -284,6 +284,22 @@ class Simulation:
                                        self.ptr("u"), self.ptr("v"), self.ptr("w"), C.byref(tot), C.byref(mx)))
         return tot.value, mx.value
 
+    def forcing_log(self):
+        """what main.f90:554-572 writes to forcing.out: the pressure gradient that keeps the bulk velocity, dpdl = -sum_rk f / dt
+        (main.f90:492, 508; -bforce when nothing is forced, main.f90:567), and the bulk means of the forced / driven components."""
+        d = self.deck
+        means = [0., 0., 0.]
+        for c, (nm, g) in enumerate((("u", "gvr_f"), ("v", "gvr_f"), ("w", "gvr_c"))):
+            if d.is_forced[c] or abs(d.bforce[c]) > 0.:
+                out = C.c_double(0.)
+                self.chk(self.lib.cales_bulk_mean(self.ctx, L._ia(self.n), self.d[g].data_ptr(), self.ptr(nm), C.byref(out)))
+                means[c] = out.value
+        if not any(d.is_forced):
+            dpdl = [-float(b) for b in d.bforce]
+        else:
+            dpdl = list(getattr(self, "dpdl", [0., 0., 0.]))
+        return dpdl, means
+
     def out1d_chan(self, fname=None):
         """on-the-fly channel statistics (out1d_single_point_chan, src/output.f90:509-691): the 27 profiles; see stats.py"""
         from . import stats
@@ -300,6 +316,10 @@ class Simulation:
         dtrki = dtrk ** (-1)
         # f(3) stays on the device inside the time loop (the reference reads it back only for its log, main.f90:559-565)
         self.f = self.rk(irk, want_f=self.want_f)
+        if self.want_f:                                        # dpdl(:) = dpdl(:) + f(:), main.f90:492
+            self._dpdl_acc = [a + b for a, b in zip(getattr(self, "_dpdl_acc", [0., 0., 0.]) if irk else [0., 0., 0.], self.f)]
+            if irk == 2:
+                self.dpdl = [-a * self.dti for a in self._dpdl_acc]        # main.f90:508
         self.bulk_forcing(self.f)
         if d.impdiff:                                          # main.f90:423-491
             alpha = -.5 * d.visc * dtrk

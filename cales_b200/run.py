@@ -112,6 +112,21 @@ def run(sim, deck, datadir="data/", rank=0, wtime=_time.time, log=print, barrier
     return res
 
 
+def calc_dims(cbcvel, sgstype, ipencil, nproc):
+    """dims for a deck that leaves them to the code (dims = 0,0).  The reference lets cuDecomp autotune, except that for
+    'smag' `calc_dims` (src/initmpi.f90:230-259) first makes sure that at most two subdomains lie between two opposite walls
+    (the van Driest damping needs a wall on every rank): the first decomposed direction with no-slip walls gets 2 ranks (1
+    when nproc is odd), the other one the rest.  Without walls in a decomposed direction: z slabs (1 x nproc)."""
+    t = {1: (1, 2), 2: (0, 2), 3: (0, 1)}[int(ipencil)]            # ipencil_t: the two decomposed directions (0-based)
+    if sgstype.strip() == "smag" and nproc >= 2:
+        for i, idir in enumerate(t):
+            if cbcvel[0, idir, idir] + cbcvel[1, idir, idir] == "DD":
+                d = [0, 0]
+                d[i], d[1 - i] = (1, nproc) if nproc % 2 == 1 else (2, nproc // 2)
+                return tuple(d)
+    return (1, nproc)
+
+
 def main(argv=None):
     import argparse
     ap = argparse.ArgumentParser(description="run a CaLES input deck on libcales_b200 (one process per GPU)")
@@ -125,8 +140,8 @@ def main(argv=None):
     from .driver import Simulation
     deck = read_input(args.deck)
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
-    if deck.dims[0] * deck.dims[1] == 0:                 # dims = 0,0: the reference autotunes (initmpi.f90:47-54); here z slabs
-        deck.dims = (1, world)
+    if deck.dims[0] * deck.dims[1] == 0:                 # dims = 0,0: the reference autotunes (initmpi.f90:47-54); here z slabs,
+        deck.dims = calc_dims(deck.cbcvel, deck.sgstype, deck.ipencil, world)   # after calc_dims for 'smag' (initmpi.f90:60-62)
     if deck.dims[0] * deck.dims[1] != world:
         raise SystemExit("dims=%s needs %d ranks, launched with %d" % (deck.dims, deck.dims[0] * deck.dims[1], world))
     torch.cuda.set_device(local)

@@ -47,7 +47,7 @@ def test_write_by_ranks_read_by_reference_reader(tmp_path, ng, dims):
         lo, hi, n = pencil(ng, dims, r)
         box = tuple(slice(lo[q] - 1, hi[q]) for q in range(3))
         f = [halo(g[box]) for g in glob]
-        ck.load_all("w", fn, ng, lo, hi, *f, time=1.25, istep=77, rank=r)
+        ck.load_all("w", fn, ng, lo, hi, *f, time=1.25, istep=77, rank=r, barrier=lambda: None)   # (ranks emulated one after the other)
     assert os.path.getsize(fn) == ck.expected_size(ng) == (np.prod(ng) * 4 + 2) * 8
     data, time, istep = reference_reader(fn, ng)
     for q in range(4):
@@ -79,7 +79,10 @@ def test_size_check_and_errors(tmp_path):
     with pytest.raises(ck.CheckpointError, match="outside"):
         ck.load_all("w", fn, ng, (1, 1, 1), (5, 4, 4), *f)
     with pytest.raises(ck.CheckpointError, match="does not match"):
-        ck.load_all("w", fn, ng, (1, 1, 1), (4, 4, 3), *f)
+        ck.load_all("w", fn, ng, (1, 1, 1), (4, 4, 3), *f, barrier=lambda: None)
+    with pytest.raises(ck.CheckpointError, match="needs a barrier"):      # a sub-box write without a barrier could race rank 0's truncate
+        g = [np.zeros((4, 6, 6), order="F") for _ in range(4)]
+        ck.load_all("w", fn, ng, (1, 1, 1), (2, ng[1], ng[2]), *g, rank=1)
 
 
 def test_alias(tmp_path):
