@@ -26,6 +26,10 @@ struct Plan {  // what fftini returns (src/fft.f90:23-143)
   char bc[2][2];     // [dir][ib]
   char c_or_f[2];
   double normfft;
+  // what initsolver returned to the caller, kept on the host: eigenvalues of x and y (scaled by dli^2), tridiagonal
+  // coefficients, z boundary types -- the distributed z solve (zdist.cu) builds its tables for the Y-pencil from them
+  std::vector<double> lx, ly, a, b, c;
+  char bcz[2] = {'P', 'P'};
 };
 
 struct FftTables {   // twiddle tables per transform length, device resident
@@ -71,6 +75,7 @@ struct cales_ctx {
   int sgs_ave = 1, sgs_filter2d = 0;    // dsmag averaging geometry / test filter (cales_set_sgs_options)
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // copy streams of the pipelined solver exchange (solver.cu)
   cudaEvent_t side_ev[8] = {nullptr};   // [0..3] chunk ready (main -> side), [4..7] chunk pushed (side -> main)
+  void* zdist = nullptr;                // tables of the distributed z solve (zdist.cu)
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;
   std::map<int, FftTables> tables;

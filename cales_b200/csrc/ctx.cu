@@ -137,6 +137,7 @@ extern "C" int cales_init(cales_ctx** out, const int ng[3], const int dims[2], i
 }
 
 void k_gaussel_tab_free(cales_ctx* ctx);
+void k_zdist_free(cales_ctx* ctx);
 void k_step_graphs_free(cales_ctx* ctx);
 
 extern "C" int cales_finalize(cales_ctx* ctx) {
@@ -148,6 +149,7 @@ extern "C" int cales_finalize(cales_ctx* ctx) {
   for (auto& e_ : ctx->side_ev) if (e_) cudaEventDestroy(e_);
   k_step_graphs_free(ctx);
   k_gaussel_tab_free(ctx);
+  k_zdist_free(ctx);
   for (auto& kv : ctx->scratch) cudaFree(kv.second.first);
   for (auto& kv : ctx->tables) { cudaFree(kv.second.w); cudaFree(kv.second.h); }
   cudaFree(ctx->red); cudaFreeHost(ctx->red_host); cudaFree(ctx->fdev); cudaFree(ctx->bar); cudaFree(ctx->halo_counter);

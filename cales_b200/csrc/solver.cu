@@ -26,6 +26,8 @@ bool k_fft_peer_capable(const char bc[2], char c_or_f, int n);
 bool k_gauss_tma_fits(int nxy, int n, int periodic);
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
                   const double* lambdaxy, double* p);
+int k_zdist_prepare(cales_ctx* ctx, int plan, const Plan& pl, const double* lambdaxy, const double* a, const double* b, const double* c, bool zper);
+int k_zdist_solve(cales_ctx* ctx, int plan, const double* lambdaxy, const double* a, const double* b, const double* c, double* w);
 
 #define EPS 2.220446049250313e-16
 
@@ -328,6 +330,8 @@ extern "C" int cales_initsolver(cales_ctx* ctx, const int ng[3], const int n_x_f
   }
   pl.normfft = 1. / nf;
   memcpy(pl.ng, ng, sizeof pl.ng);
+  pl.lx = lx; pl.ly = ly; pl.a.assign(a, a + n); pl.b.assign(b, b + n); pl.c.assign(c, c + n);
+  pl.bcz[0] = bcz[0]; pl.bcz[1] = bcz[1];
   *normfft = pl.normfft;
   int h = -1;
   for (size_t q = 0; q < ctx->plans.size(); ++q) if (!ctx->plans[q].used) { h = (int)q; break; }
@@ -389,6 +393,34 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   double* w0 = p2p ? (double*)pb0->local : (double*)cales_scratch(ctx, "solver_wk", bmax * sizeof(double));
   double* w1 = p2p ? (double*)pb1->local : (double*)cales_scratch(ctx, "solver_wk1", bmax * sizeof(double));
   if (!w0 || !w1) return CALES_ERR_NOMEM;
+  // ---- distributed z solve (zdist.cu; default in the product build with peer memory): z stays decomposed, the y <-> z
+  // transposes disappear -- two boundary planes per rank cross NVLink instead of the whole spectrum twice.  Pressure plans
+  // only (static coefficients; q == 0); CALES_ZDIST=0/1 forces it off/on (on in the strict build = tolerance parity there).
+  {
+#ifdef CALES_FMA
+    const int zd_default = 1;
+#else
+    const int zd_default = 0;
+#endif
+    static const int zd_env = getenv("CALES_ZDIST") ? atoi(getenv("CALES_ZDIST")) : -1;
+    if (p2p && (zd_env >= 0 ? zd_env != 0 : zd_default != 0) && ctx->dims[1] > 1 && ctx->dims[1] <= 8 && lambdaxy && q == 0 && n[2] >= 2) {
+      const int zr = k_zdist_prepare(ctx, plan, pl, lambdaxy, a, b, c, zper);
+      if (zr < 0) return -zr;
+      if (zr == 1) {
+        double *cur = w0, *oth = w1;
+        PeerBuf *pcur = pb0, *poth = pb1;
+        const bool xy = ctx->dims[0] > 1;
+        const long ypl = (long)ys[0] * ys[1];
+        if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, cur, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+        if (xy) { if ((rc = k_transpose_p2p(ctx, 0, cur, poth))) return rc; std::swap(cur, oth); std::swap(pcur, poth); }
+        if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], cur, ys[0], ypl, cur, ys[0], ypl, 1.0))) return rc;
+        if ((rc = k_zdist_solve(ctx, plan, lambdaxy, a, b, c, cur))) return rc;
+        if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, ys[0], ys[1], ys[2], cur, ys[0], ypl, cur, ys[0], ypl, 1.0))) return rc;
+        if (xy) { if ((rc = k_transpose_p2p(ctx, 3, cur, poth))) return rc; std::swap(cur, oth); std::swap(pcur, poth); }
+        return k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 1, xs[0], xs[1], xs[2], cur, xs[0], (long)xs[0] * xs[1], p + d.idx(1, 1, 1), d.s1, d.s2, normfft);
+      }
+    }
+  }
   // ---- pipelined exchange (default with peer memory): the y <-> z transposes are done by the COPY ENGINES, chunk by chunk,
   // while the SMs work on the next chunk.  y -> z: the local z range is cut into chunks; as soon as the x and y transforms of
   // a chunk are done, one strided 2-D DMA per peer pushes its [all x, y of that peer, chunk] box straight into the peer's

@@ -109,6 +109,7 @@ SIGNATURES = {
     "cales_chkdiv": (C.c_int, [vp, c_int_p, c_int_p, c_dbl_p, vp, vp, vp, vp, c_dbl_p, c_dbl_p]),
     "cales_fft_lines": (C.c_int, [vp, c_int_p, C.c_int, C.c_char_p, C.c_char, C.c_int, vp]),
     "cales_gaussel": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+    "cales_zdist_emulate": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp, vp]),
     "cales_transpose": (C.c_int, [vp, C.c_int, vp, vp]),
     "cales_updthalo": (C.c_int, [vp, c_int_p, c_int_p, vp]),
     "cales_peer_alloc": (C.c_int, [vp, C.c_char_p, C.c_long, C.POINTER(vp)]),

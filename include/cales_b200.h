@@ -252,6 +252,14 @@ int cales_fft_lines(cales_ctx* ctx, const int n[3], int dir, const char bc[2], c
 /* batched tridiagonal solve along z on a halo-free array (solver.f90:82-179); lambdaxy may be NULL */
 int cales_gaussel(cales_ctx* ctx, int nx, int ny, int n, int periodic, const double* a, const double* b,
                   const double* c, const double* lambdaxy, double* p);
+/* The distributed z solve of cales_solver (product build, z decomposed over 2..8 ranks with peer memory; csrc/zdist.cu) run
+ * for P emulated ranks on ONE device: the P blocks of levels are solved by the kernels of the multi-GPU path (local Thomas
+ * solve, boundary planes, tabulated inverse of the 2P x 2P interface system, correction pass), the exchange being a local
+ * copy.  Same problem as cales_gaussel (solver.f90:82-179; a,b,c: DEVICE (n), lambdaxy: DEVICE (nx*ny), required), same
+ * solution up to round-off.  pin != 0: the lambda = 0 column is singular (periodic / Neumann-Neumann z) and is regularised
+ * by pinning one interface unknown, so that column is defined up to its additive constant. */
+int cales_zdist_emulate(cales_ctx* ctx, int nx, int ny, int n, int P, int periodic, int pin, const double* a, const double* b,
+                        const double* c, const double* lambdaxy, double* p);
 /* pencil transposes (2decomp transpose_x_to_y etc. / cudecompTranspose*): which = 0 x->y, 1 y->z, 2 z->y, 3 y->x */
 int cales_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 /* work array the library owns, zero-filled, mapped into every rank of the node (CUDA IPC over NVLink; the role of cuDecomp's

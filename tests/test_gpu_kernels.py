@@ -311,6 +311,51 @@ def test_gaussel_bitexact(env, n, periodic):
             assert np.allclose(ref[i, j, :], x, rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("periodic", [0, 1])
+@pytest.mark.parametrize("n,P", [((16, 12, 16), 2), ((33, 7, 64), 4), ((64, 64, 256), 8), ((10, 5, 37), 3), ((32, 2, 17), 2), ((6, 7, 19), 8),
+                                 ((48, 40, 129), 4), ((32, 32, 600), 2)])
+def test_zdist_emulated_ranks(env, n, P, periodic):
+    """The distributed z solve (csrc/zdist.cu: z stays decomposed, two boundary planes per rank are exchanged instead of the
+    y <-> z transposes of solver.f90:56-62) with P emulated ranks on one device against gaussel / gaussel_periodic of the
+    oracle (solver.f90:82-151) on the same columns: round-off agreement (a different elimination order, both builds), for
+    well-conditioned columns, nearly singular ones (|lambda| = 1e-6) and the singular mean mode (lambda = 0, compatible
+    right-hand side, compared up to its additive constant as everywhere else)."""
+    from oracle import solver as osl
+    L, lib = env
+    rng = np.random.default_rng(16)
+    nx, ny, nz = n
+    dz = 1. + 0.5 * rng.random(nz + 2)
+    a = 1. / dz[1:nz + 1] / (0.5 * (dz[0:nz] + dz[1:nz + 1])); c_ = 1. / dz[1:nz + 1] / (0.5 * (dz[1:nz + 1] + dz[2:nz + 2])); b = -(a + c_)
+    if periodic:
+        a[0] = c_[-1] = 1. / dz[1] / (0.5 * (dz[1] + dz[nz])); b[0] = -(a[0] + c_[0]); b[-1] = -(a[-1] + c_[-1])   # a(1) couples to x(n): keep A.1 = 0
+    else:
+        b[0] += a[0]; b[-1] += c_[-1]                       # Neumann ends (initsolver.f90:156-160)
+    lam = -np.asfortranarray(rng.random((nx, ny))) * 3
+    lam[0, 0] = 0.; lam[min(1, nx - 1), 0] = -1e-6
+    p = np.asfortranarray(rng.standard_normal(n))
+    # compatible right-hand side for the singular column: orthogonal to the left null vector of A
+    A0 = np.diag(b) + np.diag(a[1:], -1) + np.diag(c_[:-1], 1)
+    if periodic:
+        A0[0, nz - 1] += a[0]; A0[nz - 1, 0] += c_[nz - 1]
+    wl = np.linalg.svd(A0)[0][:, -1]
+    p[0, 0, :] -= wl * (wl @ p[0, 0, :])
+    ref = p.copy(order="F")
+    (osl.gaussel_periodic if periodic else osl.gaussel)(nx, ny, nz, a, b, c_, ref, lam)
+    with Ctx(L, lib, n) as c:
+        dp = dev(p)
+        c.chk(lib.cales_zdist_emulate(c.ctx, nx, ny, nz, P, periodic, 1, dev(a).data_ptr(), dev(b).data_ptr(), dev(c_).data_ptr(), dev(lam).data_ptr(), dp.data_ptr()))
+        got = host(dp, p.shape)
+    # the mean mode: compare the residual-free part (constant removed); dense least squares as the reference for that column
+    x0 = np.linalg.lstsq(A0, p[0, 0, :], rcond=None)[0]
+    g0 = got[0, 0, :] - got[0, 0, :].mean(); x0 = x0 - x0.mean()
+    assert np.abs(g0 - x0).max() <= 1e-9 * max(np.abs(x0).max(), 1e-300)
+    got[0, 0, :] = ref[0, 0, :] = 0.
+    # conditioning of a column ~ 1/|lambda| (in units of the coefficients): the round-off budget follows it
+    cond = 1. + 1. / np.maximum(np.abs(lam), 1e-300); cond[0, 0] = 1.
+    err = np.abs(got - ref).max(axis=2) / np.maximum(np.abs(ref).max(axis=2), 1e-300)
+    assert (err <= 2e-14 * cond * nz).all(), float((err / cond).max())
+
+
 @pytest.mark.parametrize("n", [(16, 12, 10), (67, 9, 33), (64, 64, 64)])
 def test_rk_update_direct(env, n):
     """rk (src/rk.f90:17-121) kernel by kernel: two consecutive calls (the second reads the old right-hand side the first
