@@ -79,6 +79,7 @@ struct cales_ctx {
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;
   std::map<int, FftTables> tables;
+  int solver_path = 0;                  // exchange of the last cales_solver call: 0 none (one rank), 1 distributed z solve, 2 copy-engine pipeline, 3 kernel-fused, 4 separate transposes
   long launches = 0;                    // kernels launched by this library (bench.py gpu_launches)
   char err[512] = {0};
 };

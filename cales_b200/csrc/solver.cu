@@ -340,6 +340,12 @@ extern "C" int cales_initsolver(cales_ctx* ctx, const int ng[3], const int n_x_f
   return CALES_OK;
 }
 
+extern "C" const char* cales_solver_exchange(const cales_ctx* ctx) {
+  static const char* nm[5] = {"none (z on one rank)", "distributed z solve (zdist.cu): 2 boundary planes per rank, no y<->z transposes",
+                              "copy-engine pipelined y<->z transposes", "kernel-fused y<->z transposes", "separate transpose kernels / NCCL"};
+  return ctx && ctx->solver_path >= 0 && ctx->solver_path < 5 ? nm[ctx->solver_path] : "?";
+}
+
 extern "C" int cales_fftend(cales_ctx* ctx, int plan) {
   CHECK_CTX(ctx);
   if (plan < 0 || plan >= (int)ctx->plans.size()) return cales_fail(ctx, CALES_ERR_INVALID, "fftend: bad plan handle %d", plan);
@@ -402,11 +408,12 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
 #else
     const int zd_default = 0;
 #endif
-    static const int zd_env = getenv("CALES_ZDIST") ? atoi(getenv("CALES_ZDIST")) : -1;
+    const int zd_env = getenv("CALES_ZDIST") ? atoi(getenv("CALES_ZDIST")) : -1;   // read per call: bench.py switches it off after a failed parity check
     if (p2p && (zd_env >= 0 ? zd_env != 0 : zd_default != 0) && ctx->dims[1] > 1 && ctx->dims[1] <= 8 && lambdaxy && q == 0 && n[2] >= 2) {
       const int zr = k_zdist_prepare(ctx, plan, pl, lambdaxy, a, b, c, zper);
       if (zr < 0) return -zr;
       if (zr == 1) {
+        ctx->solver_path = 1;
         double *cur = w0, *oth = w1;
         PeerBuf *pcur = pb0, *poth = pb1;
         const bool xy = ctx->dims[0] > 1;
@@ -442,6 +449,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   const bool pipe = pipe_env >= 0 ? pipe_env != 0 : !fused_ok;
   if (p2p && pipe && ctx->dims[1] > 1 && ctx->dims[1] <= 16 && lambdaxy) {
     const int P = ctx->dims[1], me = ctx->coord[1];
+    ctx->solver_path = 2;
     if (!ctx->side[0]) {
       for (auto& st_ : ctx->side) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&st_, cudaStreamNonBlocking));
       for (auto& sev : ctx->side_ev) CUDA_TRY(ctx, cudaEventCreateWithFlags(&sev, cudaEventDisableTiming));
@@ -532,6 +540,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
     cales_distribute(ctx->ng[1], P, yst.data(), yen.data(), ysz.data());
     cales_distribute(ctx->ng[2], P, zst.data(), zen.data(), zsz.data());
     FftPeerOut FP; GPeer GP;
+    ctx->solver_path = 3;
     FP.np = GP.np = P; FP.nx = ys[0]; FP.zoff = zst[me] - 1;
     GP.plane = (long)ys[0] * ys[1]; GP.coff = (long)ys[0] * (yst[me] - 1);
     for (int q = 0; q < P; ++q) {
@@ -570,6 +579,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   }
   double *cur = w0, *oth = w1, *t_;
   PeerBuf *pcur = pb0, *poth = pb1, *pt_;
+  ctx->solver_path = 4;
 #define TRANSPOSE(which, P)                                                                       \
   if ((P) > 1) {                                                                                  \
     if ((rc = p2p ? k_transpose_p2p(ctx, which, cur, poth) : k_transpose(ctx, which, cur, oth))) return rc; \

@@ -81,6 +81,7 @@ SIGNATURES = {
                                    C.c_char_p, c_dbl_p, c_dbl_p, c_dbl_p, c_dbl_p, c_int_p, c_dbl_p]),
     "cales_fftend": (C.c_int, [vp, C.c_int]),
     "cales_solver": (C.c_int, [vp, c_int_p, c_int_p, C.c_int, C.c_double, vp, vp, vp, vp, C.c_char_p, C.c_char_p, vp]),
+    "cales_solver_exchange": (C.c_char_p, [vp]),
     "cales_solver_gaussel_z": (C.c_int, [vp, c_int_p, vp, vp, vp, C.c_char_p, C.c_char_p, vp]),
     "cales_rk": (C.c_int, [vp, c_dbl_p, c_int_p, c_dbl_p, vp, vp, vp, vp, C.c_double, C.c_double, vp, c_int_p, c_dbl_p, c_dbl_p,
                            vp, vp, vp, vp, c_dbl_p]),

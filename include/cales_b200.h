@@ -107,6 +107,8 @@ int cales_fftend(cales_ctx* ctx, int plan);
  * lambdaxy, a, b, c: DEVICE.  p: haloed field, solved in place on its interior. */
 int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int plan, double normfft, const double* lambdaxy,
                  const double* a, const double* b, const double* c, const char bc[6], const char c_or_f[3], double* p);
+/* which exchange the last cales_solver call of this context used across ranks (diagnostic string; bench.py reports it) */
+const char* cales_solver_exchange(const cales_ctx* ctx);
 /* replaces solver_gaussel_z (src/solver.f90:182-233, src/solver_gpu.f90:374-477) */
 int cales_solver_gaussel_z(cales_ctx* ctx, const int n[3], const double* a, const double* b, const double* c,
                            const char bcz[2], const char c_or_f[3], double* p);

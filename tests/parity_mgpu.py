@@ -75,6 +75,7 @@ def case_vs_oracle(name, kw, dims, nsteps, rank, world, local, uid, arith=None, 
     for _ in range(nsteps):
         res = sim.step(icheck=1)
     out = {nm: gather_field(sim, nm, rank, world) for nm in ("u", "v", "w", "p", "visct")}
+    exch = sim.lib.cales_solver_exchange(sim.ctx).decode()
     rec = {"ok": True}
     if rank == 0:
         import oracle.param as op
@@ -96,7 +97,7 @@ def case_vs_oracle(name, kw, dims, nsteps, rank, world, local, uid, arith=None, 
             errs[nm] = float(np.abs(a - b).max() / max(vscale if nm in "uvw" else max(np.abs(b).max(), vscale ** 2) if nm == "p" else np.abs(b).max(), 1e-300))
         ok = all(v <= tol for v in errs.values()) and abs(res[1] - ro[1]) < 1e-11 and abs(sim.dt - o.dt) <= 1e-10 * o.dt
         rec = {"case": name + ":" + kw.get("sgstype", "smag") + (":impdiff_" + impdiff if impdiff else ""), "ng": list(deck.ng), "dims": list(dims),
-               "steps": nsteps, "errs": errs, "divmax": [res[1], ro[1]], "tol": tol, "ok": bool(ok)}
+               "steps": nsteps, "solver_exchange": exch, "errs": errs, "divmax": [res[1], ro[1]], "tol": tol, "ok": bool(ok)}
     sim.close()
     flag = torch.tensor([1 if rec["ok"] else 0], device="cuda")
     dist.broadcast(flag, 0)

@@ -46,12 +46,18 @@ def test_eight_gpus(case, prow, pcol):
     run(case, prow, pcol, 5, 29513)
 
 
-@pytest.mark.parametrize("case,prow,pcol,env", [("tgv_smag", 1, 2, {"CALES_SOLVER_PIPE": "1"}), ("channel_dsmag", 1, 2, {"CALES_SOLVER_PIPE": "1", "CALES_SOLVER_CHUNKS": "3"}),
-                                                ("channel_smag", 1, 2, {"CALES_SOLVER_PIPE": "0"}), ("duct_smag", 1, 2, {"CALES_HALO_FUSED": "0"}),
-                                                ("channel_dsmag", 1, 2, {"CALES_NO_P2P": "1"}), ("tgv_smag", 1, 2, {"CALES_B200_ARITH": "strict"})])
+@pytest.mark.parametrize("case,prow,pcol,env", [("tgv_smag", 1, 2, {"CALES_ZDIST": "0", "CALES_SOLVER_PIPE": "1"}),
+                                                ("channel_dsmag", 1, 2, {"CALES_ZDIST": "0", "CALES_SOLVER_PIPE": "1", "CALES_SOLVER_CHUNKS": "3"}),
+                                                ("channel_smag", 1, 2, {"CALES_ZDIST": "0", "CALES_SOLVER_PIPE": "0"}), ("tgv_smag", 1, 2, {"CALES_ZDIST": "0"}),
+                                                ("duct_smag", 1, 2, {"CALES_HALO_FUSED": "0"}),
+                                                ("channel_dsmag", 1, 2, {"CALES_NO_P2P": "1"}), ("tgv_smag", 1, 2, {"CALES_B200_ARITH": "strict"}),
+                                                ("tgv_smag", 1, 2, {"CALES_B200_ARITH": "strict", "CALES_ZDIST": "1"}),
+                                                ("channel_wm_smag", 1, 2, {"CALES_B200_ARITH": "strict", "CALES_ZDIST": "1"})])
 def test_two_gpus_exchange_variants(case, prow, pcol, env):
-    """every exchange mechanism on the same cases: copy-engine pipeline, kernel-fused transposes, separate-kernel halo
-    exchange, NCCL send/recv without peer memory, and the strict arithmetic build"""
+    """every exchange mechanism on the same cases: the distributed z solve is the product build's default wherever z is
+    decomposed (all other tests of this file); here the transposing paths it replaced (copy-engine pipeline, kernel-fused
+    transposes), the separate-kernel halo exchange, NCCL send/recv without peer memory, the strict arithmetic build (bit-exact
+    Thomas through the transposes) and the strict build with the distributed z solve forced on"""
     run(case, prow, pcol, 5, 29514, env=env)
 
 
