@@ -15,6 +15,7 @@
 //   * x-lines (contiguous): the phases that touch global memory use a second thread mapping (lanes ALONG the line,
 //     coalesced) and the shared buffer is XOR-swizzled so both mappings are conflict-free: same traffic as y-lines.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 
 enum { KB_PP = 0, KB_NN = 1, KB_DD = 2 };
@@ -182,26 +183,34 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
       x[e] = make_double2(a, b);
     }
   } else {
-    // ---- backward pre-stage: half spectrum (global) -> packed complex Z (shared)
+    // ---- backward pre-stage: half spectrum (global) -> packed complex Z (shared).  All 4 (E/2 + 1) operands of the thread are
+    // loaded before the first one is used (register-blocked, like the forward pass): the loads overlap instead of
+    // alternating with the combine arithmetic and the shared-memory stores (ncu r2o: long-scoreboard stall 9.9 per issue)
+    double rk[E / 2 + 1], rnk[E / 2 + 1], rmk[E / 2 + 1], rnmk[E / 2 + 1];
 #pragma unroll
     for (int b = 0; b <= E / 2; ++b) {
       const int k = tx + T * b, mk = M - k;
+      rk[b] = rnk[b] = rmk[b] = rnmk[b] = 0.;
       if (b == E / 2 && tx > 0) continue;          // k = M/2 belongs to tx = 0
-      double rk = 0., rnk = 0., rmk = 0., rnmk = 0.;   // R[k], R[n-k], R[mk], R[n-mk]
       const int snk = k > 0 ? n - k : 0, snmk = n - mk;
       if (on) {
 #define GI(s_) gl[(long)(dd ? n - 1 - (s_) : (s_)) * ies]
-        rk = GI(k); rnk = GI(snk); rmk = GI(mk); rnmk = GI(snmk);
+        rk[b] = GI(k); rnk[b] = GI(snk); rmk[b] = GI(mk); rnmk[b] = GI(snmk);
 #undef GI
       }
+    }
+#pragma unroll
+    for (int b = 0; b <= E / 2; ++b) {
+      const int k = tx + T * b, mk = M - k;
+      if (b == E / 2 && tx > 0) continue;
       double2 Xk, Xmk;
       if (!MK) {
-        Xk = make_double2(rk, (k > 0 && k < M) ? rnk : 0.);
-        Xmk = make_double2(rmk, (mk > 0 && mk < M) ? rnmk : 0.);
+        Xk = make_double2(rk[b], (k > 0 && k < M) ? rnk[b] : 0.);
+        Xmk = make_double2(rmk[b], (mk > 0 && mk < M) ? rnmk[b] : 0.);
       } else {
         const double2 hk = conj(__ldg(A.h4 + k)), hmk = conj(__ldg(A.h4 + mk));
-        Xk = mul(make_double2(rk, k > 0 ? -rnk : 0.), hk);
-        Xmk = mul(make_double2(rmk, -rnmk), hmk);
+        Xk = mul(make_double2(rk[b], k > 0 ? -rnk[b] : 0.), hk);
+        Xmk = mul(make_double2(rmk[b], -rnmk[b]), hmk);
       }
       const double2 Aa = add(Xk, conj(Xmk));
       const double2 Bb = mul(sub(Xk, conj(Xmk)), conj(__ldg(A.wn + k)));
@@ -335,13 +344,16 @@ static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int b
   return 1;
 }
 
+// points per thread for n = 128 / 256: 8 (three / three stages) or 16 (two stages: one shared-memory exchange less); CALES_FFT_E16
+static inline bool fftb_e16() { static const int v = getenv("CALES_FFT_E16") ? atoi(getenv("CALES_FFT_E16")) : 0; return v != 0; }
+
 template <int XD>
 static inline int fftb_dispatch(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward) {
   switch (n) {
     case 32: return fftb_launch<16, 8, XD>(ctx, A, kind, backward);
     case 64: return fftb_launch<32, 8, XD>(ctx, A, kind, backward);
-    case 128: return fftb_launch<64, 8, XD>(ctx, A, kind, backward);
-    case 256: return fftb_launch<128, 8, XD>(ctx, A, kind, backward);
+    case 128: return fftb_e16() ? fftb_launch<64, 16, XD>(ctx, A, kind, backward) : fftb_launch<64, 8, XD>(ctx, A, kind, backward);
+    case 256: return fftb_e16() ? fftb_launch<128, 16, XD>(ctx, A, kind, backward) : fftb_launch<128, 8, XD>(ctx, A, kind, backward);
     case 512: return fftb_launch<256, 16, XD>(ctx, A, kind, backward);
     case 1024: return fftb_launch<512, 16, XD>(ctx, A, kind, backward);
     default: return 0;
