@@ -163,8 +163,12 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
   double2 x[E];
   int pos[E];
 
+  double2* swn = sw + M;                      // split twiddles wn[0..M/2] of the pre-/post-stage
+  double2* sh4 = swn + (M / 2 + 1);           // Makhoul twiddles h4[0..M] (MK only)
   for (int q = tid; q < M; q += NT) sw[q] = __ldg(A.wm + q);
-  double** sbase = (double**)(sw + M);        // PEER: per-rank row bases for this CTA's (x-tile, z)
+  for (int q = tid; q <= M / 2; q += NT) swn[q] = __ldg(A.wn + q);
+  if (MK) for (int q = tid; q <= M; q += NT) sh4[q] = __ldg(A.h4 + q);
+  double** sbase = (double**)(sh4 + (M + 1)); // PEER: per-rank row bases for this CTA's (x-tile, z)
   if (PEER && tid < A.np)
     sbase[tid] = A.pbase[tid] + L0 + (long)A.nx * A.pny[tid] * (A.zoff + (int)blockIdx.y) - (long)A.nx * A.pys[tid];
 
@@ -199,6 +203,7 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
 #undef GI
       }
     }
+    __syncthreads();                               // twiddle tables staged (their loads overlapped the operand loads above)
 #pragma unroll
     for (int b = 0; b <= E / 2; ++b) {
       const int k = tx + T * b, mk = M - k;
@@ -208,12 +213,12 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
         Xk = make_double2(rk[b], (k > 0 && k < M) ? rnk[b] : 0.);
         Xmk = make_double2(rmk[b], (mk > 0 && mk < M) ? rnmk[b] : 0.);
       } else {
-        const double2 hk = conj(__ldg(A.h4 + k)), hmk = conj(__ldg(A.h4 + mk));
+        const double2 hk = conj(sh4[k]), hmk = conj(sh4[mk]);
         Xk = mul(make_double2(rk[b], k > 0 ? -rnk[b] : 0.), hk);
         Xmk = mul(make_double2(rmk[b], -rnmk[b]), hmk);
       }
       const double2 Aa = add(Xk, conj(Xmk));
-      const double2 Bb = mul(sub(Xk, conj(Xmk)), conj(__ldg(A.wn + k)));
+      const double2 Bb = mul(sub(Xk, conj(Xmk)), conj(swn[k]));
       S[SI(k, lx)] = make_double2(Aa.x - Bb.y, Aa.y + Bb.x);
       if (k > 0 && mk != k) S[SI(mk, lx)] = make_double2(Aa.x + Bb.y, -Aa.y + Bb.x);
     }
@@ -269,7 +274,7 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
       const double2 Ev = make_double2(0.5 * (Zk.x + Zmk.x), 0.5 * (Zk.y + Zmk.y));
       const double2 D = sub(Zk, Zmk);
       const double2 O = make_double2(0.5 * D.y, -0.5 * D.x);
-      const double2 Tw = mul(__ldg(A.wn + k), O);
+      const double2 Tw = mul(swn[k], O);
       const double2 Xk = add(Ev, Tw), Xmk = conj(sub(Ev, Tw));
       int i0, i1, i2, i3;            // output slots of the four reals (-1: none)
       double r0, r1, r2, r3;
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
         i2 = mk; r2 = Xmk.x;
         i3 = (mk > 0 && mk < M) ? n - mk : -1; r3 = Xmk.y;
       } else {
-        const double2 Yk = mul(__ldg(A.h4 + k), Xk), Ymk = mul(__ldg(A.h4 + mk), Xmk);
+        const double2 Yk = mul(sh4[k], Xk), Ymk = mul(sh4[mk], Xmk);
         r0 = 2. * Yk.x; r1 = -2. * Yk.y; r2 = 2. * Ymk.x; r3 = -2. * Ymk.y;
         if (!dd) { i0 = k; i1 = k > 0 ? n - k : -1; i2 = mk; i3 = n - mk; }
         else { i0 = n - 1 - k; i1 = k > 0 ? k - 1 : -1; i2 = n - 1 - mk; i3 = mk - 1; }
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
 
 template <int M, int E, int XD>
 static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int backward) {
-  const size_t sh = ((size_t)M * NLB + M) * sizeof(double2) + 8 * sizeof(double*);
+  const size_t sh = ((size_t)M * NLB + M + (M / 2 + 1) + (M + 1)) * sizeof(double2) + 8 * sizeof(double*);
   dim3 g(cdiv(A.nl1, NLB), A.nl2), b(NLB, M / E);
 #define FB_GO(INV_, MK_)                                                                                           \
   {                                                                                                                \

