@@ -37,6 +37,10 @@ struct FftTables {   // twiddle tables per transform length, device resident
   double2* h = nullptr;   // exp(-  pi i k / (2 n)),  k = 0..n-1   (Makhoul DCT twiddles)
 };
 
+// fillps + updt_rhs_b handed to the pressure solve instead of being run first (substep.cu -> solver.cu): haloed velocity arrays,
+// dzfi(0:n3+1), the rhsb planes and is_bound; the forward x pass of the solver computes its input from them where it can
+struct DivSrc { const double *u, *v, *w, *dzfi, *rbx, *rby, *rbz; double dti, dxi, dyi; int bnd[6]; };
+
 #define CALES_MAX_RANKS 64
 struct PeerBuf {              // a buffer every rank allocated and mapped into every other rank (CUDA IPC over NVLink)
   void* local = nullptr;
@@ -75,6 +79,7 @@ struct cales_ctx {
   int sgs_ave = 1, sgs_filter2d = 0;    // dsmag averaging geometry / test filter (cales_set_sgs_options)
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // copy streams of the pipelined solver exchange (solver.cu)
   cudaEvent_t side_ev[8] = {nullptr};   // [0..3] chunk ready (main -> side), [4..7] chunk pushed (side -> main)
+  const DivSrc* div_src = nullptr;      // set by cales_substep around cales_solver: right-hand side still to be formed (fused fillps)
   void* zdist = nullptr;                // tables of the distributed z solve (zdist.cu)
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;

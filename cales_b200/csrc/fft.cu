@@ -368,7 +368,10 @@ __global__ void __launch_bounds__(FT) r2r_lines_k(R2RArgs A, int LS) {
 }
 
 int k_fftb_pass(cales_ctx* ctx, int dir, int kind, int backward, int n, int nl1, int nl2, const double* in, long ies, long il1, long il2,
-                double* out, long oes, long ol1, long ol2, double scale, const FftTables* T);
+                double* out, long oes, long ol1, long ol2, double scale, const FftTables* T, const DivSrc* ds);
+bool k_fftb_supported(int n);
+int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
+               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale, const DivSrc* ds = nullptr);
 
 // ---- host side -------------------------------------------------------------------------------------------------------
 FftTables* k_tables(cales_ctx* ctx, int n) {
@@ -411,13 +414,15 @@ static int r2r_pass(cales_ctx* ctx, int dir, int kind, int n, int n1, int n2, in
 
 // dir 0: lines along x of an array with row pitch ps1 and plane pitch ps2 (elements); dir 1: along y.
 int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
-               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale) {
+               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale, const DivSrc* ds) {
   bool swap;
   const int kind = kind_of(bc, c_or_f, &swap);
   if (kind < 0)
     return cales_fail(ctx, CALES_ERR_INVALID, "no transform for BC '%c%c' (%c-centred): find_fft knows P/P, N/N, D/D, N/D, D/N", bc[0], bc[1], c_or_f);
   if (swap) backward = !backward;
   const int n = dir == 0 ? n1 : n2;
+  if (ds && (swap || kind >= K_C1 || !k_fftb_supported(n) || getenv("CALES_FFT_GENERIC")))
+    return cales_fail(ctx, CALES_ERR_INVALID, "fused fillps needs the register-blocked transform (caller must check k_fft_peer_capable)");
   if (kind >= K_C1) return r2r_pass(ctx, dir, kind, n, n1, n2, n3, in, ip1, ip2, out, op1, op2, scale);
   if (n < 2 || (n & 1)) return cales_fail(ctx, CALES_ERR_INVALID, "transform length %d: only even lengths are implemented", n);
   FftTables* T = k_tables(ctx, n);
@@ -427,8 +432,8 @@ int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backw
     static const bool old_only = getenv("CALES_FFT_GENERIC") != nullptr;
     if (!old_only) {
       int rc;
-      if (dir == 0) rc = k_fftb_pass(ctx, 0, kind, backward, n, n2, n3, in, 1, ip1, ip2, out, 1, op1, op2, scale, T);
-      else rc = k_fftb_pass(ctx, 1, kind, backward, n, n1, n3, in, ip1, 1, ip2, out, op1, 1, op2, scale, T);
+      if (dir == 0) rc = k_fftb_pass(ctx, 0, kind, backward, n, n2, n3, in, 1, ip1, ip2, out, 1, op1, op2, scale, T, ds);
+      else rc = k_fftb_pass(ctx, 1, kind, backward, n, n1, n3, in, ip1, 1, ip2, out, op1, 1, op2, scale, T, nullptr);
       if (rc < 0) return -rc;
       if (rc == 1) return CALES_OK;
     }

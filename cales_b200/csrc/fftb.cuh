@@ -32,7 +32,26 @@ struct FftBArgs {
   int np, zoff, nx;
   double* pbase[8];
   int pys[9], pny[8];
+  // fillps fused into the forward x pass (su != nullptr): the line element is not read from `in` but computed from the
+  // haloed velocity arrays with the strides il1, il2 of `in` -- fillps (src/fillps.f90:14-48) followed by updt_rhs_b
+  // (src/bound.f90:562-617; rb*: the rhsb planes, bnd: is_bound) -- so the right-hand side never makes a round trip to memory
+  const double *su, *sv, *sw, *sdzfi, *rbx, *rby, *rbz;
+  double dti, dtidxi, dtidyi;
+  int bnd[6], sn1, sn2, sn3;
 };
+
+// element i0 (0-based) of line (j, k) (1-based) of the pressure right-hand side; off = offset of the line's first element
+__device__ __forceinline__ double fftb_div_src(const FftBArgs& A, long off, int i0, int j, int k, double dzfi_k) {
+  const long c = off + i0;
+  double val = ((A.sw[c] - A.sw[c - A.il2]) * A.dti * dzfi_k + (A.sv[c] - A.sv[c - A.il1]) * A.dtidyi + (A.su[c] - A.su[c - 1]) * A.dtidxi);
+  if (A.bnd[0] && i0 == 0) val = val + A.rbx[(j - 1) + (long)A.sn2 * (k - 1)];
+  if (A.bnd[1] && i0 == A.sn1 - 1) val = val + A.rbx[(j - 1) + (long)A.sn2 * ((k - 1) + (long)A.sn3)];
+  if (A.bnd[2] && j == 1) val = val + A.rby[i0 + (long)A.sn1 * (k - 1)];
+  if (A.bnd[3] && j == A.sn2) val = val + A.rby[i0 + (long)A.sn1 * ((k - 1) + (long)A.sn3)];
+  if (A.bnd[4] && k == 1) val = val + A.rbz[i0 + (long)A.sn1 * (j - 1)];
+  if (A.bnd[5] && k == A.sn3) val = val + A.rbz[i0 + (long)A.sn1 * ((j - 1) + (long)A.sn2)];
+  return val;
+}
 
 #define NLB 16
 
@@ -143,7 +162,7 @@ template <int MK> __device__ __forceinline__ int slot_of(int e, int n) {       /
 // forward stage, forward post-stage, backward pre-stage, last backward stage).  For y-lines the two coincide (the NL
 // lines are NL consecutive x, so lanes across lines ARE coalesced); for x-lines lanes run along the line (tx fastest)
 // so that global accesses are coalesced, and the shared buffer is XOR-swizzled so that both mappings are conflict-free.
-template <int M, int E, int XD, bool INV, int MK, bool PEER = false>
+template <int M, int E, int XD, bool INV, int MK, bool PEER = false, bool DIVSRC = false>
 __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
   using namespace fb;
   extern __shared__ double2 S[];
@@ -182,7 +201,14 @@ __global__ void __launch_bounds__(NLB*(M / E)) fftb_k(FftBArgs A) {
       else if (e < E / 2) { e0 = 4 * c; e1 = 4 * c + 2; }               // c < M/2  <=>  e < E/2
       else { e0 = 2 * n - 1 - 4 * c; e1 = 2 * n - 3 - 4 * c; }
       double a = 0., b = 0.;
-      if (on) { a = gl[(long)e0 * ies]; b = gl[(long)e1 * ies]; }
+      if (DIVSRC) {
+        if (on) {
+          const long off = (long)blockIdx.y * A.il2 + (long)(L0 + lx) * A.il1;
+          const int jj = L0 + lx + 1, kk = (int)blockIdx.y + 1;
+          const double dzk = __ldg(A.sdzfi + kk);
+          a = fftb_div_src(A, off, e0, jj, kk, dzk); b = fftb_div_src(A, off, e1, jj, kk, dzk);
+        }
+      } else if (on) { a = gl[(long)e0 * ies]; b = gl[(long)e1 * ies]; }
       if (MK && e >= E / 2 && dd) { a = -a; b = -b; }                  // odd line elements change sign for the DST
       x[e] = make_double2(a, b);
     }
@@ -341,6 +367,17 @@ static inline int fftb_launch(cales_ctx* ctx, const FftBArgs& A, int kind, int b
   }
     if (mk) FB_GOP(1) else FB_GOP(0)
 #undef FB_GOP
+  } else if (XD == 1 && A.su && !backward) {
+    if constexpr (XD == 1) {
+#define FB_GOD(MK_)                                                                                                \
+  {                                                                                                                \
+    static bool attr = false;                                                                                      \
+    if (!attr) { attr = true; cudaFuncSetAttribute(fftb_k<M, E, 1, false, MK_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); } \
+    fftb_k<M, E, 1, false, MK_, false, true><<<g, b, sh, ctx->stream>>>(A);                                         \
+  }
+      if (mk) FB_GOD(1) else FB_GOD(0)
+#undef FB_GOD
+    }
   } else if (!backward) { if (mk) FB_GO(false, 1) else FB_GO(false, 0) }
   else { if (mk) FB_GO(true, 1) else FB_GO(true, 0) }
 #undef FB_GO

@@ -15,7 +15,7 @@
 #include "common.cuh"
 
 int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backward, int n1, int n2, int n3,
-               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale);
+               const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale, const DivSrc* ds = nullptr);
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 int k_transpose_p2p(cales_ctx* ctx, int which, const double* src, PeerBuf* dst);
 struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };
@@ -365,12 +365,37 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
   const int q = (c_or_f[2] == 'f' && bcz[1] == 'D') ? 1 : 0;
   const bool zper = bcz[0] == 'P' && bcz[1] == 'P';
   int rc;
+  // Right-hand side still to be formed (cales_substep hands fillps + updt_rhs_b over): the forward x pass computes it on the
+  // fly where the register-blocked transform runs on whole planes (one rank; distributed z solve) -- 32 instead of 48 B/cell
+  // for fillps + pass, one launch less; everywhere else the two kernels run here first.  CALES_FUSE_FILLPS=0 always splits.
+  const DivSrc* ds_in = ctx->div_src;
+  ctx->div_src = nullptr;
+  DivSrc dsv;
+  const DivSrc* ds = nullptr;
+  if (ds_in) {
+    static const int fuse_env = getenv("CALES_FUSE_FILLPS") ? atoi(getenv("CALES_FUSE_FILLPS")) : 1;
+    dsv = *ds_in;
+    const long o111 = d.idx(1, 1, 1);
+    dsv.u += o111; dsv.v += o111; dsv.w += o111;
+    // measured at 256^3 on one GPU: step 3.635 -> 3.619 ms (the forward x pass is bound by its load/shared-memory pipe, so
+    // most of the 16 B/cell saved comes back as extra load instructions).  On by default on one rank, where the fused
+    // step is held to the per-procedure sequence by the tests; across ranks only with CALES_FUSE_FILLPS=2.
+    if (fuse_env && (ctx->nranks == 1 || fuse_env == 2) && k_fft_peer_capable(pl.bc[0], pl.c_or_f[0], n[0])) ds = &dsv;
+  }
+  auto form_rhs = [&]() -> int {                            // the unfused pair, for the paths that do not take `ds`
+    if (!ds_in) return CALES_OK;
+    const double dli_[3] = {ds_in->dxi, ds_in->dyi, 0.};
+    int r_;
+    if ((r_ = cales_fillps(ctx, n, dli_, ds_in->dzfi, ds_in->dti, ds_in->u, ds_in->v, ds_in->w, p))) return r_;
+    return cales_updt_rhs_b(ctx, "ccc", bc, n, ds_in->bnd, ds_in->rbx, ds_in->rby, ds_in->rbz, p);
+  };
   if (ctx->nranks == 1) {
+    if (!ds && (rc = form_rhs())) return rc;
     const long p1 = n[0], p2 = (long)n[0] * n[1];
     double* wk = (double*)cales_scratch(ctx, "solver_wk", (size_t)p2 * n[2] * sizeof(double));
     if (!wk) return CALES_ERR_NOMEM;
     // fwd x: haloed p -> wk ; fwd y in place ; z solve ; bwd y ; bwd x: wk -> haloed p * normfft
-    if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, n[0], n[1], n[2], p + d.idx(1, 1, 1), d.s1, d.s2, wk, p1, p2, 1.0))) return rc;
+    if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, n[0], n[1], n[2], p + d.idx(1, 1, 1), d.s1, d.s2, wk, p1, p2, 1.0, ds))) return rc;
     if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, n[0], n[1], n[2], wk, p1, p2, wk, p1, p2, 1.0))) return rc;
     if ((rc = k_gaussel(ctx, n[0], n[1], n[2] - q, p2, zper, a, b, c, lambdaxy, wk))) return rc;
     if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 1, n[0], n[1], n[2], wk, p1, p2, wk, p1, p2, 1.0))) return rc;
@@ -418,7 +443,8 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
         PeerBuf *pcur = pb0, *poth = pb1;
         const bool xy = ctx->dims[0] > 1;
         const long ypl = (long)ys[0] * ys[1];
-        if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, cur, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;
+        if (!ds && (rc = form_rhs())) return rc;
+        if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, cur, xs[0], (long)xs[0] * xs[1], 1.0, ds))) return rc;
         if (xy) { if ((rc = k_transpose_p2p(ctx, 0, cur, poth))) return rc; std::swap(cur, oth); std::swap(pcur, poth); }
         if ((rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], cur, ys[0], ypl, cur, ys[0], ypl, 1.0))) return rc;
         if ((rc = k_zdist_solve(ctx, plan, lambdaxy, a, b, c, cur))) return rc;
@@ -428,6 +454,7 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
       }
     }
   }
+  if ((rc = form_rhs())) return rc;                         // the transposing paths below read their right-hand side from p
   // ---- pipelined exchange (default with peer memory): the y <-> z transposes are done by the COPY ENGINES, chunk by chunk,
   // while the SMs work on the next chunk.  y -> z: the local z range is cut into chunks; as soon as the x and y transforms of
   // a chunk are done, one strided 2-D DMA per peer pushes its [all x, y of that peer, chunk] box straight into the peer's

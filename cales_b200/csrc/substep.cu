@@ -44,9 +44,18 @@ extern "C" int cales_substep(cales_ctx* ctx, const cales_step_args* a, int irk, 
   // main.f90:493-497
   if ((rc = cales_bounduvw(ctx, a->cbcvel, n, &a->bcu, &a->bcv, &a->bcw, &a->bcu_mag, &a->bcv_mag, &a->bcw_mag, a->nb, a->is_bound, a->lwm, a->l, a->dl,
                            a->zc, a->zf, a->dzc, a->dzf, a->visc, a->hwm, a->index_wm, 1, 0, us, vs, ws))) return rc;
-  if ((rc = cales_fillps(ctx, n, a->dli, a->dzfi, dtrki, us, vs, ws, a->pp))) return rc;
-  if ((rc = cales_updt_rhs_b(ctx, "ccc", a->cbcpre, n, a->is_bound, a->rhsbx, a->rhsby, a->rhsbz, a->pp))) return rc;
-  if ((rc = cales_solver(ctx, n, a->ng, a->plan, a->normfft, a->lambdaxy, a->a, a->b, a->c, a->cbcpre, "ccc", a->pp))) return rc;
+  // fillps + updt_rhs_b + solver (main.f90:495-497): the first two are handed to the solver, whose forward x pass forms the
+  // right-hand side on the fly where it can (solver.cu) and runs the two kernels itself where it cannot
+  {
+    DivSrc S;
+    S.u = us; S.v = vs; S.w = ws; S.dzfi = a->dzfi; S.rbx = a->rhsbx; S.rby = a->rhsby; S.rbz = a->rhsbz;
+    S.dti = dtrki; S.dxi = a->dli[0]; S.dyi = a->dli[1];
+    for (int q6 = 0; q6 < 6; ++q6) S.bnd[q6] = a->is_bound[q6];
+    ctx->div_src = &S;
+    rc = cales_solver(ctx, n, a->ng, a->plan, a->normfft, a->lambdaxy, a->a, a->b, a->c, a->cbcpre, "ccc", a->pp);
+    ctx->div_src = nullptr;
+    if (rc) return rc;
+  }
   // main.f90:498-503
   if ((rc = cales_boundp(ctx, a->cbcpre, n, &a->bcp, a->nb, a->is_bound, a->dl, a->dzc, a->pp))) return rc;
   if ((rc = k_correc_updatep(ctx, n, a->dli, a->dzci, dtrk, a->pp, us, vs, ws, a->u, a->v, a->w, a->p))) return rc;

@@ -150,11 +150,30 @@ __global__ void __launch_bounds__(256) zd_reduce_k(int nxy, int U, const double*
   XP[col] = xp; XP[nxy + col] = xn;
 }
 
+// The spikes v, w decay geometrically away from the block ends (ratio rho, rho + 1/rho = 2 + |lambda| dz^2), so for all but the
+// lowest modes they are below any round-off a few dozen levels in.  The correction pass works on boxes of ZD_CT columns x
+// ZD_LZ levels; a box whose largest |v|, |w| is below ZD_TINY leaves y unchanged (the dropped term is < 1e-30 of the
+// interface values) and is skipped altogether -- no loads, no stores.  mask: one byte per box, built with the tables.
 #define ZD_LZ 8
+#define ZD_CT 64
+#define ZD_TINY 1e-30
+__global__ void __launch_bounds__(ZD_CT) zd_mask_k(int nxy, int m, const double* __restrict__ V, const double* __restrict__ W, unsigned char* __restrict__ mask) {
+  const int col = blockIdx.x * ZD_CT + threadIdx.x, l0 = blockIdx.y * ZD_LZ;
+  bool act = false;
+  if (col < nxy)
+    for (int q = 0; q < ZD_LZ && l0 + q < m; ++q) {
+      const long o = (long)(l0 + q) * nxy + col;
+      act = act || !(fabs(V[o]) < ZD_TINY) || !(fabs(W[o]) < ZD_TINY);      // NaN counts as active
+    }
+  const int any = __syncthreads_or(act ? 1 : 0);
+  if (threadIdx.x == 0) mask[(long)blockIdx.y * gridDim.x + blockIdx.x] = any ? 1 : 0;
+}
+
 template <int VEC>
-__global__ void __launch_bounds__(256) zd_correct_k(int nxy, int m, const double* __restrict__ V, const double* __restrict__ W,
-                                                     const double* __restrict__ XP, double* __restrict__ w) {
-  const int c0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+__global__ void __launch_bounds__(ZD_CT / VEC) zd_correct_k(int nxy, int m, const double* __restrict__ V, const double* __restrict__ W,
+                                                             const double* __restrict__ XP, const unsigned char* __restrict__ mask, double* __restrict__ w) {
+  if (!mask[(long)blockIdx.y * gridDim.x + blockIdx.x]) return;
+  const int c0 = blockIdx.x * ZD_CT + threadIdx.x * VEC;
   if (c0 >= nxy) return;
   const int l0 = blockIdx.y * ZD_LZ;
   if (VEC == 2) {
@@ -207,6 +226,7 @@ struct ZdTab {
   ZdGeom g;
   int nlam = 0;                                        // size of the caller's Z-pencil lambda slice
   double *lamY = nullptr, *aG = nullptr, *bG = nullptr, *cG = nullptr, *lamZ = nullptr, *V = nullptr, *W = nullptr, *G = nullptr, *XP = nullptr;
+  unsigned char* mask = nullptr;                       // [levels / ZD_LZ][columns / ZD_CT] boxes of the correction pass that do anything
   unsigned long long seq = 0;                          // solves so far (parity of the gather buffer)
 };
 struct ZdState { std::vector<ZdTab> tabs; int* hostflag = nullptr; int* devflag = nullptr; };
@@ -226,7 +246,7 @@ static ZdState* zd_state(cales_ctx* ctx) {
 void k_zdist_free(cales_ctx* ctx) {
   ZdState* st = (ZdState*)ctx->zdist;
   if (!st) return;
-  for (auto& t : st->tabs) { cudaFree(t.lamY); cudaFree(t.aG); cudaFree(t.lamZ); cudaFree(t.V); cudaFree(t.W); cudaFree(t.G); cudaFree(t.XP); }
+  for (auto& t : st->tabs) { cudaFree(t.lamY); cudaFree(t.aG); cudaFree(t.lamZ); cudaFree(t.V); cudaFree(t.W); cudaFree(t.G); cudaFree(t.XP); cudaFree(t.mask); }
   if (st->hostflag) cudaFreeHost(st->hostflag);
   delete st;
   ctx->zdist = nullptr;
@@ -235,6 +255,9 @@ void k_zdist_free(cales_ctx* ctx) {
 static int zd_launch_build(cales_ctx* ctx, const ZdTab& t) {
   zd_build_k<<<cdiv(t.g.nxy, 64), 64, 0, ctx->stream>>>(t.g, t.aG, t.bG, t.cG, t.lamY, t.V, t.W, t.G);
   KERNEL_CHECK(ctx);
+  const int m = t.g.zs[t.g.me + 1] - t.g.zs[t.g.me];
+  zd_mask_k<<<dim3(cdiv(t.g.nxy, ZD_CT), cdiv(m, ZD_LZ)), ZD_CT, 0, ctx->stream>>>(t.g.nxy, m, t.V, t.W, t.mask);
+  KERNEL_CHECK(ctx);
   return CALES_OK;
 }
 
@@ -242,7 +265,8 @@ static int zd_alloc(cales_ctx* ctx, ZdTab& t, int m) {
   const size_t nxy = t.g.nxy, n = t.g.n, U = 2 * t.g.P;
   bool ok = cudaMalloc(&t.lamY, nxy * sizeof(double)) == cudaSuccess && cudaMalloc(&t.aG, 3 * n * sizeof(double)) == cudaSuccess &&
             cudaMalloc(&t.V, nxy * m * sizeof(double)) == cudaSuccess && cudaMalloc(&t.W, nxy * m * sizeof(double)) == cudaSuccess &&
-            cudaMalloc(&t.G, 2 * U * nxy * sizeof(double)) == cudaSuccess && cudaMalloc(&t.XP, 2 * nxy * sizeof(double)) == cudaSuccess;
+            cudaMalloc(&t.G, 2 * U * nxy * sizeof(double)) == cudaSuccess && cudaMalloc(&t.XP, 2 * nxy * sizeof(double)) == cudaSuccess &&
+            cudaMalloc(&t.mask, (size_t)cdiv(nxy, ZD_CT) * cdiv(m, ZD_LZ)) == cudaSuccess;
   if (!ok) return cales_fail(ctx, CALES_ERR_NOMEM, "distributed z solve: tables (%zu bytes) could not be allocated", (2 * m + 2 * U + 3) * nxy * sizeof(double));
   t.bG = t.aG + n; t.cG = t.bG + n;
   return CALES_OK;
@@ -263,8 +287,9 @@ static int zd_finish(cales_ctx* ctx, const ZdTab& t, const double* gather, doubl
   const int m = t.g.zs[t.g.me + 1] - t.g.zs[t.g.me], nxy = t.g.nxy;
   zd_reduce_k<<<cdiv(nxy, 256), 256, 0, ctx->stream>>>(nxy, 2 * t.g.P, t.G, gather, t.XP);
   KERNEL_CHECK(ctx);
-  if (nxy % 2 == 0 && ((uintptr_t)w & 15) == 0) zd_correct_k<2><<<dim3(cdiv(nxy / 2, 256), cdiv(m, ZD_LZ)), 256, 0, ctx->stream>>>(nxy, m, t.V, t.W, t.XP, w);
-  else zd_correct_k<1><<<dim3(cdiv(nxy, 256), cdiv(m, ZD_LZ)), 256, 0, ctx->stream>>>(nxy, m, t.V, t.W, t.XP, w);
+  const dim3 gc(cdiv(nxy, ZD_CT), cdiv(m, ZD_LZ));
+  if (nxy % 2 == 0 && ((uintptr_t)w & 15) == 0) zd_correct_k<2><<<gc, ZD_CT / 2, 0, ctx->stream>>>(nxy, m, t.V, t.W, t.XP, t.mask, w);
+  else zd_correct_k<1><<<gc, ZD_CT, 0, ctx->stream>>>(nxy, m, t.V, t.W, t.XP, t.mask, w);
   KERNEL_CHECK(ctx);
   return CALES_OK;
 }
@@ -401,6 +426,6 @@ extern "C" int cales_zdist_emulate(cales_ctx* ctx, int nx, int ny, int n, int P,
   }
   for (int s = 0; s < P && !rc; ++s) rc = zd_finish(ctx, tabs[s], gather, p + (size_t)(zst[s] - 1) * nxy);
   cudaStreamSynchronize(ctx->stream);
-  for (auto& t : tabs) { cudaFree(t.lamY); cudaFree(t.aG); cudaFree(t.V); cudaFree(t.W); cudaFree(t.G); cudaFree(t.XP); }
+  for (auto& t : tabs) { cudaFree(t.lamY); cudaFree(t.aG); cudaFree(t.V); cudaFree(t.W); cudaFree(t.G); cudaFree(t.XP); cudaFree(t.mask); }
   return rc;
 }
