@@ -41,6 +41,11 @@ struct FftTables {   // twiddle tables per transform length, device resident
 // dzfi(0:n3+1), the rhsb planes and is_bound; the forward x pass of the solver computes its input from them where it can
 struct DivSrc { const double *u, *v, *w, *dzfi, *rbx, *rby, *rbz; double dti, dxi, dyi; int bnd[6]; };
 
+// destinations of the kernel-fused transposes of the distributed solver (solver.cu sets them on the context around the
+// producing kernel; fftb_y.cu / gaussel_tab.cu consume them)
+struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };   // forward y pass -> peers' Z-pencils
+struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };        // z solve -> peers' Y-pencils: pbase[r] + (col + coff) + plane (l - pzs[r])
+
 #define CALES_MAX_RANKS 64
 struct PeerBuf {              // a buffer every rank allocated and mapped into every other rank (CUDA IPC over NVLink)
   void* local = nullptr;
@@ -80,6 +85,9 @@ struct cales_ctx {
   cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};   // copy streams of the pipelined solver exchange (solver.cu)
   cudaEvent_t side_ev[8] = {nullptr};   // [0..3] chunk ready (main -> side), [4..7] chunk pushed (side -> main)
   const DivSrc* div_src = nullptr;      // set by cales_substep around cales_solver: right-hand side still to be formed (fused fillps)
+  const FftPeerOut* fft_peer_out = nullptr;   // per-context (two contexts / host threads in one process do not interfere)
+  const GPeer* gauss_peer_out = nullptr;
+  void* gauss_state = nullptr;          // pivot tables of the tridiagonal solves (gaussel_tab.cu)
   void* zdist = nullptr;                // tables of the distributed z solve (zdist.cu)
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;

@@ -9,8 +9,6 @@ int k_fftb_y(cales_ctx* ctx, int n, const FftBArgs& A, int kind, int backward) {
 bool k_fftb_supported(int n) { return n >= 32 && n <= 1024 && !(n & (n - 1)) && getenv("CALES_FFT_GENERIC") == nullptr; }
 
 // returns 1 if handled, 0 if this length is not covered by the fast path (caller falls back), <0 on error
-struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };
-const FftPeerOut* g_fft_peer_out = nullptr;    // set by the distributed solver around the forward y pass (solver.cu)
 
 // ds (forward x pass only): the line elements are computed from the velocity arrays (fused fillps, see FftBArgs); `in` then
 // only defines the strides and ds->u/v/w point at element (1,1,1) like `in` would
@@ -32,8 +30,8 @@ int k_fftb_pass(cales_ctx* ctx, int dir, int kind, int backward, int n, int nl1,
     for (int q = 0; q < 6; ++q) A.bnd[q] = ds->bnd[q] && (q < 2 ? ds->rbx : q < 4 ? ds->rby : ds->rbz) != nullptr;
     A.sn1 = n; A.sn2 = nl1; A.sn3 = nl2;
   }
-  if (g_fft_peer_out && dir == 1 && !backward) {
-    const FftPeerOut& P = *g_fft_peer_out;
+  if (ctx->fft_peer_out && dir == 1 && !backward) {
+    const FftPeerOut& P = *ctx->fft_peer_out;
     A.np = P.np; A.zoff = P.zoff; A.nx = P.nx;
     for (int q = 0; q < P.np; ++q) { A.pbase[q] = P.pbase[q]; A.pys[q] = P.pys[q]; A.pny[q] = P.pny[q]; }
     A.pys[P.np] = P.pys[P.np];

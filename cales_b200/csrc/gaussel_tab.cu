@@ -45,8 +45,12 @@ struct GaussTab {
   double *MW = nullptr, *MDF = nullptr, *MDB = nullptr; // [nxy] meeting row: 1/(1 - db df), df(s-1), db(s)
 };
 
-static std::map<cales_ctx*, std::vector<GaussTab>> g_tabs;
-static long g_use = 0;
+// per context (cales_ctx::gauss_state): the tables, their LRU clock and the validation generation
+struct GaussState { std::vector<GaussTab> tabs; long use = 0; unsigned gen = 0; };
+static GaussState* gauss_state(cales_ctx* ctx) {
+  if (!ctx->gauss_state) ctx->gauss_state = new GaussState();
+  return (GaussState*)ctx->gauss_state;
+}
 
 __device__ __forceinline__ void cp8(double* dst_smem, const double* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -122,8 +126,7 @@ __device__ __forceinline__ void g_issue(double* dst, const double* src, long str
 
 // Peer-fused z -> y transpose: the solution of level l (global z) of my columns goes straight into the Y-pencil of the
 // rank that owns z = l: pbase[r] + (col + coff) + plane (l - pzs[r]).
-struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };
-const GPeer* g_gauss_peer_out = nullptr;       // set by the distributed solver around the z solve (solver.cu)
+// (GPeer: common.cuh; set on the context by the distributed solver around the z solve, solver.cu)
 
 template <int PER, bool SP, int GNG, bool PEER>
 __global__ void __launch_bounds__(GC) gauss_solve_k(int nxy, int n, int spill, long sz, const double* __restrict__ a, const double* __restrict__ c,
@@ -713,7 +716,7 @@ static bool make_tmap(CUtensorMap* tm, const double* base, int cols, int rows, l
 }
 
 static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const double* a, const double* b, const double* c, const double* lam, int twoway) {
-  std::vector<GaussTab>& v = g_tabs[ctx];
+  std::vector<GaussTab>& v = gauss_state(ctx)->tabs;
   for (auto& t : v)
     if (t.nxy == nxy && t.n == n && t.periodic == periodic && t.twoway == twoway && t.key[0] == a && t.key[1] == b && t.key[2] == c && t.key[3] == lam) return &t;
   GaussTab* t = nullptr;
@@ -748,10 +751,11 @@ static GaussTab* find_tab(cales_ctx* ctx, int nxy, int n, int periodic, const do
 }
 
 void k_gaussel_tab_free(cales_ctx* ctx) {
-  auto it = g_tabs.find(ctx);
-  if (it == g_tabs.end()) return;
-  for (auto& t : it->second) { cudaFree(t.Z); cudaFree(t.P2); cudaFree(t.DEN); cudaFree(t.ca); cudaFree(t.clam); cudaFree(t.flag); cudaFree(t.MW); }
-  g_tabs.erase(it);
+  GaussState* gs = (GaussState*)ctx->gauss_state;
+  if (!gs) return;
+  for (auto& t : gs->tabs) { cudaFree(t.Z); cudaFree(t.P2); cudaFree(t.DEN); cudaFree(t.ca); cudaFree(t.clam); cudaFree(t.flag); cudaFree(t.MW); }
+  delete gs;
+  ctx->gauss_state = nullptr;
 }
 
 // Would k_gaussel_tab run the TMA kernel for this problem?  The distributed solver fuses the z -> y transpose into the z
@@ -775,7 +779,7 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   const int nxy = nx * ny;
   const int nlev = periodic ? n - 1 : n;
   if (nlev < 1) return 0;
-  const bool peer = g_gauss_peer_out != nullptr;
+  const bool peer = ctx->gauss_peer_out != nullptr;
   // contraction build: the two-way kernel (gauss2_k) whenever the solution stays on this rank, the column has at least two
   // level groups and its block fits in shared memory; CALES_GAUSS_TWOWAY=0 keeps the one-warp Thomas kernel
   int twoway = 0, cw2 = 16, tng2 = 3;
@@ -798,9 +802,9 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
 #endif
   GaussTab* t = find_tab(ctx, nxy, n, periodic, a, b, c, lambdaxy, twoway);
   if (!t) return -CALES_ERR_NOMEM;
-  t->last_use = ++g_use;
-  static unsigned gen = 0;
-  ++gen;
+  GaussState* gs = gauss_state(ctx);
+  t->last_use = ++gs->use;
+  const unsigned gen = ++gs->gen;
   const long tot = 3L * n + nxy;
   gauss_validate_k<<<(int)std::min<long>((tot + 255) / 256, 592), 256, 0, ctx->stream>>>(n, nxy, a, b, c, lambdaxy, t->ca, t->cb, t->cc, t->clam, t->flag, gen);
   ctx->launches++;
@@ -846,7 +850,7 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
     memset(&PO, 0, sizeof PO);
     bool peer_ok = true;
     if (peer) {                    // destination pencils: base + coff, rows = levels of that rank, row stride = Y-pencil plane
-      const GPeer& GPr = *g_gauss_peer_out;
+      const GPeer& GPr = *ctx->gauss_peer_out;
       peer_ok = GPr.np <= 8 && GPr.plane % 2 == 0 && GPr.coff % 2 == 0 && GPr.pzs[GPr.np] == n && nxy % cw == 0;
       PO.np = GPr.np;
       for (int r = 0; r <= GPr.np && peer_ok; ++r) PO.zs[r] = GPr.pzs[r];
@@ -891,7 +895,7 @@ int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, 
   const dim3 g(cdiv(nxy, GC));
   GPeer G;
   memset(&G, 0, sizeof G);
-  if (peer) G = *g_gauss_peer_out;
+  if (peer) G = *ctx->gauss_peer_out;
 #define GS_GO(PER_, SP_, NG_)                                                                                         \
   {                                                                                                                   \
     static bool attr = false;                                                                                         \

@@ -18,10 +18,6 @@ int k_fft_pass(cales_ctx* ctx, int dir, const char bc[2], char c_or_f, int backw
                const double* in, long ip1, long ip2, double* out, long op1, long op2, double scale, const DivSrc* ds = nullptr);
 int k_transpose(cales_ctx* ctx, int which, const double* src, double* dst);
 int k_transpose_p2p(cales_ctx* ctx, int which, const double* src, PeerBuf* dst);
-struct FftPeerOut { int np, zoff, nx; double* pbase[8]; int pys[9], pny[8]; };
-extern const FftPeerOut* g_fft_peer_out;
-struct GPeer { int np; long plane, coff; double* pbase[8]; int pzs[9]; };
-extern const GPeer* g_gauss_peer_out;
 bool k_fft_peer_capable(const char bc[2], char c_or_f, int n);
 bool k_gauss_tma_fits(int nxy, int n, int periodic);
 int k_gaussel_tab(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, const double* a, const double* b, const double* c,
@@ -235,7 +231,7 @@ int k_gaussel(cales_ctx* ctx, int nx, int ny, int n, long sz, int periodic, cons
       if (rc == 1) return CALES_OK;
     }
   }
-  if (g_gauss_peer_out) return cales_fail(ctx, CALES_ERR_INVALID, "peer-fused z solve requested but the cached-pivot kernel is unavailable");
+  if (ctx->gauss_peer_out) return cales_fail(ctx, CALES_ERR_INVALID, "peer-fused z solve requested but the cached-pivot kernel is unavailable");
   const int ntile = ((periodic ? n - 1 : n) + TZ - 1) / TZ;
   const size_t sh = ((size_t)ntile * GT * (periodic ? 2 : 1) + (size_t)n * (periodic ? 4 : 3)) * sizeof(double);
   if (sh > 200 * 1024) return cales_fail(ctx, CALES_ERR_INVALID, "tridiagonal system of %d points exceeds the checkpoint buffer", n);
@@ -581,9 +577,9 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
     // of gauss_tma_k; only when every level is solved, i.e. not for the shortened face-centred Dirichlet system)
     static const int fmask = getenv("CALES_FUSE_MASK") ? atoi(getenv("CALES_FUSE_MASK")) : 3;
     if (fmask & 1) {
-      g_fft_peer_out = &FP;
+      ctx->fft_peer_out = &FP;
       rc = k_fft_pass(ctx, 1, pl.bc[1], pl.c_or_f[1], 0, ys[0], ys[1], ys[2], w0, ys[0], (long)ys[0] * ys[1], w1, ys[0], (long)ys[0] * ys[1], 1.0);
-      g_fft_peer_out = nullptr;
+      ctx->fft_peer_out = nullptr;
       if (rc) return rc;
       if ((rc = k_barrier(ctx))) return rc;
     } else {
@@ -591,9 +587,9 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
       if ((rc = k_transpose_p2p(ctx, 1, w0, pb1))) return rc;
     }
     if ((fmask & 2) && q == 0 && k_gauss_tma_fits(zs[0] * zs[1], zs[2], zper)) {
-      g_gauss_peer_out = &GP;
+      ctx->gauss_peer_out = &GP;
       rc = k_gaussel(ctx, zs[0], zs[1], zs[2] - q, (long)zs[0] * zs[1], zper, a, b, c, lambdaxy, w1);
-      g_gauss_peer_out = nullptr;
+      ctx->gauss_peer_out = nullptr;
       if (rc) return rc;
       if ((rc = k_barrier(ctx))) return rc;
     } else {
