@@ -89,6 +89,7 @@ struct cales_ctx {
   const GPeer* gauss_peer_out = nullptr;
   void* gauss_state = nullptr;          // pivot tables of the tridiagonal solves (gaussel_tab.cu)
   void* zdist = nullptr;                // tables of the distributed z solve (zdist.cu)
+  void* step_graphs = nullptr;          // captured time steps of cales_step (substep.cu)
   long step_calls = 0;                  // cales_step calls so far (the first ones run eagerly: lazy allocations)
   std::vector<Plan> plans;
   std::map<int, FftTables> tables;

@@ -566,10 +566,10 @@ extern "C" int cales_solver(cales_ctx* ctx, const int n[3], const int ng[3], int
     ctx->solver_path = 3;
     FP.np = GP.np = P; FP.nx = ys[0]; FP.zoff = zst[me] - 1;
     GP.plane = (long)ys[0] * ys[1]; GP.coff = (long)ys[0] * (yst[me] - 1);
-    for (int q = 0; q < P; ++q) {
-      const int r = ctx->coord[0] * ctx->dims[1] + q;
-      FP.pbase[q] = (double*)pb1->ptr[r]; FP.pys[q] = yst[q] - 1; FP.pny[q] = ysz[q];
-      GP.pbase[q] = (double*)pb0->ptr[r]; GP.pzs[q] = zst[q] - 1;
+    for (int pr = 0; pr < P; ++pr) {
+      const int r = ctx->coord[0] * ctx->dims[1] + pr;
+      FP.pbase[pr] = (double*)pb1->ptr[r]; FP.pys[pr] = yst[pr] - 1; FP.pny[pr] = ysz[pr];
+      GP.pbase[pr] = (double*)pb0->ptr[r]; GP.pzs[pr] = zst[pr] - 1;
     }
     FP.pys[P] = ctx->ng[1]; GP.pzs[P] = ctx->ng[2];
     if ((rc = k_fft_pass(ctx, 0, pl.bc[0], pl.c_or_f[0], 0, xs[0], xs[1], xs[2], p + d.idx(1, 1, 1), d.s1, d.s2, w0, xs[0], (long)xs[0] * xs[1], 1.0))) return rc;

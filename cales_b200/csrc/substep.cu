@@ -83,7 +83,11 @@ extern "C" int cales_step_args_layout(long out[4]) {
 // every substep, hence every step) and on the argument block; graphs are cached under that key.  The first two steps of a
 // context run eagerly (lazy scratch allocations are not capturable); afterwards a new key is captured and launched at once.  Single rank only: the peer-memory barrier and halo kernels carry sequence numbers as arguments.
 struct StepGraph { double dt; int swap; unsigned long long hash; long nlaunch; cudaGraphExec_t exec; };
-static std::map<cales_ctx*, std::vector<StepGraph>> g_graphs;
+// the cache lives on the context (cales_ctx::step_graphs): contexts of different host threads share nothing
+static std::vector<StepGraph>& step_graphs(cales_ctx* ctx) {
+  if (!ctx->step_graphs) ctx->step_graphs = new std::vector<StepGraph>();
+  return *(std::vector<StepGraph>*)ctx->step_graphs;
+}
 
 static unsigned long long hash_args(const cales_step_args* a) {
   const unsigned char* p = (const unsigned char*)a;
@@ -93,10 +97,11 @@ static unsigned long long hash_args(const cales_step_args* a) {
 }
 
 void k_step_graphs_free(cales_ctx* ctx) {
-  auto it = g_graphs.find(ctx);
-  if (it == g_graphs.end()) return;
-  for (auto& g : it->second) if (g.exec) cudaGraphExecDestroy(g.exec);
-  g_graphs.erase(it);
+  std::vector<StepGraph>* v = (std::vector<StepGraph>*)ctx->step_graphs;
+  if (!v) return;
+  for (auto& g : *v) if (g.exec) cudaGraphExecDestroy(g.exec);
+  delete v;
+  ctx->step_graphs = nullptr;
 }
 
 extern "C" int cales_step(cales_ctx* ctx, const cales_step_args* a, double dt, int use_graph) {
@@ -106,7 +111,7 @@ extern "C" int cales_step(cales_ctx* ctx, const cales_step_args* a, double dt, i
     for (int irk = 1; irk <= 3; ++irk) if ((rc = cales_substep(ctx, a, irk, dt))) return rc;
     return CALES_OK;
   }
-  std::vector<StepGraph>& v = g_graphs[ctx];
+  std::vector<StepGraph>& v = step_graphs(ctx);
   const unsigned long long h = hash_args(a);
   StepGraph* g = nullptr;
   for (auto& e : v) if (e.dt == dt && e.swap == ctx->rk_swap && e.hash == h) { g = &e; break; }
