@@ -237,111 +237,6 @@ def test_full_size_properties():
     g.close()
 
 
-# ---- BASELINE-size parity: the CUDA path against the CPU restatements at the sizes the metric is quoted on ----
-def _errs(g, ref, names=("u", "v", "w", "p", "visct")):
-    out = {}
-    vs = vel_scale(ref)
-    for nm in names:
-        out[nm] = relerr(g.get(nm), ref[nm], demean=(nm == "p"), scale=field_scale(nm, ref[nm], vs))
-    return out
-
-
-@pytest.mark.fullsize
-def test_fullsize_tgv256_vs_c_port(arith):
-    """BASELINE config 2 at its full size: 256^3 tri-periodic TGV, static Smagorinsky, 5 RK3 steps of the CUDA path against the
-    C/OpenMP restatement of the reference loops (oracle/c, 0.3 s/step): fields to 1e-10, then ONE Poisson solve of the same
-    right-hand side on both sides to 1e-12 (de-meaned; floor = the restatement's own sensitivity to a 1-ulp perturbation)."""
-    import oracle.param as op
-    from oracle.cport import CSim
-    from cales_b200.deck import deck_tgv
-    from cales_b200.driver import Simulation
-    ng = (256, 256, 256)
-    o = CSim(op.deck_tgv(ng=ng))
-    g = Simulation(deck_tgv(ng=ng))
-    g.init_flow(); g.start()
-    assert abs(g.dt - o.dt) <= 1e-12 * o.dt      # (the device-generated initial field differs from numpy by round-off)
-    for _ in range(5):
-        dmo = o.step(icheck=1)
-        tot, dmg = g.step(icheck=1)
-    errs = _errs(g, o.f)
-    assert all(v <= 1e-10 for v in errs.values()), errs
-    assert dmg < 1e-11 and abs(dmg - dmo) <= 1e-12 * float(np.abs(o.f["u"]).max()) * max(g.deck.dli), (dmg, dmo)
-    assert abs(g.dt - o.dt) <= 1e-10 * o.dt
-    # one solver call on the same right-hand side on both sides: a seeded random field with zero mean (the compatibility
-    # condition of the singular all-periodic problem; the fillps output of a projected field would be pure round-off)
-    rng = np.random.default_rng(3)
-    rhs = np.asfortranarray(rng.standard_normal(o.f["pp"].shape))
-    rhs[1:-1, 1:-1, 1:-1] -= rhs[1:-1, 1:-1, 1:-1].mean()
-    g.set_fields(pp=rhs)
-    g.solver(g.poi, "pp")
-    o.f["pp"][...] = rhs
-    o.lib.cales_cpu_solver(o.h)
-    ref = o.f["pp"].copy(order="F")
-    o.f["pp"][...] = rhs * (1. + 1.1e-16 * np.sign(rng.standard_normal(rhs.shape)))
-    o.lib.cales_cpu_solver(o.h)
-    floor = relerr(o.f["pp"], ref, demean=True)
-    e = relerr(g.get("pp"), ref, demean=True)
-    # strict build: dgtsv_homebrewed's own operation order, within 20 floors.  Product build: the two-way (twisted)
-    # factorisation is a different, equally stable elimination -- its rounding is independent of the reference's, so the
-    # distance is that of two independent realisations of the floor (measured: up to 21 floors on the stretched
-    # 96x30x40 all-Neumann grid, whose floor is 1.7e-13); 50 floors bound it.
-    from cales_b200 import lib as L_
-    assert e <= max(1e-12, (20. if L_.DEFAULT_ARITH == "strict" else 50.) * floor), (e, floor)
-    g.close(); o.close()
-
-
-@pytest.mark.fullsize
-def test_fullsize_config1_channel64_dsmag_100_steps():
-    """BASELINE config 1 (the reference's own CPU-runnable case): periodic channel Re_tau ~ 180, 64^3, dynamic Smagorinsky,
-    100 RK3 steps; both library variants against ONE run of the numpy oracle; fields to 1e-10 (north star)."""
-    import oracle.param as op
-    import cales_b200.deck as pd
-    from oracle.main import Sim
-    from cales_b200.driver import Simulation
-    kw = dict(ng=(64, 64, 64), sgstype="dsmag")
-    need_gpu()
-    o = Sim(op.deck_channel(**kw))
-    gs = [Simulation(pd.deck_channel(**kw), arith=a) for a in ("strict", "fma")]
-    for g in gs:
-        g.init_flow(); g.start()
-    for _ in range(100):
-        o.step(icheck=10)
-        for g in gs:
-            g.step(icheck=10)
-    ref = {nm: getattr(o, nm.upper())[0] for nm in ("u", "v", "w", "p", "visct")}
-    for g in gs:
-        errs = _errs(g, ref)
-        assert all(v <= 1e-10 for v in errs.values()), (g.lib.arith, errs)
-        assert abs(g.dt - o.dt) <= 1e-10 * o.dt
-        g.close()
-
-
-@pytest.mark.fullsize
-def test_fullsize_config3_wm_channel_512x256x192():
-    """BASELINE config 3 at its full size: wall-modelled channel (log-law wall stress, van Driest-damped static Smagorinsky,
-    gtype 6 grid), 512x256x192, start-up + 2 RK3 steps; both library variants against ONE run of the numpy oracle (about 100 s
-    of CPU per step); fields to 1e-10, divergence at round-off."""
-    import oracle.param as op
-    import cales_b200.deck as pd
-    from oracle.main import Sim
-    from cales_b200.driver import Simulation
-    kw = dict(ng=(512, 256, 192), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.)
-    need_gpu()
-    o = Sim(op.deck_channel(**kw))
-    for _ in range(2):
-        ro = o.step(icheck=1)
-    ref = {nm: getattr(o, nm.upper())[0] for nm in ("u", "v", "w", "p", "visct")}
-    for a in ("strict", "fma"):
-        g = Simulation(pd.deck_channel(**kw), arith=a)
-        g.init_flow(); g.start()
-        for _ in range(2):
-            rg = g.step(icheck=1)
-        errs = _errs(g, ref)
-        assert all(v <= 1e-10 for v in errs.values()), (a, errs)
-        assert rg[1] < 1e-9 and abs(g.dt - o.dt) <= 1e-10 * o.dt, (a, rg, ro)
-        g.close()
-
-
 @pytest.mark.parametrize("case", ["channel_dsmag", "tgv_smag", "channel_wm_smag", "duct_wm_smag", "cavity_smag"])
 def test_fused_step_identical_to_per_procedure_sequence(case, arith):
     """the fused entries (cales_substep / cales_step: update fused into the momentum kernel, out-of-place correc +
