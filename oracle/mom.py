@@ -12,8 +12,57 @@ def _views(a, n):
     return s
 
 
+# Large grids (the BASELINE-size parity cases) are evaluated slab by slab in z on a thread pool: every operation below is
+# elementwise on shifted views, so cutting the k range changes neither the operations nor their order -- the results are
+# the same bits (tests/test_oracle_identities.py::test_mom_slabs_identical) -- but the temporaries stay in cache and
+# numpy's inner loops (which release the GIL) run on all host cores.
+SLAB_CELLS = 1 << 18          # cells per slab
+SLAB_MIN_CELLS = 1 << 21      # grids below this size are evaluated in one piece
+
+
+def slab_threads():
+    import os
+    try:
+        return max(1, min(32, len(os.sched_getaffinity(0))))
+    except AttributeError:
+        return max(1, min(32, os.cpu_count() or 1))
+
+
+def run_slabs(n3, nplane, fn):
+    """fn(k0, nb) for consecutive k ranges [k0+1, k0+nb] (1-based interior levels) covering 1..n3."""
+    nb = max(1, SLAB_CELLS // max(nplane, 1))
+    jobs = [(k0, min(nb, n3 - k0)) for k0 in range(0, n3, nb)]
+    nt = min(slab_threads(), len(jobs))
+    if nt <= 1:
+        for j in jobs:
+            fn(*j)
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(nt) as ex:
+        list(ex.map(lambda j: fn(*j), jobs))
+
+
 def mom_xyz_ad(n, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, impdiff=False, impdiff_1d=False):
     """Returns (dudt,dvdt,dwdt) and, with impdiff, also (dudtd,dvdtd,dwdtd); arrays (n1,n2,n3)."""
+    n1, n2, n3 = n
+    if n1 * n2 * n3 < SLAB_MIN_CELLS:
+        return _mom_block(n, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, impdiff, impdiff_1d)
+    out = [np.empty((n1, n2, n3), order="F") for _ in range(3)]
+    outd = [np.empty((n1, n2, n3), order="F") for _ in range(3)] if impdiff else None
+
+    def job(k0, nb):
+        z = slice(k0, k0 + nb + 2)
+        r, rd = _mom_block((n1, n2, nb), dxi, dyi, dzci[z], dzfi[z], visc, u[:, :, z], v[:, :, z], w[:, :, z], visct[:, :, z],
+                           impdiff, impdiff_1d)
+        for c in range(3):
+            out[c][:, :, k0:k0 + nb] = r[c]
+            if impdiff:
+                outd[c][:, :, k0:k0 + nb] = rd[c]
+    run_slabs(n3, n1 * n2, job)
+    return tuple(out), (tuple(outd) if impdiff else None)
+
+
+def _mom_block(n, dxi, dyi, dzci, dzfi, visc, u, v, w, visct, impdiff=False, impdiff_1d=False):
     n1, n2, n3 = n
     U, V, W, S = _views(u, n), _views(v, n), _views(w, n), _views(visct, n)
     k = np.arange(1, n3 + 1)

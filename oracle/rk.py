@@ -2,7 +2,7 @@
 src/utils.f90:16-47 (`bulk_mean`).  The `save`d arrays of the Fortran routine live in RkState."""
 import numpy as np
 
-from .mom import mom_xyz_ad
+from .mom import mom_xyz_ad, SLAB_MIN_CELLS, run_slabs
 
 
 class RkState:
@@ -28,20 +28,27 @@ def rk_update(rkpar, n, dli, dzci, dzfi, visc, dt, p, bforce, visct, u, v, w, st
     factor12 = factor1 + factor2
     (dudtrk, dvdtrk, dwdtrk), imp = mom_xyz_ad(n, dli[0], dli[1], dzci, dzfi, visc, u, v, w, visct,
                                               impdiff, impdiff_1d)
-    I = (slice(1, n1 + 1), slice(1, n2 + 1), slice(1, n3 + 1))
-    pc = p[I]
-    dzci_k = dzci[1:n3 + 1][None, None, :]
-    unew = u[I] + factor1 * dudtrk + factor2 * state.o[0] + \
-        factor12 * (bforce[0] - dli[0] * (p[2:n1 + 2, 1:n2 + 1, 1:n3 + 1] - pc))
-    vnew = v[I] + factor1 * dvdtrk + factor2 * state.o[1] + \
-        factor12 * (bforce[1] - dli[1] * (p[1:n1 + 1, 2:n2 + 2, 1:n3 + 1] - pc))
-    wnew = w[I] + factor1 * dwdtrk + factor2 * state.o[2] + \
-        factor12 * (bforce[2] - dzci_k * (p[1:n1 + 1, 1:n2 + 1, 2:n3 + 2] - pc))
-    if impdiff:
-        unew = unew + factor12 * imp[0]
-        vnew = vnew + factor12 * imp[1]
-        wnew = wnew + factor12 * imp[2]
-    u[I] = unew; v[I] = vnew; w[I] = wnew
+    def update(k0, nb):
+        """levels k0+1 .. k0+nb (per-cell work: any k range gives the same bits)"""
+        K = slice(k0 + 1, k0 + nb + 1); Kp = slice(k0 + 2, k0 + nb + 2); Kh = slice(k0, k0 + nb)
+        I = (slice(1, n1 + 1), slice(1, n2 + 1), K)
+        pc = p[I]
+        dzci_k = dzci[K][None, None, :]
+        unew = u[I] + factor1 * dudtrk[:, :, Kh] + factor2 * state.o[0][:, :, Kh] + \
+            factor12 * (bforce[0] - dli[0] * (p[2:n1 + 2, 1:n2 + 1, K] - pc))
+        vnew = v[I] + factor1 * dvdtrk[:, :, Kh] + factor2 * state.o[1][:, :, Kh] + \
+            factor12 * (bforce[1] - dli[1] * (p[1:n1 + 1, 2:n2 + 2, K] - pc))
+        wnew = w[I] + factor1 * dwdtrk[:, :, Kh] + factor2 * state.o[2][:, :, Kh] + \
+            factor12 * (bforce[2] - dzci_k * (p[1:n1 + 1, 1:n2 + 1, Kp] - pc))
+        if impdiff:
+            unew = unew + factor12 * imp[0][:, :, Kh]
+            vnew = vnew + factor12 * imp[1][:, :, Kh]
+            wnew = wnew + factor12 * imp[2][:, :, Kh]
+        u[I] = unew; v[I] = vnew; w[I] = wnew
+    if n1 * n2 * n3 < SLAB_MIN_CELLS:
+        update(0, n3)
+    else:
+        run_slabs(n3, n1 * n2, update)
     state.o = [dudtrk, dvdtrk, dwdtrk]                      # swap: the new RHS becomes the old one
     return imp, factor12
 

@@ -7,6 +7,7 @@ import numpy as np
 
 from . import bound as bnd
 from .param import big, c_smag
+from .mom import SLAB_MIN_CELLS, run_slabs
 
 
 def _S(a, n):
@@ -15,7 +16,20 @@ def _S(a, n):
 
 
 def strain_rate(n, dli, dzci, dzfi, u, v, w, s0, sij=None):
-    """sgs.f90:1019-1110.  Writes the interior of s0 (and sij[m], m=0..5 = s11,s22,s33,s12,s13,s23)."""
+    """sgs.f90:1019-1110.  Writes the interior of s0 (and sij[m], m=0..5 = s11,s22,s33,s12,s13,s23).
+    Large grids: slab by slab in z on a thread pool (elementwise work: the same bits, see oracle/mom.py)."""
+    n1, n2, n3 = n
+    if n1 * n2 * n3 < SLAB_MIN_CELLS:
+        return _strain_block(n, dli, dzci, dzfi, u, v, w, s0, sij)
+
+    def job(k0, nb):
+        z = slice(k0, k0 + nb + 2)
+        _strain_block((n1, n2, nb), dli, dzci[z], dzfi[z], u[:, :, z], v[:, :, z], w[:, :, z], s0[:, :, z],
+                      None if sij is None else [a[:, :, z] for a in sij])
+    run_slabs(n3, n1 * n2, job)
+
+
+def _strain_block(n, dli, dzci, dzfi, u, v, w, s0, sij=None):
     n1, n2, n3 = n
     dxi, dyi = dli[0], dli[1]
     U, V, W = _S(u, n), _S(v, n), _S(w, n)
@@ -254,26 +268,32 @@ def _smag_local(r, s, deck, cbcvel, u, v, w, visct):
     dele = (dl[0] * dl[1] * s.dzf[kk]) ** (1. / 3.)
     if np.sum(g.is_wall) == 0:
         fd = np.ones((n1, n2, n3))
-    else:
-        i = np.arange(1, n1 + 1); j = np.arange(1, n2 + 1)
-        shp = (n1, n2, n3)
+        visct[I] = (c_smag * dele[None, None, :] * fd) ** 2 * g.s0[I]
+        return
+    i = np.arange(1, n1 + 1); j = np.arange(1, n2 + 1)
+    J = slice(1, n2 + 1); Jm = slice(0, n2)
+    Ii = slice(1, n1 + 1); Im = slice(0, n1)
+
+    def mag(t1, t2, f):
+        return np.sqrt(t1 * t1 + t2 * t2) * f
+
+    def vandriest(k0, nb):
+        """levels k0+1 .. k0+nb (every operation is per cell: any k range gives the same bits)"""
+        kb = np.arange(k0 + 1, k0 + nb + 1)
+        K = slice(k0 + 1, k0 + nb + 1); Km = slice(k0, k0 + nb)
+        shp = (n1, n2, nb)
         dw = np.empty((6,) + shp)
         dw[0] = (dl[0] * (i - 0.5))[:, None, None]
         dw[1] = (dl[0] * (n1 - i + 0.5))[:, None, None]
         dw[2] = (dl[1] * (j - 0.5))[None, :, None]
         dw[3] = (dl[1] * (n2 - j + 0.5))[None, :, None]
-        dw[4] = s.zc[kk][None, None, :]
-        dw[5] = (l[2] - s.zc[kk])[None, None, :]
+        dw[4] = s.zc[kb][None, None, :]
+        dw[5] = (l[2] - s.zc[kb])[None, None, :]
         iw = g.is_wall[:, None, None, None]
         dw = dw * iw + big * (1. - iw)
         loc = np.argmin(dw, axis=0)                         # minloc: first minimum
         dw_min = np.take_along_axis(dw, loc[None], axis=0)[0]
-        J = slice(1, n2 + 1); Jm = slice(0, n2); K = slice(1, n3 + 1); Km = slice(0, n3)
-        Ii = slice(1, n1 + 1); Im = slice(0, n1)
         tw = np.zeros((6,) + shp)
-
-        def mag(t1, t2, f):
-            return np.sqrt(t1 * t1 + t2 * t2) * f
         t1 = v[1, J, K] - v[0, J, K] + v[1, Jm, K] - v[0, Jm, K]
         t2 = w[1, J, K] - w[0, J, K] + w[1, J, Km] - w[0, J, Km]
         tw[0] = mag(t1, t2, dxi)[None, :, :]
@@ -296,7 +316,11 @@ def _smag_local(r, s, deck, cbcvel, u, v, w, visct):
         tauw_s = 0.5 * visc * tauw_s
         dw_plus = dw_min * np.sqrt(tauw_s) * visci
         fd = 1. - np.exp(-dw_plus / 25.)
-    visct[I] = (c_smag * dele[None, None, :] * fd) ** 2 * g.s0[I]
+        visct[Ii, J, K] = (c_smag * dele[None, None, k0:k0 + nb] * fd) ** 2 * g.s0[Ii, J, K]
+    if n1 * n2 * n3 < SLAB_MIN_CELLS:
+        vandriest(0, n3)
+    else:
+        run_slabs(n3, n1 * n2, vandriest)
 
 
 def cmpt_sgs(world, st, deck, cbcvel, U, V, W, VISCT, ave="channel", filter_2d=False):

@@ -13,6 +13,29 @@ import numpy as np
 import scipy.fft as sfft
 
 from .param import eps, pi
+from .mom import SLAB_MIN_CELLS, slab_threads
+
+
+def _workers(x):
+    """threads for the batched transforms / column solves of large arrays (the BASELINE-size parity cases); the lines and
+    columns are independent, small arrays stay on one thread"""
+    return slab_threads() if x.size >= SLAB_MIN_CELLS else 1
+
+
+def _column_chunks(nx, nt):
+    step = -(-nx // nt)
+    return [(i0, min(nx, i0 + step)) for i0 in range(0, nx, step)]
+
+
+def _dgtsv_threads(n, a, b, c, p):
+    """dgtsv_homebrewed on chunks of independent columns (leading axis) in parallel"""
+    nt = min(_workers(p), p.shape[0])
+    if nt <= 1:
+        return dgtsv_homebrewed(n, a, b, c, p)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(nt) as ex:
+        list(ex.map(lambda ch: dgtsv_homebrewed(n, a, b if b.ndim == 1 else b[ch[0]:ch[1]], c, p[ch[0]:ch[1]]),
+                    _column_chunks(p.shape[0], nt)))
 
 
 # ---- initsolver ------------------------------------------------------------------------------
@@ -100,25 +123,29 @@ def initsolver(ng, lo_z, hi_z, dli, dzci_g, dzfi_g, cbc, c_or_f):
 
 
 # ---- transforms (FFTW r2r kinds) ----------------------------------------------------------------
+def _ax(ndim, axis, sl):
+    idx = [slice(None)] * ndim
+    idx[axis] = sl
+    return tuple(idx)
+
+
 def _r2hc(x, axis):
     n = x.shape[axis]
-    X = sfft.rfft(x, axis=axis)
+    X = sfft.rfft(x, axis=axis, workers=_workers(x))
     re = X.real
-    im = np.flip(np.take(X.imag, np.arange(1, (n + 1) // 2), axis=axis), axis=axis)
+    im = np.flip(X.imag[_ax(X.ndim, axis, slice(1, (n + 1) // 2))], axis=axis)
     return np.concatenate([re, im], axis=axis)
 
 
 def _hc2r(h, axis):
     n = h.shape[axis]
     nre = n // 2 + 1
-    re = np.take(h, np.arange(0, nre), axis=axis)
-    im_tail = np.flip(np.take(h, np.arange(nre, n), axis=axis), axis=axis)      # i_1 .. i_{(n+1)/2-1}
-    shp = list(re.shape)
-    im = np.zeros(shp)
-    idx = [slice(None)] * h.ndim
-    idx[axis] = slice(1, 1 + im_tail.shape[axis])
-    im[tuple(idx)] = im_tail
-    return sfft.irfft(re + 1j * im, n=n, axis=axis) * n
+    re = h[_ax(h.ndim, axis, slice(0, nre))]
+    im_tail = np.flip(h[_ax(h.ndim, axis, slice(nre, n))], axis=axis)           # i_1 .. i_{(n+1)/2-1}
+    X = np.zeros(re.shape, dtype=complex, order="F" if h.flags.f_contiguous else "C")
+    X.real = re
+    X.imag[_ax(h.ndim, axis, slice(1, 1 + im_tail.shape[axis]))] = im_tail
+    return sfft.irfft(X, n=n, axis=axis, workers=_workers(h)) * n
 
 
 _R2R = {"REDFT00": ("dct", 1), "REDFT10": ("dct", 2), "REDFT01": ("dct", 3), "REDFT11": ("dct", 4),
@@ -137,7 +164,7 @@ def fft(kind, nlen, arr, axis):
         y = _hc2r(x, axis)
     else:
         f, t = _R2R[kind]
-        y = getattr(sfft, f)(x, type=t, axis=axis, norm=None)
+        y = getattr(sfft, f)(x, type=t, axis=axis, norm=None, workers=_workers(x))
     arr[tuple(idx)] = y
 
 
@@ -165,7 +192,7 @@ def gaussel(nx, ny, n, a, b, c, p, lambdaxy=None):
     else:
         bb = b[0:n]
     pp = p[:, :, 0:n].copy()
-    dgtsv_homebrewed(n, a, bb, c, pp)
+    _dgtsv_threads(n, a, bb, c, pp)
     p[:, :, 0:n] = pp
 
 
@@ -176,11 +203,11 @@ def gaussel_periodic(nx, ny, n, a, b, c, p, lambdaxy=None):
     else:
         bb = np.broadcast_to(b[None, None, 0:n], (nx, ny, n))
     p1 = p[:, :, 0:n - 1].copy()
-    dgtsv_homebrewed(n - 1, a, bb[:, :, 0:n - 1], c, p1)
+    _dgtsv_threads(n - 1, a, bb[:, :, 0:n - 1], c, p1)
     p2 = np.zeros((nx, ny, n - 1))
     p2[:, :, 0] = -a[0]
     p2[:, :, n - 2] = -c[n - 2]
-    dgtsv_homebrewed(n - 1, a, bb[:, :, 0:n - 1], c, p2)
+    _dgtsv_threads(n - 1, a, bb[:, :, 0:n - 1], c, p2)
     pn = (p[:, :, n - 1] - c[n - 1] * p1[:, :, 0] - a[n - 1] * p1[:, :, n - 2]) / \
          (bb[:, :, n - 1] + c[n - 1] * p2[:, :, 0] + a[n - 1] * p2[:, :, n - 2] + eps)
     p[:, :, n - 1] = pn
