@@ -84,6 +84,33 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
+def bind_near_gpu(index):
+    """Restrict the calling thread to the CPUs NVML reports as local to GPU `index` (its NUMA node), so that the pinned
+    host buffers of the end-to-end leg are allocated next to the PCIe root the GPU hangs off (first touch follows the
+    allocating thread).  Returns (previous mask, record for the JSON line) or (None, reason); never raises."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(torch.cuda.get_device_properties(index).uuid)).encode())
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * wi + b for wi, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cur = os.sched_getaffinity(0)
+        new = near & cur
+        if not new:
+            return None, "NVML's CPU set for the GPU does not intersect this process's CPUs"
+        if new == cur:
+            return None, "already local (%d CPUs)" % len(cur)
+        os.sched_setaffinity(0, new)
+        return cur, "host thread bound to the %d of %d CPUs local to the GPU while the pinned buffers are allocated and the copies driven" % (len(new), len(cur))
+    except Exception as e:                                   # no NVML, no permission, ...: run unbound
+        return None, "unbound (%s)" % type(e).__name__
+
+
 # ---- workloads --------------------------------------------------------------------------------------------------------
 def workload(args, world):
     """-> (deck constructor name, kwargs, global grid, dims, label, scaling)"""
@@ -329,6 +356,7 @@ def run_ours(args):
     # compute of step s on the library's stream, through double-buffered device staging; PCIe is full duplex.
     e2e = None
     if not args.no_e2e:
+        old_mask, numa_note = bind_near_gpu(local)
         names = ("u", "v", "w", "p")
         hin = {nm: torch.empty(sim.ncell, dtype=torch.float64).pin_memory() for nm in names}
         hout = {nm: torch.empty(sim.ncell, dtype=torch.float64).pin_memory() for nm in names}
@@ -384,9 +412,12 @@ def run_ours(args):
         barrier()
         t_e2e = maxranks(e0.elapsed_time(e1) * 1e-3) / ke
         del stage_in, stage_out
+        if old_mask is not None:
+            os.sched_setaffinity(0, old_mask)
         e2e = {"value": ncell / t_e2e / 1e6, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "ms_per_step": t_e2e * 1e3,
                "what": "every step: pinned host u,v,w,p -> device, one RK3 step through the C ABI, u,v,w,p -> pinned host; uploads/downloads "
-                       "pipelined on copy streams (double-buffered staging), timed until the last result is on the host; bytes are per rank"}
+                       "pipelined on copy streams (double-buffered staging), timed until the last result is on the host; bytes are per rank",
+               "numa": numa_note}
     # ---- roofline of the kernels (live CUDA-event timing on the launch stream) -------------------------
     n = sim.n
     scr = [torch.zeros(int(ncell_loc), dtype=torch.float64, device="cuda") for _ in range(3)]
