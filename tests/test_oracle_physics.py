@@ -14,6 +14,27 @@ def _run_to_steady(s, t_end):
         s.step()
 
 
+def discrete_poiseuille(dzc, dzf, visc, l3):
+    """Dense solution of the discrete steady channel problem nu D2 u = -G, centred Dirichlet ghosts u_0 = -u_1 and
+    u_{n+1} = -u_n, bulk velocity 1; dzc[k] = zc[k+1] - zc[k], dzf[k] = zf[k] - zf[k-1], k = 0..n3+1.  -> (u(1:n3), G)"""
+    n3 = dzf.size - 2
+    A = np.zeros((n3, n3))
+    for k in range(1, n3 + 1):
+        up, lo = 1. / (dzc[k] * dzf[k]), 1. / (dzc[k - 1] * dzf[k])
+        A[k - 1, k - 1] = -(up + lo)
+        if k < n3:
+            A[k - 1, k] = up
+        else:
+            A[k - 1, k - 1] -= up
+        if k > 1:
+            A[k - 1, k - 2] = lo
+        else:
+            A[k - 1, k - 1] -= lo
+    shape = np.linalg.solve(visc * A, -np.ones(n3))      # u for G = 1
+    G = 1. / float((shape * dzf[1:n3 + 1] / l3).sum())
+    return shape * G, G
+
+
 def test_laminar_channel_reaches_the_discrete_poiseuille_solution_and_its_pressure_gradient():
     """Forced laminar channel (bulk velocity held at 1): the steady state of the scheme is the solution of the DISCRETE
     problem nu * D2 u = -G with the centred Dirichlet ghost u_0 = -u_1, mean(u) = 1 -- solved here with a dense matrix --
@@ -25,24 +46,7 @@ def test_laminar_channel_reaches_the_discrete_poiseuille_solution_and_its_pressu
         d.is_wallturb = False
         s = Sim(d)
         _run_to_steady(s, 3.0)
-        # dense discrete problem on the same grid
-        dzc, dzf = s.dzc_g, s.dzf_g                      # dzc[k] = zc[k+1]-zc[k], dzf[k] = zf[k]-zf[k-1], k = 0..n3+1
-        A = np.zeros((n3, n3))
-        for k in range(1, n3 + 1):
-            up, lo = 1. / (dzc[k] * dzf[k]), 1. / (dzc[k - 1] * dzf[k])
-            A[k - 1, k - 1] = -(up + lo)
-            if k < n3:
-                A[k - 1, k] = up
-            else:
-                A[k - 1, k - 1] -= up                   # ghost u_{n+1} = -u_n
-            if k > 1:
-                A[k - 1, k - 2] = lo
-            else:
-                A[k - 1, k - 1] -= lo                   # ghost u_0 = -u_1
-        shape = np.linalg.solve(d.visc * A, -np.ones(n3))   # u for G = 1
-        w = dzf[1:n3 + 1] / d.l[2]
-        G = 1. / float((shape * w).sum())                # bulk velocity 1
-        u_ref = shape * G
+        u_ref, G = discrete_poiseuille(s.dzc_g, s.dzf_g, d.visc, d.l[2])
         u = s.U[0][1:-1, 1:-1, 1:-1]
         assert np.abs(u - u_ref[None, None, :]).max() < 1e-9, gr
         assert np.abs(s.V[0]).max() < 1e-12 and np.abs(s.W[0]).max() < 1e-12
