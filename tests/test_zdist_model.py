@@ -98,3 +98,87 @@ def test_zdist_model_vs_dense(n, P, periodic):
     assert np.abs(A @ x - r).max() <= 1e-9 * np.abs(r).max()
     xr = np.linalg.lstsq(A, r, rcond=None)[0]
     assert np.abs((x - x.mean()) - (xr - xr.mean())).max() <= 1e-8 * np.abs(xr - xr.mean()).max()
+
+
+# ---- the same algorithm across REAL processes (torch.distributed / gloo): every rank holds only its block of the right-hand
+# side, solves it locally, contributes its first and last value to an all-gather (the push of two boundary planes into every
+# rank's gather buffer in zdist.cu), forms its two interface unknowns from the gathered values and corrects its block -------
+def _spikes(a, bb, c, z0, z1, has_prev, has_next):
+    A, B, C = a[z0:z1], bb[z0:z1], c[z0:z1]; m = z1 - z0
+    d = 0.; zf = np.zeros(m)
+    for l in range(m):
+        zf[l] = 1. / (B[l] - A[l] * d + EPS); d = C[l] * zf[l]
+    w = np.zeros(m); w[m - 1] = C[m - 1] * zf[m - 1] if has_next else 0.
+    for l in range(m - 2, -1, -1):
+        w[l] = -(C[l] * zf[l]) * w[l + 1]
+    d = 0.; zb = np.zeros(m)
+    for l in range(m - 1, -1, -1):
+        zb[l] = 1. / (B[l] - C[l] * d + EPS); d = A[l] * zb[l]
+    v = np.zeros(m); v[0] = A[0] * zb[0] if has_prev else 0.
+    for l in range(1, m):
+        v[l] = -(A[l] * zb[l]) * v[l - 1]
+    return v, w
+
+
+def _zdist_rank(rank, P, n, periodic, port, q):
+    try:
+        import os
+        import torch
+        import torch.distributed as dist
+        os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=P)
+        rng = np.random.default_rng(7 * n + P + periodic)        # the coefficients are global (every rank has a, b, c, lambda)
+        a, b, c = system(n, periodic, rng)
+        ncol = 5
+        lams = -np.abs(rng.standard_normal(ncol)) - 1e-3
+        R = rng.standard_normal((ncol, n))
+        zs = distribute(n, P); z0, z1 = zs[rank], zs[rank + 1]
+        mine = R[:, z0:z1].copy()                                # this rank's block of the right-hand side: all it ever reads of R
+        x_loc = np.zeros_like(mine)
+        ends = torch.zeros(ncol, 2, dtype=torch.float64)
+        Y, VW = [], []
+        for col in range(ncol):
+            bb = b + lams[col]
+            y = thomas(a[z0:z1], bb[z0:z1], c[z0:z1], mine[col])
+            Y.append(y); ends[col, 0] = y[0]; ends[col, 1] = y[-1]
+            VW.append(_spikes(a, bb, c, z0, z1, periodic or rank > 0, periodic or rank < P - 1))
+        gathered = [torch.zeros_like(ends) for _ in range(P)]
+        dist.all_gather(gathered, ends)                          # 2 values per column and rank cross the network, nothing else
+        for col in range(ncol):
+            bb = b + lams[col]
+            U = 2 * P; M = np.zeros((U, U)); rhs = np.zeros(U)
+            for s in range(P):                                   # interface system from the spikes of every block (coefficients only)
+                v, w = _spikes(a, bb, c, zs[s], zs[s + 1], periodic or s > 0, periodic or s < P - 1)
+                ip, inx = 2 * ((s - 1) % P) + 1, 2 * ((s + 1) % P)
+                for e in range(2):
+                    row = 2 * s + e
+                    M[row, row] += 1.; M[row, ip] += v[-1 if e else 0]; M[row, inx] += w[-1 if e else 0]
+                    rhs[row] = float(gathered[s][col, e])
+            u = np.linalg.solve(M, rhs)
+            xp = u[2 * ((rank - 1) % P) + 1] if (periodic or rank > 0) else 0.
+            xn = u[2 * ((rank + 1) % P)] if (periodic or rank < P - 1) else 0.
+            v, w = VW[col]
+            x_loc[col] = Y[col] - v * xp - w * xn
+        # check against the dense solve of the whole system (every rank can form it: test only)
+        for col in range(ncol):
+            xr = np.linalg.solve(dense(a, b, c, lams[col], periodic), R[col])
+            assert np.abs(x_loc[col] - xr[z0:z1]).max() <= 1e-9 * max(1., 1e-4 / abs(lams[col])) * np.abs(xr).max()
+        dist.barrier(); dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "FAIL: " + traceback.format_exc()))
+
+
+@pytest.mark.parametrize("P,n,periodic,port", [(2, 24, 0, 29621), (2, 24, 1, 29622), (4, 37, 1, 29623), (3, 20, 0, 29624)])
+def test_zdist_across_gloo_processes(P, n, periodic, port):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_zdist_rank, args=(r, P, n, periodic, port, q)) for r in range(P)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(P)]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
