@@ -321,3 +321,77 @@ def read_input(path):
     if missing:
         raise DeckError("%s: required entries missing from &dns: %s" % (path, ", ".join(missing)))
     return d
+
+
+# ---------------------------------------------------------------------------
+# writer: a Deck as an input.nml the REFERENCE reads (namelists /dns/ and /les/, param.f90:95-120; layout of
+# examples/les/_manuscript_turbulent_channel_wall_model/input.nml), so that a site-built CaLES and this library can be run
+# on the same file ("Pinning the oracle off this box")
+# ---------------------------------------------------------------------------
+def _f(x):
+    s = repr(float(x))
+    return s.replace("e", "d") if "e" in s else s            # 1e-05 -> 1d-05: a double-precision literal either way
+
+
+def _l(x):
+    return "T" if x else "F"
+
+
+def write_input(d, path=None):
+    """Returns (and, with `path`, writes) the text of input.nml for deck `d`.  The cpp switches that are run-time options here
+    (impdiff, impdiff_1d, ipencil) are build options of the reference and appear as a comment."""
+    def pairs(arr, fmt):
+        return ",  ".join(",".join(fmt(arr[ib, idir]) for ib in range(2)) for idir in range(3))
+    q = lambda s: "'%s'" % s
+    L = ["&dns",
+         "ng(1:3) = %d, %d, %d" % tuple(d.ng),
+         "l(1:3) = %s, %s, %s" % tuple(_f(x) for x in d.l),
+         "gtype = %d, gr = %s" % (d.gtype, _f(d.gr)),
+         "cfl = %s, dtmax = %s, dt_f = %s" % (_f(d.cfl), _f(d.dtmax), _f(d.dt_f)),
+         "visci = %s" % _f(d.visci),
+         "inivel = '%s'" % d.inivel,
+         "is_wallturb = %s" % _l(d.is_wallturb),
+         "nstep = %d, time_max = %s, tw_max = %s" % (d.nstep, _f(d.time_max), _f(d.tw_max)),
+         "stop_type(1:3) = %s, %s, %s" % tuple(_l(x) for x in d.stop_type),
+         "restart = %s, is_overwrite_save = %s, nsaves_max = %d" % (_l(d.restart), _l(d.is_overwrite_save), d.nsaves_max),
+         "icheck = %d, iout0d = %d, iout1d = %d, iout2d = %d, iout3d = %d, isave = %d" % (d.icheck, d.iout0d, d.iout1d, d.iout2d, d.iout3d, d.isave)]
+    for c in range(3):
+        L.append("cbcvel(0:1,1:3,%d) = %s" % (c + 1, pairs(d.cbcvel[:, :, c], q)))
+    L.append("cbcpre(0:1,1:3)   = %s" % pairs(d.cbcpre, q))
+    L.append("cbcsgs(0:1,1:3)   = %s" % pairs(d.cbcsgs, q))
+    for c in range(3):
+        L.append("bcvel(0:1,1:3,%d) = %s" % (c + 1, pairs(d.bcvel[:, :, c], _f)))
+    L.append("bcpre(0:1,1:3)   = %s" % pairs(d.bcpre, _f))
+    L.append("bcsgs(0:1,1:3)   = %s" % pairs(d.bcsgs, _f))
+    L += ["bforce(1:3) = %s, %s, %s" % tuple(_f(x) for x in d.bforce),
+          "is_forced(1:3) = %s, %s, %s" % tuple(_l(x) for x in d.is_forced),
+          "velf(1:3) = %s, %s, %s" % tuple(_f(x) for x in d.velf),
+          "dims(1:2) = %d, %d" % tuple(d.dims),
+          "/", "",
+          "&les",
+          "sgstype = '%s'" % d.sgstype,
+          "lwm(0:1,1:3) = %s" % pairs(d.lwm, lambda x: "%d" % x),
+          "hwm = %s" % _f(d.hwm),
+          "/", ""]
+    build = []
+    if d.impdiff:
+        build.append("-D_IMPDIFF")
+    if d.impdiff_1d:
+        build.append("-D_IMPDIFF_1D")
+    build.append("-D_DECOMP_%s" % "XYZ"[d.ipencil - 1])
+    L.append("! reference build options matching this deck: " + " ".join(build))
+    txt = "\n".join(L) + "\n"
+    if path:
+        with open(path, "w") as f:
+            f.write(txt)
+    return txt
+
+
+BASELINE_DECKS = {   # BASELINE.json configs (SURVEY.md section 8d); nstep / isave as the pinning recipe wants them
+    "config1": lambda: deck_channel(ng=(64, 64, 64), sgstype="dsmag"),
+    "config2": lambda: deck_tgv(ng=(256, 256, 256), sgstype="smag"),
+    "config3": lambda: deck_channel(ng=(512, 256, 192), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.),
+    "config4_duct": lambda: deck_duct(ng=(512, 256, 256), sgstype="smag"),
+    "config4_cavity": lambda: deck_cavity(ng=(512, 256, 256), sgstype="smag"),
+    "config5": lambda: deck_channel(ng=(1024, 512, 512), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.),
+}
