@@ -93,3 +93,38 @@ def test_alias(tmp_path):
     ck.gen_alias(str(tmp_path), "fld_0001.bin", "fld.bin")             # idempotent
     data, t, i = reference_reader(str(tmp_path / "fld.bin"), ng)
     assert t == 0.5 and i == 3 and np.array_equal(data[:, :, :, 2], f[2][1:-1, 1:-1, 1:-1])
+
+
+def test_compare_fld_tool_on_oracle_restart_files(tmp_path):
+    """tools/compare_fld.py (the off-box pin of INTEGRATION.md) end to end: two restart files of the same oracle run agree; the
+    additive constant of the pressure is ignored; a 1e-6 perturbation of one velocity, a different step count or a different
+    time are reported as FAIL with a non-zero exit code."""
+    import subprocess
+    import sys
+    import oracle.param as op
+    from oracle.main import Sim
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ng = (12, 10, 8)
+    s = Sim(op.deck_tgv(ng=ng))
+    for _ in range(3):
+        s.step()
+    f = [getattr(s, nm)[0] for nm in ("U", "V", "W", "P")]
+
+    def write(name, fields, time, istep):
+        fn = str(tmp_path / name)
+        ck.load_all("w", fn, ng, (1, 1, 1), ng, *fields, time=time, istep=istep)
+        return fn
+
+    def run(a, b):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "compare_fld.py"), a, b, "--ng"] + [str(x) for x in ng],
+                           capture_output=True, text=True)
+        return r.returncode, r.stdout
+    ref = write("ref.bin", f, s.time, s.istep)
+    shifted = [f[0], f[1], f[2], f[3] + 123.456]
+    rc, out = run(write("same.bin", shifted, s.time, s.istep), ref)
+    assert rc == 0 and "PASS" in out, out
+    bad = [f[0], f[1] * (1. + 1e-6), f[2], f[3]]
+    rc, out = run(write("bad.bin", bad, s.time, s.istep), ref)
+    assert rc == 1 and "FAIL" in out and "v: relative L-inf difference" in out, out
+    assert run(write("step.bin", f, s.time, s.istep + 1), ref)[0] == 1
+    assert run(write("time.bin", f, s.time * 1.001, s.istep), ref)[0] == 1
