@@ -146,14 +146,14 @@ def workload(args, world):
 
 
 # ---- reference arm -------------------------------------------------------------------------------------------------------
-def cpu_port_rate(ng, steps, warmup, threads=None):
+def cpu_port_rate(ng, steps, warmup, threads=None, deck=None):
     """Mcell-updates/s of the CPU restatement of the reference (oracle/c: C + OpenMP, the same loops as the Fortran) on the
-    bench workload, on `threads` OpenMP threads (default: every core this process may run on -- set explicitly, because
-    torchrun exports OMP_NUM_THREADS=1 to its workers).  Returns (rate, seconds/step, threads)."""
+    bench workload (default deck: TGV smag on grid `ng`), on `threads` OpenMP threads (default: every core this process may
+    run on -- set explicitly, because torchrun exports OMP_NUM_THREADS=1 to its workers).  Returns (rate, seconds/step, threads)."""
     import oracle.param as op
     from oracle.cport import CSim
     threads = threads or len(os.sched_getaffinity(0))
-    s = CSim(op.deck_tgv(ng=ng), threads=threads)
+    s = CSim(deck if deck is not None else op.deck_tgv(ng=ng), threads=threads)
     for _ in range(warmup):
         s.step()
     t0 = time.perf_counter()
@@ -174,20 +174,25 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.workload != "tgv256":
-        print(json.dumps({"impl": "reference", "unavailable": "the C/OpenMP port covers the tri-periodic smag path (BASELINE config 2) only"}))
-        return
+    import oracle.param as op
+    from oracle.cport import CSim
     n = max(1, args.gpus)
-    ng = (256, 256, 256 * n)
+    name, kw, ng, dims, label, scaling = workload(args, n)       # our arm's workload at N GPUs: the same global grid
+    kw = dict(kw); kw["ng"] = tuple(ng)
+    deck = getattr(op, name)(**kw)
+    if CSim.kind(deck) is None:
+        print(json.dumps({"impl": "reference", "unavailable": "the C/OpenMP port (oracle/c) covers static-Smagorinsky tri-periodic and plane-channel decks; "
+                                                              "not %s" % label}))
+        return
     threads = len(os.sched_getaffinity(0))
-    est = 0.3 * n * 16.0 / max(threads, 1)                       # s/step guess: 0.3 s per 256^3 on 16 threads
+    est = 0.3 * (float(np.prod(ng)) / 256 ** 3) * 16.0 / max(threads, 1)   # s/step guess: 0.3 s per 256^3 on 16 threads
     steps = max(1, min(args.steps, int(150.0 / max(est, 1e-3))))
-    val, dt, th = cpu_port_rate(ng, steps, max(1, min(args.warmup, 2)), threads)
-    sample = "TGV smag %dx%dx%d (the full grid of our arm at %d GPU%s), %d timed RK3 steps, C/OpenMP port of the reference loops, %d threads" % (
-        ng + (n, "" if n == 1 else "s", steps, th))
+    val, dt, th = cpu_port_rate(ng, steps, max(1, min(args.warmup, 2)), threads, deck=deck)
+    sample = "%s, grid %dx%dx%d (the full grid of our arm at %d GPU%s), %d timed RK3 steps, C/OpenMP port of the reference loops, %d threads" % (
+        (label,) + tuple(ng) + (n, "" if n == 1 else "s", steps, th))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BASELINE config 2: tri-periodic decaying turbulence (TGV init), static Smagorinsky, 256x256x256 per GPU, explicit diffusion",
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": label,
                        "grid": list(ng), "timed_steps": steps,
                        "note": "restated CPU path (the Fortran/MPI/FFTW reference cannot be built in this image); one process, all host threads"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": th, "kind": "port", "sample": sample},
@@ -459,11 +464,17 @@ def run_ours(args):
     if rank == 0:
         # CPU baseline (oracle port) on a bounded sample, N=1 only
         cpu = None
-        if world == 1 and not args.no_cpu_baseline and args.workload == "tgv256":
-            val, dtc, th = cpu_port_rate((256, 256, 256), 5, 1)
-            cpu = {"value": val, "unit": UNIT, "cores": th, "kind": "port",
-                   "sample": "the same 256x256x256 workload, 5 RK3 steps, C/OpenMP port of the reference loops (oracle/c), "
-                             "%d threads (%.2f s/step)" % (th, dtc)}
+        if world == 1 and not args.no_cpu_baseline:
+            import oracle.param as op
+            from oracle.cport import CSim
+            okw = dict(kw); okw["ng"] = tuple(ng)
+            odeck = getattr(op, name)(**okw)
+            if CSim.kind(odeck) is not None:
+                nst = 5 if ncell <= 2.0e7 else 2
+                val, dtc, th = cpu_port_rate(ng, nst, 1, deck=odeck)
+                cpu = {"value": val, "unit": UNIT, "cores": th, "kind": "port",
+                       "sample": "the same %dx%dx%d workload, %d RK3 steps, C/OpenMP port of the reference loops (oracle/c), "
+                                 "%d threads (%.2f s/step)" % (tuple(ng) + (nst, th, dtc))}
         line = {"metric": METRIC, "value": ncell / t_step / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": t_step * 1e3, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",

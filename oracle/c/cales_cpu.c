@@ -1,7 +1,14 @@
 /* oracle/c/cales_cpu.c -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline; never on the product path).
  *
- * Plain C / OpenMP restatement of the reference's per-RK3-substep path for the tri-periodic, explicit-
- * diffusion, static-Smagorinsky configuration (BASELINE config 2, the bench.py workload): the loops of
+ * Plain C / OpenMP restatement of the reference's per-RK3-substep path, explicit diffusion, static Smagorinsky, one
+ * rank, for (i) the tri-periodic configuration (BASELINE config 2, the bench.py workload) and (ii) the plane channel:
+ * periodic x and y, no-slip walls in z (velocity D, pressure N, eddy viscosity D), bulk-velocity forcing, stretched
+ * grids, van Driest damping, and optionally the log-law wall model on the z walls (BASELINE configs 3 and 5):
+ *   src/bound.f90:18-154 (bounduvw), 156-200 (boundp), 202-399 (set_bc: P, D and N, centred and face),
+ *   src/wmodel.f90:19-335 (updt_wallmodelbc / cmpt_wallmodelbc case(3) / vel_relative / wallmodel),
+ *   src/sgs.f90:69-152 with extrapolate 682-767, src/rk.f90:197-222 + src/utils.f90:16-47 + src/mom.f90:311-335
+ *   (bulk forcing), src/initsolver.f90:127-169 (tridmatrix with the N fold-in), src/solver.f90:82-107 (gaussel).
+ * The loops of
  *   src/mom.f90:17-309 (mom_xyz_ad), src/rk.f90:17-121 (rk), src/fillps.f90:14-48, src/solver.f90:20-80
  *   (solver: x transform, y transform, gaussel_periodic 109-151 with dgtsv_homebrewed 153-179, backward),
  *   src/correc.f90:14-68, src/updatep.f90:14-49, src/sgs.f90:69-152 ('smag') + strain_rate 1019-1110,
@@ -48,6 +55,15 @@ typedef struct {
   double *wk;                          /* solver work array (n1,n2,n3) */
   fftplan px, py;
   double eps;
+  /* channel family (zwall = 1): z walls, forcing, wall model */
+  int zwall;                           /* 0: z periodic; 1: walls at both z faces (cbcvel D, cbcpre N, cbcsgs D) */
+  int lwm[2], index_wm[2];             /* wall model on the lower / upper z wall (lwm(0:1,3)), interpolation level k2 */
+  double hwm;
+  int is_forced[3];
+  double velf[3], bforce[3], f[3];
+  double *zc, *zf, *gvr_c, *gvr_f;     /* 0:n3+1 */
+  double *bcu_z, *bcv_z;               /* wall-model Neumann planes bcu%z, bcv%z: (0:n1+1, 0:n2+1, 0:1) */
+  double *wku, *wkv;                   /* copies of u, v for the extrapolation of cmpt_sgs (sgs.f90:84-90) */
 } cpu_t;
 
 #define IDX(s, i, j, k) ((long)(i) + (s)->sj * ((long)(j) + (long)((s)->n2 + 2) * (long)(k)))
@@ -164,6 +180,135 @@ static void bound_periodic(const cpu_t *s, double *p) {
     for (int i = 0; i <= n1 + 1; i++) { p[IDX(s, i, j, 0)] = p[IDX(s, i, j, n3)]; p[IDX(s, i, j, n3 + 1)] = p[IDX(s, i, j, 1)]; }
 }
 
+/* x and y periodic fills, full extent (x: set_bc('P'), bound.f90:232-248; y: the self halo exchange of one rank) */
+static void bound_xy_periodic(const cpu_t *s, double *p) {
+  int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k <= n3 + 1; k++)
+    for (int i = 0; i <= n1 + 1; i++) { p[IDX(s, i, 0, k)] = p[IDX(s, i, n2, k)]; p[IDX(s, i, n2 + 1, k)] = p[IDX(s, i, 1, k)]; }
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 0; k <= n3 + 1; k++)
+    for (int j = 0; j <= n2 + 1; j++) { p[IDX(s, 0, j, k)] = p[IDX(s, n1, j, k)]; p[IDX(s, n1 + 1, j, k)] = p[IDX(s, 1, j, k)]; }
+}
+
+/* set_bc in z on whole planes (bound.f90:202-399): ctype 'D' / 'N', centred or face, boundary value planes bc0 / bc1
+ * (NULL = the constant 0 of the channel decks), dr = dzc(0) / dzc(n3) (dzf for the face-centred w, unused by D). */
+static void set_bc_z(const cpu_t *s, char ctype, int centered, const double *bc0, const double *bc1, double dr0, double dr1, double *p,
+                     int do0, int do1) {
+  const int n1 = s->n1, n2 = s->n2, n = s->n3;
+  const long pl = (long)(n1 + 2) * (n2 + 2);
+  const double sgn = (ctype == 'D' && centered) ? -1. : 1.;
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j <= n2 + 1; j++)
+    for (int i = 0; i <= n1 + 1; i++) {
+      const long q = (long)i + (long)(n1 + 2) * j;
+      const double b0 = bc0 ? bc0[q] : 0., b1 = bc1 ? bc1[q] : 0.;
+      if (ctype == 'D' && centered) {                                            /* 250-282 */
+        if (do0) p[q] = 2. * b0 + sgn * p[q + pl];
+        if (do1) p[q + pl * (n + 1)] = 2. * b1 + sgn * p[q + pl * n];
+      } else if (ctype == 'D') {                                                 /* 283-319 */
+        if (do0) p[q] = b0;
+        if (do1) { p[q + pl * (n + 1)] = p[q + pl * (n - 1)]; p[q + pl * n] = b1; }
+      } else if (centered) {                                                     /* 'N', 320-353 */
+        if (do0) p[q] = -dr0 * b0 + sgn * p[q + pl];
+        if (do1) p[q + pl * (n + 1)] = dr1 * b1 + sgn * p[q + pl * n];
+      }
+    }
+}
+
+/* wmodel.f90:288-335, WM_LOG */
+static void wallmodel_log(double uh, double vh, double h, double visc, double eps, double tauw[2]) {
+  const double kap_log = 0.41, b_log = 5.20;                                     /* param.f90:31-32 */
+  double conv = 1.;
+  const double upar = sqrt(uh * uh + vh * vh);
+  double utau = fmax(sqrt(upar / h * visc), visc / h * exp(-kap_log * b_log));
+  while (conv > 0.5e-4) {
+    const double utau_old = utau;
+    const double f = upar / utau - 1. / kap_log * log(h * utau / visc) - b_log;
+    const double fp = -1. / utau * (upar / utau + 1. / kap_log);
+    utau = fabs(utau - f / fp);
+    conv = fabs(utau / utau_old - 1.);
+  }
+  const double tauw_tot = utau * utau;
+  tauw[0] = tauw_tot * uh / (upar + eps);
+  tauw[1] = tauw_tot * vh / (upar + eps);
+}
+
+/* cmpt_wallmodelbc, case(3) (wmodel.f90:215-271), wall at rest (bcu_mag = bcv_mag = 0: the channel decks) */
+static void cmpt_wallmodelbc_z(cpu_t *s, int ibound) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj;
+  const double h = s->hwm, visc = s->visc, visci = 1. / visc;
+  const double *u = s->u, *v = s->v;
+  int k1, k2; double coef, sgn;
+  if (ibound == 0) { k2 = s->index_wm[0]; k1 = k2 - 1; coef = (h - s->zc[k1]) / s->dzc[k1]; sgn = 1.; }
+  else { k2 = s->index_wm[1]; k1 = k2 + 1; coef = (h - (s->l[2] - s->zc[k1])) / (s->dzc[k2]); sgn = -1.; }
+  double *bcu = s->bcu_z + (long)ibound * (n1 + 2) * (n2 + 2), *bcv = s->bcv_z + (long)ibound * (n1 + 2) * (n2 + 2);
+  (void)n3;
+#pragma omp parallel for schedule(static)
+  for (int j = 1; j <= n2; j++)
+    for (int i = 0; i <= n1; i++) {
+      const long c1 = IDX(s, i, j, k1), c2 = IDX(s, i, j, k2);
+      const double u1 = u[c1], u2 = u[c2];
+      const double v1 = 0.25 * (v[c1] + v[c1 + 1] + v[c1 - sj] + v[c1 + 1 - sj]);
+      const double v2 = 0.25 * (v[c2] + v[c2 + 1] + v[c2 - sj] + v[c2 + 1 - sj]);
+      const double u_mag = 0., v_mag = 0.25 * (0. + 0. + 0. + 0.);
+      double uh = (1. - coef) * u1 + coef * u2; uh = uh - u_mag;                  /* vel_relative, 273-286 */
+      double vh = (1. - coef) * v1 + coef * v2; vh = vh - v_mag;
+      double tauw[2];
+      wallmodel_log(uh, vh, h, visc, s->eps, tauw);
+      bcu[(long)i + (long)(n1 + 2) * j] = sgn * visci * tauw[0];
+    }
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j <= n2; j++)
+    for (int i = 1; i <= n1; i++) {
+      const long c1 = IDX(s, i, j, k1), c2 = IDX(s, i, j, k2);
+      const double u1 = 0.25 * (u[c1 - 1] + u[c1] + u[c1 - 1 + sj] + u[c1 + sj]);
+      const double u2 = 0.25 * (u[c2 - 1] + u[c2] + u[c2 - 1 + sj] + u[c2 + sj]);
+      const double v1 = v[c1], v2 = v[c2];
+      const double u_mag = 0.25 * (0. + 0. + 0. + 0.), v_mag = 0.;
+      double uh = (1. - coef) * u1 + coef * u2; uh = uh - u_mag;
+      double vh = (1. - coef) * v1 + coef * v2; vh = vh - v_mag;
+      double tauw[2];
+      wallmodel_log(uh, vh, h, visc, s->eps, tauw);
+      bcv[(long)i + (long)(n1 + 2) * j] = sgn * visci * tauw[1];
+    }
+}
+
+/* bounduvw (bound.f90:18-154) for the channel on one rank, is_updt_wm = .true. */
+static void bounduvw_channel(cpu_t *s, int is_correc) {
+  const int n3 = s->n3;
+  const long pl = (long)(s->n1 + 2) * (s->n2 + 2);
+  bound_xy_periodic(s, s->u); bound_xy_periodic(s, s->v); bound_xy_periodic(s, s->w);
+  const int impose_norm_bc = !is_correc;                                         /* cbc(:,3,3) = 'D','D': never 'PP' */
+  if (impose_norm_bc) set_bc_z(s, 'D', 0, NULL, NULL, s->dzf[0], s->dzf[n3], s->w, 1, 1);
+  for (int ib = 0; ib < 2; ib++)
+    if (s->lwm[ib] == 0) {
+      set_bc_z(s, 'D', 1, NULL, NULL, s->dzc[0], s->dzc[n3], s->u, ib == 0, ib == 1);
+      set_bc_z(s, 'D', 1, NULL, NULL, s->dzc[0], s->dzc[n3], s->v, ib == 0, ib == 1);
+    }
+  for (int ib = 0; ib < 2; ib++) if (s->lwm[ib] != 0) cmpt_wallmodelbc_z(s, ib);   /* updt_wallmodelbc, 125-128 */
+  for (int ib = 0; ib < 2; ib++)
+    if (s->lwm[ib] != 0) {                                                       /* cbcvel(:,3,1:2) = 'N' (initbc, bound.f90:746-758) */
+      set_bc_z(s, 'N', 1, s->bcu_z, s->bcu_z + pl, s->dzc[0], s->dzc[n3], s->u, ib == 0, ib == 1);
+      set_bc_z(s, 'N', 1, s->bcv_z, s->bcv_z + pl, s->dzc[0], s->dzc[n3], s->v, ib == 0, ib == 1);
+    }
+}
+
+/* boundp (bound.f90:156-200) for the channel: ctype 'N' (pressure) or 'D' (eddy viscosity), boundary value 0 */
+static void boundp_channel(const cpu_t *s, char ctype, double *p) {
+  bound_xy_periodic(s, p);
+  set_bc_z(s, ctype, 1, NULL, NULL, s->dzc[0], s->dzc[s->n3], p, 1, 1);
+}
+
+static void fill_uvw(cpu_t *s, int is_correc) {
+  if (s->zwall) bounduvw_channel(s, is_correc);
+  else { bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w); }
+}
+static void fill_p(cpu_t *s, double *p, char ctype) {
+  if (s->zwall) boundp_channel(s, ctype, p); else bound_periodic(s, p);
+}
+
 /* ------------------------------------------------------------------------------------------------ SGS */
 /* sgs.f90:1019-1110 (s0 only) fused with the 'smag' model of sgs.f90:69-152; no walls -> fd = 1. */
 static void cmpt_sgs_smag(cpu_t *s) {
@@ -171,13 +316,49 @@ static void cmpt_sgs_smag(cpu_t *s) {
   const long sj = s->sj, sk = s->sk;
   const double dxi = s->dli[0], dyi = s->dli[1];
   const double *u = s->u, *v = s->v, *w = s->w;
+  const double *uo = s->u, *vo = s->v;                                          /* the un-extrapolated fields: van Driest wall shear */
+  if (s->zwall && (s->lwm[0] || s->lwm[1])) {
+    /* sgs.f90:84-90: copies, then extrapolate(iface = 1, 2, lwm) (682-767): wall-parallel ghosts on the wall-model
+     * faces by linear extrapolation; w (iface = 3) is not extrapolated on the z walls */
+    memcpy(s->wku, s->u, sizeof(double) * (size_t)s->ntot); memcpy(s->wkv, s->v, sizeof(double) * (size_t)s->ntot);
+    const double factor0 = s->dzc[0] * s->dzci[1], factor1 = s->dzc[n3] * s->dzci[n3 - 1];
+    double *wk[2] = {s->wku, s->wkv};
+    for (int m = 0; m < 2; m++) {
+      double *p = wk[m];
+#pragma omp parallel for schedule(static)
+      for (int j = 0; j <= n2 + 1; j++)
+        for (int i = 0; i <= n1 + 1; i++) {
+          if (s->lwm[0]) p[IDX(s, i, j, 0)] = (1. + factor0) * p[IDX(s, i, j, 1)] - factor0 * p[IDX(s, i, j, 2)];
+          if (s->lwm[1]) p[IDX(s, i, j, n3 + 1)] = (1. + factor1) * p[IDX(s, i, j, n3)] - factor1 * p[IDX(s, i, j, n3 - 1)];
+        }
+    }
+    u = s->wku; v = s->wkv;
+  }
+  const double visc = s->visc, visci = 1. / visc;
 #pragma omp parallel for collapse(2) schedule(static)
   for (int k = 1; k <= n3; k++)
     for (int j = 1; j <= n2; j++) {
       const double dzci_k = s->dzci[k], dzci_km = s->dzci[k - 1], dzfi_k = s->dzfi[k];
       const double dele = pow(s->dl[0] * s->dl[1] * s->dzf[k], 1. / 3.);
-      const double cs = C_SMAG * dele * 1.0;
       for (int i = 1; i <= n1; i++) {
+        double fd = 1.0;
+        if (s->zwall) {                                                          /* van Driest, sgs.f90:106-147: walls 5 and 6 only */
+          const double dw5 = s->zc[k], dw6 = s->l[2] - s->zc[k];
+          double dw_min, tauw_s;
+          if (dw5 <= dw6) {                                                      /* minloc: the first minimum */
+            const long c1 = IDX(s, i, j, 1), c0 = IDX(s, i, j, 0);
+            const double t1 = uo[c1] - uo[c0] + uo[c1 - 1] - uo[c0 - 1], t2 = vo[c1] - vo[c0] + vo[c1 - sj] - vo[c0 - sj];
+            dw_min = dw5; tauw_s = sqrt(t1 * t1 + t2 * t2) * s->dzci[0];
+          } else {
+            const long c1 = IDX(s, i, j, n3), c0 = IDX(s, i, j, n3 + 1);
+            const double t1 = uo[c1] - uo[c0] + uo[c1 - 1] - uo[c0 - 1], t2 = vo[c1] - vo[c0] + vo[c1 - sj] - vo[c0 - sj];
+            dw_min = dw6; tauw_s = sqrt(t1 * t1 + t2 * t2) * s->dzci[n3];
+          }
+          tauw_s = 0.5 * visc * tauw_s;
+          const double dw_plus = dw_min * sqrt(tauw_s) * visci;
+          fd = 1. - exp(-dw_plus / 25.);
+        }
+        const double cs = C_SMAG * dele * fd;
         const long c = IDX(s, i, j, k);
         double s11 = (u[c] - u[c - 1]) * dxi;
         double s22 = (v[c] - v[c - sj]) * dyi;
@@ -202,7 +383,7 @@ static void cmpt_sgs_smag(cpu_t *s) {
 }
 
 /* ---------------------------------------------------------------------------------------------- mom + rk */
-/* mom.f90:142-302 (explicit branch) and rk.f90:45-100; bforce = 0, nothing forced (TGV deck). */
+/* mom.f90:142-302 (explicit branch) and rk.f90:45-100, then cmpt_bulk_forcing (rk.f90:197-222). */
 static void rk_substep(cpu_t *s, const double rkpar[2], double dt) {
   const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
   const long sj = s->sj, sk = s->sk;
@@ -314,12 +495,40 @@ static void rk_substep(cpu_t *s, const double rkpar[2], double dt) {
       const double dzci_k = s->dzci[k];
       for (int i = 1; i <= n1; i++) {
         const long c = IDX(s, i, j, k), o = (long)(i - 1) + (long)n1 * ((long)(j - 1) + (long)n2 * (long)(k - 1));
-        uu[c] = uu[c] + factor1 * du[o] + factor2 * s->rhso[0][o] + factor12 * (0.0 - dxi * (p[c + 1] - p[c]));
-        vv[c] = vv[c] + factor1 * dv[o] + factor2 * s->rhso[1][o] + factor12 * (0.0 - dyi * (p[c + sj] - p[c]));
-        ww[c] = ww[c] + factor1 * dw[o] + factor2 * s->rhso[2][o] + factor12 * (0.0 - dzci_k * (p[c + sk] - p[c]));
+        uu[c] = uu[c] + factor1 * du[o] + factor2 * s->rhso[0][o] + factor12 * (s->bforce[0] - dxi * (p[c + 1] - p[c]));
+        vv[c] = vv[c] + factor1 * dv[o] + factor2 * s->rhso[1][o] + factor12 * (s->bforce[1] - dyi * (p[c + sj] - p[c]));
+        ww[c] = ww[c] + factor1 * dw[o] + factor2 * s->rhso[2][o] + factor12 * (s->bforce[2] - dzci_k * (p[c + sk] - p[c]));
       }
     }
   for (int m = 0; m < 3; m++) { double *tmp = s->rhs[m]; s->rhs[m] = s->rhso[m]; s->rhso[m] = tmp; } /* swap, rk.f90:92-100 */
+  /* cmpt_bulk_forcing (rk.f90:197-222) with bulk_mean (utils.f90:33-44): ONE sequential accumulation, i fastest -- the
+   * summation order is part of the result (the reference compiles that routine with -O0 for this reason) */
+  double *fld[3] = {s->u, s->v, s->w};
+  const double *gvr[3] = {s->gvr_f, s->gvr_f, s->gvr_c};
+  for (int m = 0; m < 3; m++) {
+    s->f[m] = 0.;
+    if (!s->is_forced[m]) continue;
+    double mean = 0.;
+    for (int k = 1; k <= n3; k++)
+      for (int j = 1; j <= n2; j++)
+        for (int i = 1; i <= n1; i++) mean = mean + fld[m][IDX(s, i, j, k)] * gvr[m][k];
+    s->f[m] = s->velf[m] - mean;
+  }
+}
+
+/* bulk_forcing, mom.f90:311-335 */
+static void bulk_forcing(cpu_t *s) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  double *fld[3] = {s->u, s->v, s->w};
+  for (int m = 0; m < 3; m++) {
+    if (!s->is_forced[m]) continue;
+    const double ff = s->f[m];
+    double *a = fld[m];
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int k = 1; k <= n3; k++)
+      for (int j = 1; j <= n2; j++)
+        for (int i = 1; i <= n1; i++) { const long c = IDX(s, i, j, k); a[c] = a[c] + ff; }
+  }
 }
 
 /* -------------------------------------------------------------------------------- pressure correction */
@@ -368,6 +577,26 @@ static void solver(cpu_t *s) { /* solver.f90:20-80, one rank: no transposes */
     }
     free(x); free(y);
   }
+  if (s->zwall) {                                                                /* gaussel, solver.f90:82-107 */
+#pragma omp parallel
+    {
+      const int n = n3;
+      size_t rowsz = (size_t)n1 * (size_t)n;
+      double *bb = (double *)malloc(sizeof(double) * rowsz), *p1 = (double *)malloc(sizeof(double) * rowsz), *d = (double *)malloc(sizeof(double) * rowsz);
+#pragma omp for schedule(static)
+      for (int j = 0; j < n2; j++) {
+        for (int l = 0; l < n; l++)
+          for (int i = 0; i < n1; i++) {
+            bb[(long)l * n1 + i] = s->b[l] + s->lambdaxy[i + (long)n1 * j];
+            p1[(long)l * n1 + i] = wk[i + (long)n1 * (j + (long)n2 * l)];
+          }
+        dgtsv_row(n1, n, s->a, bb, s->c, p1, d, s->eps);
+        for (int l = 0; l < n; l++)
+          for (int i = 0; i < n1; i++) wk[i + (long)n1 * (j + (long)n2 * l)] = p1[(long)l * n1 + i];
+      }
+      free(bb); free(p1); free(d);
+    }
+  } else
   /* gaussel_periodic, solver.f90:109-151 */
 #pragma omp parallel
   {
@@ -467,6 +696,40 @@ void *cales_cpu_new(int n1, int n2, int n3, const double *l, double visc, const 
   return s;
 }
 
+/* Channel family: walls at both z faces (cbcvel(:,3,:) = 'D', cbcpre(:,3) = 'N', cbcsgs(:,3) = 'D', boundary values 0),
+ * lwm[2] = lwm(0:1,3), hwm, forcing.  Call once, right after cales_cpu_new and before the fields are filled.
+ * initbc (bound.f90:846-863): index_wm; initsolver: tridmatrix fold-in b(1) += a(1), b(n) += c(n) for 'N'
+ * (initsolver.f90:149-164); grid_vol_ratio (main.f90:270-283). */
+int cales_cpu_set_channel(void *h, const double *zc, const double *zf, const int *lwm, double hwm, const int *is_forced,
+                          const double *velf, const double *bforce) {
+  cpu_t *s = (cpu_t *)h;
+  const int n3 = s->n3;
+  s->zwall = 1;
+  size_t nz = (size_t)(n3 + 2);
+  s->zc = (double *)malloc(8 * nz); s->zf = (double *)malloc(8 * nz); s->gvr_c = (double *)malloc(8 * nz); s->gvr_f = (double *)malloc(8 * nz);
+  for (int k = 0; k < n3 + 2; k++) {
+    s->zc[k] = zc[k]; s->zf[k] = zf[k];
+    s->gvr_c[k] = s->dl[0] * s->dl[1] * s->dzc[k] / (s->l[0] * s->l[1] * s->l[2]);
+    s->gvr_f[k] = s->dl[0] * s->dl[1] * s->dzf[k] / (s->l[0] * s->l[1] * s->l[2]);
+  }
+  for (int m = 0; m < 3; m++) { s->is_forced[m] = is_forced[m]; s->velf[m] = velf[m]; s->bforce[m] = bforce[m]; }
+  s->lwm[0] = lwm[0]; s->lwm[1] = lwm[1]; s->hwm = hwm;
+  if (lwm[0] || lwm[1]) {
+    if (lwm[0] != 1 && lwm[0] != 0) return 1;                                    /* WM_LOG only */
+    if (lwm[1] != 1 && lwm[1] != 0) return 1;
+    const size_t pl = (size_t)(s->n1 + 2) * (size_t)(s->n2 + 2);
+    s->bcu_z = (double *)calloc(2 * pl, 8); s->bcv_z = (double *)calloc(2 * pl, 8);
+    s->wku = (double *)calloc((size_t)s->ntot, 8); s->wkv = (double *)calloc((size_t)s->ntot, 8);
+    if (lwm[0]) { int k = 1; while (s->zc[k] < hwm) k = k + 1; s->index_wm[0] = k; }
+    if (lwm[1]) { int k = n3; while (s->l[2] - s->zc[k] < hwm) k = k - 1; s->index_wm[1] = k; }
+  }
+  s->b[0] = s->b[0] + 1. * s->a[0];
+  s->b[n3 - 1] = s->b[n3 - 1] + 1. * s->c[n3 - 1];
+  return 0;
+}
+
+double cales_cpu_forcing(void *h, int m) { return ((cpu_t *)h)->f[m]; }
+
 double *cales_cpu_field(void *h, int which) { /* 0 u, 1 v, 2 w, 3 p, 4 pp, 5 visct, 6 s0 */
   cpu_t *s = (cpu_t *)h;
   double *f[] = {s->u, s->v, s->w, s->p, s->pp, s->visct, s->s0};
@@ -478,12 +741,12 @@ double *cales_cpu_lambdaxy(void *h) { return ((cpu_t *)h)->lambdaxy; }
 /* main.f90:370-375: ghost fill of the initial fields and the first eddy viscosity */
 void cales_cpu_start(void *h) {
   cpu_t *s = (cpu_t *)h;
-  bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w); bound_periodic(s, s->p);
-  cmpt_sgs_smag(s); bound_periodic(s, s->visct);
+  fill_uvw(s, 0); fill_p(s, s->p, 'N');
+  cmpt_sgs_smag(s); fill_p(s, s->visct, 'D');
 }
 
 void cales_cpu_cmpt_sgs(void *h) { cmpt_sgs_smag((cpu_t *)h); }
-void cales_cpu_boundp(void *h, int which) { bound_periodic((cpu_t *)h, cales_cpu_field(h, which)); }
+void cales_cpu_boundp(void *h, int which) { fill_p((cpu_t *)h, cales_cpu_field(h, which), which == 5 ? 'D' : 'N'); }
 void cales_cpu_solver(void *h) { solver((cpu_t *)h); }
 void cales_cpu_fillps(void *h, double dti) { fillps((cpu_t *)h, dti); }
 void cales_cpu_correc(void *h, double dt) { correc((cpu_t *)h, dt); }
@@ -495,16 +758,17 @@ void cales_cpu_step(void *h, double dt) {
   for (int irk = 0; irk < 3; irk++) {
     const double dtrk = (RKCOEFF[irk][0] + RKCOEFF[irk][1]) * dt, dtrki = 1. / dtrk;
     rk_substep(s, RKCOEFF[irk], dt);                                             /* main.f90:420 */
-    bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w);   /* 493 */
-    fillps(s, dtrki);                                                            /* 495 (updt_rhs_b: nothing for P) */
+    bulk_forcing(s);                                                             /* 422 */
+    fill_uvw(s, 0);                                                              /* 493 */
+    fillps(s, dtrki);                                                            /* 495 (updt_rhs_b 496: the rhsb planes of P and of N with value 0 are zero) */
     solver(s);                                                                   /* 497 */
-    bound_periodic(s, s->pp);                                                    /* 498 */
+    fill_p(s, s->pp, 'N');                                                       /* 498 */
     correc(s, dtrk);                                                             /* 499 */
-    bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w);   /* 500 */
+    fill_uvw(s, 1);                                                              /* 500 */
     updatep(s);                                                                  /* 502 */
-    bound_periodic(s, s->p);                                                     /* 503 */
+    fill_p(s, s->p, 'N');                                                        /* 503 */
     cmpt_sgs_smag(s);                                                            /* 504 */
-    bound_periodic(s, s->visct);                                                 /* 506 */
+    fill_p(s, s->visct, 'D');                                                    /* 506 */
   }
 }
 
@@ -571,7 +835,8 @@ void cales_cpu_set_threads(int n) {
 void cales_cpu_free(void *h) {
   cpu_t *s = (cpu_t *)h;
   if (!s) return;
-  double *f[] = {s->u, s->v, s->w, s->p, s->pp, s->visct, s->s0, s->wk, s->dzc, s->dzf, s->dzci, s->dzfi, s->a, s->b, s->c, s->lambdaxy};
+  double *f[] = {s->u, s->v, s->w, s->p, s->pp, s->visct, s->s0, s->wk, s->dzc, s->dzf, s->dzci, s->dzfi, s->a, s->b, s->c, s->lambdaxy,
+                 s->zc, s->zf, s->gvr_c, s->gvr_f, s->bcu_z, s->bcv_z, s->wku, s->wkv};
   for (size_t m = 0; m < sizeof(f) / sizeof(f[0]); m++) free(f[m]);
   for (int m = 0; m < 3; m++) { free(s->rhs[m]); free(s->rhso[m]); }
   free(s->px.tw); free(s->py.tw); free(s);

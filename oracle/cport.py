@@ -1,5 +1,6 @@
-"""ctypes front end of oracle/c/libcales_cpu.so -- the C/OpenMP restatement of the tri-periodic, explicit,
-static-Smagorinsky RK3 step (see the header of oracle/c/cales_cpu.c for the reference lines it follows).
+"""ctypes front end of oracle/c/libcales_cpu.so -- the C/OpenMP restatement of the explicit, static-Smagorinsky RK3 step
+for the tri-periodic deck and for the plane channel (z walls, forcing, van Driest damping, optional log-law wall model;
+see the header of oracle/c/cales_cpu.c for the reference lines it follows).
 TEST INFRASTRUCTURE ONLY: the checker in tests/ and the CPU arm of bench.py."""
 import ctypes as C
 import os
@@ -35,6 +36,11 @@ def load():
         lib.cales_cpu_divmax.argtypes = [C.c_void_p]; lib.cales_cpu_divmax.restype = C.c_double
         lib.cales_cpu_chkdt.argtypes = [C.c_void_p]; lib.cales_cpu_chkdt.restype = C.c_double
         lib.cales_cpu_threads.restype = C.c_int
+        ip = C.POINTER(C.c_int)
+        lib.cales_cpu_set_channel.restype = C.c_int
+        lib.cales_cpu_set_channel.argtypes = [C.c_void_p, dp, dp, ip, C.c_double, ip, dp, dp]
+        lib.cales_cpu_forcing.restype = C.c_double
+        lib.cales_cpu_forcing.argtypes = [C.c_void_p, C.c_int]
         lib.cales_cpu_set_threads.argtypes = [C.c_int]; lib.cales_cpu_set_threads.restype = None
         _LIB = lib
     return _LIB
@@ -45,13 +51,28 @@ def _dp(a):
 
 
 class CSim:
-    """Mirror of oracle.main.Sim for an all-periodic 'smag' deck on one rank, backed by the C library."""
+    """Mirror of oracle.main.Sim for an all-periodic or plane-channel 'smag' deck on one rank, backed by the C library."""
+
+    @staticmethod
+    def kind(deck):
+        """'periodic', 'channel' or None (not covered by the C restatement)"""
+        if deck.sgstype.strip() != "smag" or deck.impdiff or tuple(deck.dims) != (1, 1):
+            return None
+        if (deck.cbcvel == "P").all() and (deck.cbcpre == "P").all() and not any(deck.is_forced) and not any(deck.bforce) \
+                and not deck.lwm.any():
+            return "periodic"
+        ok = (deck.cbcvel[:, 0:2, :] == "P").all() and (deck.cbcvel[:, 2, :] == "D").all() and (deck.cbcpre[:, 0:2] == "P").all() and \
+            (deck.cbcpre[:, 2] == "N").all() and (deck.cbcsgs[:, 0:2] == "P").all() and (deck.cbcsgs[:, 2] == "D").all() and \
+            not deck.bcvel.any() and not deck.bcpre.any() and not deck.bcsgs.any() and not deck.lwm[:, 0:2].any() and \
+            all(int(x) in (0, 1) for x in deck.lwm[:, 2])
+        return "channel" if ok else None
 
     def __init__(self, deck, threads=None):
         """threads: OpenMP threads to use (None = the OpenMP default, i.e. OMP_NUM_THREADS or all cores)."""
         from .initflow import initflow
         from .initgrid import initgrid
-        assert (deck.cbcvel == "P").all() and deck.sgstype == "smag" and not deck.impdiff and tuple(deck.dims) == (1, 1)
+        kind = self.kind(deck)
+        assert kind is not None, "deck not covered by the C restatement (oracle/c)"
         self.lib = load()
         if threads:
             self.lib.cales_cpu_set_threads(int(threads))
@@ -61,6 +82,12 @@ class CSim:
         l = np.array(deck.l, dtype=np.float64)
         self.h = C.c_void_p(self.lib.cales_cpu_new(n[0], n[1], n[2], _dp(l), float(deck.visc), _dp(np.ascontiguousarray(dzc)),
                                                    _dp(np.ascontiguousarray(dzf))))
+        if kind == "channel":
+            ia = lambda a: (C.c_int * len(a))(*[int(x) for x in a])
+            da = lambda a: (C.c_double * len(a))(*[float(x) for x in a])
+            rc = self.lib.cales_cpu_set_channel(self.h, _dp(np.ascontiguousarray(zc)), _dp(np.ascontiguousarray(zf)), ia(deck.lwm[:, 2]),
+                                                float(deck.hwm), ia([bool(x) for x in deck.is_forced]), da(deck.velf), da(deck.bforce))
+            assert rc == 0
         shp = (n[0] + 2, n[1] + 2, n[2] + 2)
         self.f = {nm: np.ctypeslib.as_array(self.lib.cales_cpu_field(self.h, i), shape=shp[::-1]).T for nm, i in FIELDS.items()}
         u, v, w, p = initflow(deck, (1, 1, 1), n, zc, zf, dzc, dzf)
@@ -80,6 +107,10 @@ class CSim:
             self.dt = d.dt_f if d.dt_f > 0. else min(d.cfl * self.dt_cfl, d.dtmax)
             return self.lib.cales_cpu_divmax(self.h)
         return None
+
+    def forcing(self):
+        """f(1:3) of the last substep (rk.f90:197-222)"""
+        return [self.lib.cales_cpu_forcing(self.h, m) for m in range(3)]
 
     def threads(self):
         return int(self.lib.cales_cpu_threads())

@@ -59,3 +59,47 @@ def test_c_port_poisson_residual():
         assert np.abs(lap - rhs).max() < max(1e-11 * np.abs(rhs).max(), 4. * floor)
     finally:
         c.close()
+
+
+# ---- the plane-channel family of the C restatement: z walls, forcing, stretched grids, van Driest, log-law wall model ----
+CHANNEL = {"channel_smag": dict(ng=(16, 12, 14), sgstype="smag"),
+           "channel_smag_uniform": dict(ng=(16, 12, 14), sgstype="smag", gr=0.),
+           "channel_wm_smag": dict(ng=(32, 16, 24), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.),
+           "channel_wm_smag_odd": dict(ng=(18, 10, 17), sgstype="smag", wall_model=True, gtype=6, gr=0., l=(12.8, 4.8, 2.), visci=43500.)}
+
+
+@pytest.mark.parametrize("case", list(CHANNEL))
+def test_c_port_channel_matches_numpy_oracle(case):
+    d = op.deck_channel(**CHANNEL[case])
+    assert CSim.kind(d) == "channel"
+    o, c = Sim(d), CSim(d)
+    try:
+        for nm, on in PAIRS[:4]:                              # ghost fill incl. the wall-model Neumann planes: bit-exact
+            assert np.array_equal(c.f[nm], getattr(o, on)[0]), nm
+        # first eddy viscosity: the same operations; libm's exp / pow vs numpy's may differ by an ulp in the van Driest factor
+        assert np.abs(c.f["visct"] - o.VISCT[0]).max() <= 4e-16 * np.abs(o.VISCT[0]).max()
+        assert abs(c.dt - o.dt) <= 1e-15 * o.dt
+        for _ in range(3):
+            divo = o.step(icheck=1)
+            divc = c.step(icheck=1)
+        assert divc < 1e-11 and divo[1] < 1e-11
+        vs = max(np.abs(getattr(o, on)[0]).max() for on in ("U", "V", "W"))
+        for nm, on in PAIRS:
+            a = c.f[nm][1:-1, 1:-1, 1:-1]
+            b = getattr(o, on)[0][1:-1, 1:-1, 1:-1]
+            if nm == "p":
+                a = a - a.mean(); b = b - b.mean()
+            scale = vs if nm in ("u", "v", "w") else np.abs(b).max()
+            assert np.abs(a - b).max() / scale < 1e-11, nm
+        assert abs(c.forcing()[0] - o.f[0]) <= 1e-11 * abs(o.f[0])      # bulk forcing of the last substep (sequential sums on both sides)
+        assert abs(c.dt - o.dt) <= 1e-12 * o.dt
+    finally:
+        c.close()
+
+
+def test_c_port_refuses_what_it_does_not_cover():
+    assert CSim.kind(op.deck_channel(ng=(8, 8, 8), sgstype="dsmag")) is None
+    assert CSim.kind(op.deck_duct(ng=(8, 8, 8))) is None and CSim.kind(op.deck_cavity(ng=(8, 8, 8))) is None
+    assert CSim.kind(op.deck_tgv(ng=(8, 8, 8))) == "periodic"
+    with pytest.raises(AssertionError):
+        CSim(op.deck_duct(ng=(8, 8, 8)))
