@@ -1,4 +1,4 @@
-"""Dry run of tests/test_zy_gpu_physics.py on the CPU: the same test bodies, with cales_b200.driver.Simulation replaced by a
+"""Dry run of tests/test_zzz_gpu_physics.py on the CPU: the same test bodies, with cales_b200.driver.Simulation replaced by a
 stand-in that drives the oracle through the same calls (init_flow/start/step/get/set_fields/cmpt_sgs).  Checks the HARNESS of
 the GPU physics tests -- indexing, normalisations, run lengths, thresholds -- where no GPU is available; on the GPU box the
 real library takes the stand-in's place."""
@@ -53,7 +53,7 @@ class OracleBackedSimulation:
 @pytest.fixture
 def physics(monkeypatch):
     import cales_b200.driver as drv
-    import test_zy_gpu_physics as mod
+    import test_zzz_gpu_physics as mod
     monkeypatch.setattr(drv, "Simulation", OracleBackedSimulation)
     return mod
 
