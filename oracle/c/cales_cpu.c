@@ -1,9 +1,11 @@
 /* oracle/c/cales_cpu.c -- TEST INFRASTRUCTURE ONLY (checker + CPU baseline; never on the product path).
  *
- * Plain C / OpenMP restatement of the reference's per-RK3-substep path, explicit diffusion, static Smagorinsky, one
+ * Plain C / OpenMP restatement of the reference's per-RK3-substep path, explicit diffusion, static or dynamic Smagorinsky, one
  * rank, for (i) the tri-periodic configuration (BASELINE config 2, the bench.py workload) and (ii) the plane channel:
  * periodic x and y, no-slip walls in z (velocity D, pressure N, eddy viscosity D), bulk-velocity forcing, stretched
- * grids, van Driest damping, and optionally the log-law wall model on the z walls (BASELINE configs 3 and 5):
+ * grids, van Driest damping, optionally the log-law wall model on the z walls, and the dynamic Smagorinsky model
+ * (sgs.f90:153-380 with filter3d 616-680, extrapolate 682-767, cmpt_alph2 769-822, interpolate 850-870, ave1d_channel
+ * 433-538) for both (BASELINE configs 1, 3 and 5):
  *   src/bound.f90:18-154 (bounduvw), 156-200 (boundp), 202-399 (set_bc: P, D and N, centred and face),
  *   src/wmodel.f90:19-335 (updt_wallmodelbc / cmpt_wallmodelbc case(3) / vel_relative / wallmodel),
  *   src/sgs.f90:69-152 with extrapolate 682-767, src/rk.f90:197-222 + src/utils.f90:16-47 + src/mom.f90:311-335
@@ -64,6 +66,8 @@ typedef struct {
   double *zc, *zf, *gvr_c, *gvr_f;     /* 0:n3+1 */
   double *bcu_z, *bcv_z;               /* wall-model Neumann planes bcu%z, bcv%z: (0:n1+1, 0:n2+1, 0:1) */
   double *wku, *wkv;                   /* copies of u, v for the extrapolation of cmpt_sgs (sgs.f90:84-90) */
+  int dsmag;                           /* 0: 'smag', 1: 'dsmag' */
+  double *dyn[24];                     /* work arrays of the dynamic model (sgs.f90:156-166): uc,vc,wc, uf,vf,wf, wk(6), sij(6), mij(6) */
 } cpu_t;
 
 #define IDX(s, i, j, k) ((long)(i) + (s)->sj * ((long)(j) + (long)((s)->n2 + 2) * (long)(k)))
@@ -275,25 +279,30 @@ static void cmpt_wallmodelbc_z(cpu_t *s, int ibound) {
     }
 }
 
-/* bounduvw (bound.f90:18-154) for the channel on one rank, is_updt_wm = .true. */
-static void bounduvw_channel(cpu_t *s, int is_correc) {
+/* bounduvw (bound.f90:18-154) for the channel on one rank.  is_updt_wm = 1: the fields are s->u, v, w and the wall-model
+ * planes bcu%z, bcv%z are recomputed first (125-128); is_updt_wm = 0 (the filtered velocities of the dynamic model,
+ * sgs.f90:256-257, with bcuf = bcvf = the initial planes = 0): the Neumann planes are zero. */
+static void bounduvw_ch(cpu_t *s, double *u, double *v, double *w, int is_correc, int is_updt_wm) {
   const int n3 = s->n3;
   const long pl = (long)(s->n1 + 2) * (s->n2 + 2);
-  bound_xy_periodic(s, s->u); bound_xy_periodic(s, s->v); bound_xy_periodic(s, s->w);
+  bound_xy_periodic(s, u); bound_xy_periodic(s, v); bound_xy_periodic(s, w);
   const int impose_norm_bc = !is_correc;                                         /* cbc(:,3,3) = 'D','D': never 'PP' */
-  if (impose_norm_bc) set_bc_z(s, 'D', 0, NULL, NULL, s->dzf[0], s->dzf[n3], s->w, 1, 1);
+  if (impose_norm_bc) set_bc_z(s, 'D', 0, NULL, NULL, s->dzf[0], s->dzf[n3], w, 1, 1);
   for (int ib = 0; ib < 2; ib++)
     if (s->lwm[ib] == 0) {
-      set_bc_z(s, 'D', 1, NULL, NULL, s->dzc[0], s->dzc[n3], s->u, ib == 0, ib == 1);
-      set_bc_z(s, 'D', 1, NULL, NULL, s->dzc[0], s->dzc[n3], s->v, ib == 0, ib == 1);
+      set_bc_z(s, 'D', 1, NULL, NULL, s->dzc[0], s->dzc[n3], u, ib == 0, ib == 1);
+      set_bc_z(s, 'D', 1, NULL, NULL, s->dzc[0], s->dzc[n3], v, ib == 0, ib == 1);
     }
-  for (int ib = 0; ib < 2; ib++) if (s->lwm[ib] != 0) cmpt_wallmodelbc_z(s, ib);   /* updt_wallmodelbc, 125-128 */
+  if (is_updt_wm)
+    for (int ib = 0; ib < 2; ib++) if (s->lwm[ib] != 0) cmpt_wallmodelbc_z(s, ib); /* updt_wallmodelbc, 125-128 */
   for (int ib = 0; ib < 2; ib++)
     if (s->lwm[ib] != 0) {                                                       /* cbcvel(:,3,1:2) = 'N' (initbc, bound.f90:746-758) */
-      set_bc_z(s, 'N', 1, s->bcu_z, s->bcu_z + pl, s->dzc[0], s->dzc[n3], s->u, ib == 0, ib == 1);
-      set_bc_z(s, 'N', 1, s->bcv_z, s->bcv_z + pl, s->dzc[0], s->dzc[n3], s->v, ib == 0, ib == 1);
+      const double *b0u = is_updt_wm ? s->bcu_z : NULL, *b0v = is_updt_wm ? s->bcv_z : NULL;
+      set_bc_z(s, 'N', 1, b0u, b0u ? b0u + pl : NULL, s->dzc[0], s->dzc[n3], u, ib == 0, ib == 1);
+      set_bc_z(s, 'N', 1, b0v, b0v ? b0v + pl : NULL, s->dzc[0], s->dzc[n3], v, ib == 0, ib == 1);
     }
 }
+static void bounduvw_channel(cpu_t *s, int is_correc) { bounduvw_ch(s, s->u, s->v, s->w, is_correc, 1); }
 
 /* boundp (bound.f90:156-200) for the channel: ctype 'N' (pressure) or 'D' (eddy viscosity), boundary value 0 */
 static void boundp_channel(const cpu_t *s, char ctype, double *p) {
@@ -381,6 +390,185 @@ static void cmpt_sgs_smag(cpu_t *s) {
       }
     }
 }
+
+/* ---------------------------------------------------------------------------------------- dynamic Smagorinsky */
+/* strain_rate with sij (sgs.f90:1019-1110): interior of s0 and of sij(1:6) = s11, s22, s33, s12, s13, s23 */
+static void strain_rate_sij(const cpu_t *s, const double *u, const double *v, const double *w, double *s0a, double *const sij[6]) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj, sk = s->sk;
+  const double dxi = s->dli[0], dyi = s->dli[1];
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++) {
+      const double dzci_k = s->dzci[k], dzci_km = s->dzci[k - 1], dzfi_k = s->dzfi[k];
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+        double s11 = (u[c] - u[c - 1]) * dxi;
+        double s22 = (v[c] - v[c - sj]) * dyi;
+        double s33 = (w[c] - w[c - sk]) * dzfi_k;
+        double s12 = .125 * ((u[c + sj] - u[c]) * dyi + (v[c + 1] - v[c]) * dxi +
+                             (u[c] - u[c - sj]) * dyi + (v[c + 1 - sj] - v[c - sj]) * dxi +
+                             (u[c - 1 + sj] - u[c - 1]) * dyi + (v[c] - v[c - 1]) * dxi +
+                             (u[c - 1] - u[c - 1 - sj]) * dyi + (v[c - sj] - v[c - 1 - sj]) * dxi);
+        double s13 = .125 * ((u[c + sk] - u[c]) * dzci_k + (w[c + 1] - w[c]) * dxi +
+                             (u[c] - u[c - sk]) * dzci_km + (w[c + 1 - sk] - w[c - sk]) * dxi +
+                             (u[c - 1 + sk] - u[c - 1]) * dzci_k + (w[c] - w[c - 1]) * dxi +
+                             (u[c - 1] - u[c - 1 - sk]) * dzci_km + (w[c - sk] - w[c - 1 - sk]) * dxi);
+        double s23 = .125 * ((v[c + sk] - v[c]) * dzci_k + (w[c + sj] - w[c]) * dyi +
+                             (v[c] - v[c - sk]) * dzci_km + (w[c + sj - sk] - w[c - sk]) * dyi +
+                             (v[c - sj + sk] - v[c - sj]) * dzci_k + (w[c] - w[c - sj]) * dyi +
+                             (v[c - sj] - v[c - sj - sk]) * dzci_km + (w[c - sk] - w[c - sj - sk]) * dyi);
+        s0a[c] = sqrt(2. * (s11 * s11 + s22 * s22 + s33 * s33 + 2. * (s12 * s12 + s13 * s13 + s23 * s23)));
+        sij[0][c] = s11; sij[1][c] = s22; sij[2][c] = s33; sij[3][c] = s12; sij[4][c] = s13; sij[5][c] = s23;
+      }
+    }
+}
+
+/* filter3d, sgs.f90:616-680: 27-point top hat, trapezoidal weights 8/4/2/1 over 64, the reference's summation order */
+static void filter3d(const cpu_t *s, const double *p, double *pf) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sj = s->sj, sk = s->sk;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++)
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+#define P(di, dj, dk) p[c + (di) + (dj) * sj + (dk) * sk]
+        pf[c] = (8. * (P(0, 0, 0)) +
+                 4. * (P(-1, 0, 0) + P(0, -1, 0) + P(0, 0, -1) + P(1, 0, 0) + P(0, 1, 0) + P(0, 0, 1)) +
+                 2. * (P(0, -1, -1) + P(-1, 0, -1) + P(-1, -1, 0) + P(0, 1, -1) + P(1, 0, -1) + P(1, -1, 0) +
+                       P(0, -1, 1) + P(-1, 0, 1) + P(-1, 1, 0) + P(0, 1, 1) + P(1, 0, 1) + P(1, 1, 0)) +
+                 1. * (P(-1, -1, -1) + P(1, -1, -1) + P(-1, 1, -1) + P(1, 1, -1) + P(-1, -1, 1) + P(1, -1, 1) + P(-1, 1, 1) + P(1, 1, 1))) / 64.;
+#undef P
+      }
+}
+
+/* extrapolate (sgs.f90:682-767) on the z faces, whole planes: with `cbc` (factor 1, faces with cbcvel(:,3,3) = 'D': both walls
+ * of the channel) or with `lwm` (grid-ratio factors, wall-model faces only) */
+static void extrapolate_z(const cpu_t *s, double *p, int use_lwm) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  if (!s->zwall) return;
+  const double f0 = use_lwm ? s->dzc[0] * s->dzci[1] : 1., f1 = use_lwm ? s->dzc[n3] * s->dzci[n3 - 1] : 1.;
+  const int do0 = use_lwm ? s->lwm[0] != 0 : 1, do1 = use_lwm ? s->lwm[1] != 0 : 1;
+#pragma omp parallel for schedule(static)
+  for (int j = 0; j <= n2 + 1; j++)
+    for (int i = 0; i <= n1 + 1; i++) {
+      if (do0) p[IDX(s, i, j, 0)] = (1. + f0) * p[IDX(s, i, j, 1)] - f0 * p[IDX(s, i, j, 2)];
+      if (do1) p[IDX(s, i, j, n3 + 1)] = (1. + f1) * p[IDX(s, i, j, n3)] - f1 * p[IDX(s, i, j, n3 - 1)];
+    }
+}
+
+/* ave1d_channel(idir = 3), sgs.f90:455-482: per-level sequential sum (i fastest), times the area ratio, written back to the
+ * whole plane */
+static void ave1d_channel_z(const cpu_t *s, double *p) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const double grid_area_ratio = s->dl[0] * s->dl[1] / (s->l[0] * s->l[1]);
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= n3; k++) {
+    double p1d_s = 0.;
+    for (int j = 1; j <= n2; j++)
+      for (int i = 1; i <= n1; i++) p1d_s = p1d_s + p[IDX(s, i, j, k)];
+    const double p1d = p1d_s * grid_area_ratio;
+    for (int j = 0; j <= n2 + 1; j++)
+      for (int i = 0; i <= n1 + 1; i++) p[IDX(s, i, j, k)] = p1d;
+  }
+}
+
+/* cmpt_sgs('dsmag'), sgs.f90:153-380, 3-D test filter, plane averaging of the hard-wired _CHANNEL build (sgs.f90:8) */
+static void cmpt_sgs_dsmag(cpu_t *s) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const size_t nb = sizeof(double) * (size_t)s->ntot;
+  if (!s->dyn[0]) for (int m = 0; m < 24; m++) s->dyn[m] = (double *)calloc((size_t)s->ntot, 8);   /* 154-166 */
+  double *uc = s->dyn[0], *vc = s->dyn[1], *wc = s->dyn[2], *uf = s->dyn[3], *vf = s->dyn[4], *wf = s->dyn[5];
+  double *wk[6], *sij[6], *mij[6];
+  for (int m = 0; m < 6; m++) { wk[m] = s->dyn[6 + m]; sij[m] = s->dyn[12 + m]; mij[m] = s->dyn[18 + m]; }
+  double *s0 = s->s0;
+  const char sg = 'D';                                                           /* cbcsgs(:,3) of the channel; periodic decks ignore it */
+  /* 173-185 */
+  memcpy(wk[0], s->u, nb); memcpy(wk[1], s->v, nb); memcpy(wk[2], s->w, nb);
+  extrapolate_z(s, wk[0], 1); extrapolate_z(s, wk[1], 1);                        /* iface = 3 (w): not on the z faces */
+  strain_rate_sij(s, wk[0], wk[1], wk[2], s0, sij);
+  memcpy(s->visct, s0, nb);
+  /* Mij, 191-223 */
+  fill_p(s, s0, sg);
+  for (int m = 0; m < 6; m++) fill_p(s, sij[m], sg);
+  for (int m = 0; m < 6; m++) {
+    double *a = wk[m]; const double *b = sij[m];
+#pragma omp parallel for schedule(static)
+    for (long q = 0; q < s->ntot; q++) a[q] = s0[q] * b[q];
+  }
+  for (int m = 0; m < 6; m++) extrapolate_z(s, wk[m], 0);
+  for (int m = 0; m < 6; m++) filter3d(s, wk[m], mij[m]);
+  /* 225-235 */
+  memcpy(wk[0], s->u, nb); memcpy(wk[1], s->v, nb); memcpy(wk[2], s->w, nb);
+  extrapolate_z(s, wk[0], 0); extrapolate_z(s, wk[1], 0);                        /* iface = 3: no */
+  filter3d(s, wk[0], uf); filter3d(s, wk[1], vf); filter3d(s, wk[2], wf);
+  /* 256-272 */
+  if (s->zwall) bounduvw_ch(s, uf, vf, wf, 0, 0);
+  else { bound_periodic(s, uf); bound_periodic(s, vf); bound_periodic(s, wf); }
+  extrapolate_z(s, uf, 1); extrapolate_z(s, vf, 1);
+  strain_rate_sij(s, uf, vf, wf, s0, sij);
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++) {
+      const double alph2 = (s->zwall && (k == 1 || k == n3)) ? 2.52 : 4.00;      /* cmpt_alph2, 769-822 */
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+        for (int m = 0; m < 6; m++) mij[m][c] = 2. * (mij[m][c] - alph2 * s0[c] * sij[m][c]);
+      }
+    }
+  /* Lij (stored in sij), 277-315 */
+  double **lij = sij;
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++)
+      for (int i = 1; i <= n1; i++) {                                            /* interpolate, 860-869 */
+        const long c = IDX(s, i, j, k);
+        uc[c] = 0.5 * (s->u[c] + s->u[c - 1]);
+        vc[c] = 0.5 * (s->v[c] + s->v[c - s->sj]);
+        wc[c] = 0.5 * (s->w[c] + s->w[c - s->sk]);
+      }
+  fill_p(s, uc, sg); fill_p(s, vc, sg); fill_p(s, wc, sg);
+#pragma omp parallel for schedule(static)
+  for (long q = 0; q < s->ntot; q++) {
+    wk[0][q] = uc[q] * uc[q]; wk[1][q] = vc[q] * vc[q]; wk[2][q] = wc[q] * wc[q];
+    wk[3][q] = uc[q] * vc[q]; wk[4][q] = uc[q] * wc[q]; wk[5][q] = vc[q] * wc[q];
+  }
+  for (int m = 0; m < 6; m++) extrapolate_z(s, wk[m], 0);
+  for (int m = 0; m < 6; m++) filter3d(s, wk[m], lij[m]);
+  extrapolate_z(s, uc, 0); extrapolate_z(s, vc, 0); extrapolate_z(s, wc, 0);
+  filter3d(s, uc, uf); filter3d(s, vc, vf); filter3d(s, wc, wf);
+  /* 328-358 */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int j = 1; j <= n2; j++)
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+        double mij_s[6], lij_s[6];
+        for (int m = 0; m < 6; m++) { mij_s[m] = mij[m][c]; lij_s[m] = lij[m][c]; }
+        lij_s[0] = lij_s[0] - uf[c] * uf[c];
+        lij_s[1] = lij_s[1] - vf[c] * vf[c];
+        lij_s[2] = lij_s[2] - wf[c] * wf[c];
+        lij_s[3] = lij_s[3] - uf[c] * vf[c];
+        lij_s[4] = lij_s[4] - uf[c] * wf[c];
+        lij_s[5] = lij_s[5] - vf[c] * wf[c];
+        wk[0][c] = mij_s[0] * lij_s[0] + mij_s[1] * lij_s[1] + mij_s[2] * lij_s[2] +
+                   (mij_s[3] * lij_s[3] + mij_s[4] * lij_s[4] + mij_s[5] * lij_s[5]) * 2.;
+        wk[1][c] = mij_s[0] * mij_s[0] + mij_s[1] * mij_s[1] + mij_s[2] * mij_s[2] +
+                   (mij_s[3] * mij_s[3] + mij_s[4] * mij_s[4] + mij_s[5] * mij_s[5]) * 2.;
+      }
+  ave1d_channel_z(s, wk[0]); ave1d_channel_z(s, wk[1]);                          /* 363-364 */
+#pragma omp parallel for collapse(2) schedule(static)
+  for (int k = 1; k <= n3; k++)                                                  /* 372-380 */
+    for (int j = 1; j <= n2; j++)
+      for (int i = 1; i <= n1; i++) {
+        const long c = IDX(s, i, j, k);
+        double t = s->visct[c] * wk[0][c] / wk[1][c];
+        s->visct[c] = fmax(t, 0.);
+      }
+}
+
+static void cmpt_sgs(cpu_t *s) { if (s->dsmag) cmpt_sgs_dsmag(s); else cmpt_sgs_smag(s); }
 
 /* ---------------------------------------------------------------------------------------------- mom + rk */
 /* mom.f90:142-302 (explicit branch) and rk.f90:45-100, then cmpt_bulk_forcing (rk.f90:197-222). */
@@ -742,10 +930,11 @@ double *cales_cpu_lambdaxy(void *h) { return ((cpu_t *)h)->lambdaxy; }
 void cales_cpu_start(void *h) {
   cpu_t *s = (cpu_t *)h;
   fill_uvw(s, 0); fill_p(s, s->p, 'N');
-  cmpt_sgs_smag(s); fill_p(s, s->visct, 'D');
+  cmpt_sgs(s); fill_p(s, s->visct, 'D');
 }
 
-void cales_cpu_cmpt_sgs(void *h) { cmpt_sgs_smag((cpu_t *)h); }
+void cales_cpu_cmpt_sgs(void *h) { cmpt_sgs((cpu_t *)h); }
+void cales_cpu_set_sgs(void *h, int dsmag) { ((cpu_t *)h)->dsmag = dsmag; }
 void cales_cpu_boundp(void *h, int which) { fill_p((cpu_t *)h, cales_cpu_field(h, which), which == 5 ? 'D' : 'N'); }
 void cales_cpu_solver(void *h) { solver((cpu_t *)h); }
 void cales_cpu_fillps(void *h, double dti) { fillps((cpu_t *)h, dti); }
@@ -767,7 +956,7 @@ void cales_cpu_step(void *h, double dt) {
     fill_uvw(s, 1);                                                              /* 500 */
     updatep(s);                                                                  /* 502 */
     fill_p(s, s->p, 'N');                                                        /* 503 */
-    cmpt_sgs_smag(s);                                                            /* 504 */
+    cmpt_sgs(s);                                                                 /* 504 */
     fill_p(s, s->visct, 'D');                                                    /* 506 */
   }
 }
@@ -839,5 +1028,6 @@ void cales_cpu_free(void *h) {
                  s->zc, s->zf, s->gvr_c, s->gvr_f, s->bcu_z, s->bcv_z, s->wku, s->wkv};
   for (size_t m = 0; m < sizeof(f) / sizeof(f[0]); m++) free(f[m]);
   for (int m = 0; m < 3; m++) { free(s->rhs[m]); free(s->rhso[m]); }
+  for (int m = 0; m < 24; m++) free(s->dyn[m]);
   free(s->px.tw); free(s->py.tw); free(s);
 }

@@ -1,5 +1,5 @@
-"""ctypes front end of oracle/c/libcales_cpu.so -- the C/OpenMP restatement of the explicit, static-Smagorinsky RK3 step
-for the tri-periodic deck and for the plane channel (z walls, forcing, van Driest damping, optional log-law wall model;
+"""ctypes front end of oracle/c/libcales_cpu.so -- the C/OpenMP restatement of the explicit RK3 step with the static or the
+dynamic Smagorinsky model for the tri-periodic deck and for the plane channel (z walls, forcing, van Driest damping, optional log-law wall model;
 see the header of oracle/c/cales_cpu.c for the reference lines it follows).
 TEST INFRASTRUCTURE ONLY: the checker in tests/ and the CPU arm of bench.py."""
 import ctypes as C
@@ -39,6 +39,8 @@ def load():
         ip = C.POINTER(C.c_int)
         lib.cales_cpu_set_channel.restype = C.c_int
         lib.cales_cpu_set_channel.argtypes = [C.c_void_p, dp, dp, ip, C.c_double, ip, dp, dp]
+        lib.cales_cpu_set_sgs.restype = None
+        lib.cales_cpu_set_sgs.argtypes = [C.c_void_p, C.c_int]
         lib.cales_cpu_forcing.restype = C.c_double
         lib.cales_cpu_forcing.argtypes = [C.c_void_p, C.c_int]
         lib.cales_cpu_set_threads.argtypes = [C.c_int]; lib.cales_cpu_set_threads.restype = None
@@ -56,7 +58,7 @@ class CSim:
     @staticmethod
     def kind(deck):
         """'periodic', 'channel' or None (not covered by the C restatement)"""
-        if deck.sgstype.strip() != "smag" or deck.impdiff or tuple(deck.dims) != (1, 1):
+        if deck.sgstype.strip() not in ("smag", "dsmag") or deck.impdiff or tuple(deck.dims) != (1, 1):
             return None
         if (deck.cbcvel == "P").all() and (deck.cbcpre == "P").all() and not any(deck.is_forced) and not any(deck.bforce) \
                 and not deck.lwm.any():
@@ -88,6 +90,7 @@ class CSim:
             rc = self.lib.cales_cpu_set_channel(self.h, _dp(np.ascontiguousarray(zc)), _dp(np.ascontiguousarray(zf)), ia(deck.lwm[:, 2]),
                                                 float(deck.hwm), ia([bool(x) for x in deck.is_forced]), da(deck.velf), da(deck.bforce))
             assert rc == 0
+        self.lib.cales_cpu_set_sgs(self.h, 1 if deck.sgstype.strip() == "dsmag" else 0)
         shp = (n[0] + 2, n[1] + 2, n[2] + 2)
         self.f = {nm: np.ctypeslib.as_array(self.lib.cales_cpu_field(self.h, i), shape=shp[::-1]).T for nm, i in FIELDS.items()}
         u, v, w, p = initflow(deck, (1, 1, 1), n, zc, zf, dzc, dzf)

@@ -18,14 +18,14 @@ def _errs(g, ref, names=("u", "v", "w", "p", "visct")):
     return out
 
 
-def c_port_errs(kw, nsteps, ref):
+def c_port_errs(kw, nsteps, ref, icheck=1):
     """the C/OpenMP restatement (oracle/c) on the same channel deck and number of steps, against the numpy oracle's fields `ref`
     (interior arrays keyed u, v, w, p, visct): the two independently written restatements must agree to round-off"""
     import oracle.param as op
     from oracle.cport import CSim
     c = CSim(op.deck_channel(**kw))
     for _ in range(nsteps):
-        c.step(icheck=1)
+        c.step(icheck=icheck)
     vs = max(float(np.abs(ref[k][1:-1, 1:-1, 1:-1]).max()) for k in ("u", "v", "w"))
     out = {nm: relerr(c.f[nm], ref[nm], demean=(nm == "p"), scale=field_scale(nm, ref[nm], vs)) for nm in ("u", "v", "w", "p", "visct")}
     c.close()
@@ -94,6 +94,8 @@ def test_fullsize_config1_channel64_dsmag_100_steps():
         for g in gs:
             g.step(icheck=10)
     ref = {nm: getattr(o, nm.upper())[0] for nm in ("u", "v", "w", "p", "visct")}
+    cerr = c_port_errs(kw, 100, ref, icheck=10)              # the second CPU restatement (oracle/c, dynamic model included)
+    assert all(v <= 1e-12 for v in cerr.values()), cerr
     for g in gs:
         errs = _errs(g, ref)
         assert all(v <= 1e-10 for v in errs.values()), (g.lib.arith, errs)
