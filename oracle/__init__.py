@@ -14,7 +14,14 @@ vectors or tests for this path, so this oracle is pinned only by
      divergence after projection, Thomas vs dense solve, transform round
      trips, 2-D Taylor-Green decay, polynomial checks of mom_xyz_ad), and
  (ii) the cuDecomp/2decomp transpose-test convention for the index maps
-     (payload = global linear index, compared exactly).
+     (payload = global linear index, compared exactly),
+ (iii) physics known-answer runs (tests/test_oracle_physics.py: discrete
+     Poiseuille steady state and its pressure gradient, duct series solution
+     at second order, Smagorinsky / van Driest / dynamic-model closed forms), and
+ (iv) a second restatement written independently from the same Fortran lines
+     (oracle/c: C + OpenMP; static and dynamic Smagorinsky, tri-periodic and
+     plane-channel decks incl. the wall model), which reproduces this one bit
+     for bit wherever no transform is involved (tests/test_oracle_c.py).
 Transforms use scipy.fft (pocketfft), whose unnormalised rfft/DCT/DST kinds
 have the same definitions as the FFTW R2HC/HC2R/REDFT/RODFT kinds the
 reference plans (src/fft.f90:192-245).
