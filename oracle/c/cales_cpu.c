@@ -5,7 +5,9 @@
  * periodic x and y, no-slip walls in z (velocity D, pressure N, eddy viscosity D), bulk-velocity forcing, stretched
  * grids, van Driest damping, optionally the log-law wall model on the z walls, and the dynamic Smagorinsky model
  * (sgs.f90:153-380 with filter3d 616-680, extrapolate 682-767, cmpt_alph2 769-822, interpolate 850-870, ave1d_channel
- * 433-538) for both (BASELINE configs 1, 3 and 5):
+ * 433-538) for both (BASELINE configs 1, 3 and 5); (iii) static Smagorinsky with walls in x and / or y as well -- square
+ * duct, lid-driven cavity (BASELINE config 4): the general set_bc sequence of bounduvw / boundp, van Driest distance over all
+ * walls, and the cell-centred Neumann-Neumann transforms REDFT10 / REDFT01 (fft.f90:192-245) through the same complex FFT:
  *   src/bound.f90:18-154 (bounduvw), 156-200 (boundp), 202-399 (set_bc: P, D and N, centred and face),
  *   src/wmodel.f90:19-335 (updt_wallmodelbc / cmpt_wallmodelbc case(3) / vel_relative / wallmodel),
  *   src/sgs.f90:69-152 with extrapolate 682-767, src/rk.f90:197-222 + src/utils.f90:16-47 + src/mom.f90:311-335
@@ -44,6 +46,7 @@ typedef struct { double re, im; } cpx;
 typedef struct {
   int n, nfac, fac[32];
   cpx *tw; /* tw[k] = exp(-2 pi i k / n) */
+  cpx *tq; /* tq[k] = exp(-i pi k / (2 n)): the quarter-wave factors of the cosine transforms */
 } fftplan;
 
 typedef struct {
@@ -67,6 +70,10 @@ typedef struct {
   double *bcu_z, *bcv_z;               /* wall-model Neumann planes bcu%z, bcv%z: (0:n1+1, 0:n2+1, 0:1) */
   double *wku, *wkv;                   /* copies of u, v for the extrapolation of cmpt_sgs (sgs.f90:84-90) */
   int dsmag;                           /* 0: 'smag', 1: 'dsmag' */
+  char kx, ky;                         /* transform kind of x and y: 'P' (R2HC/HC2R) or 'N' (REDFT10/REDFT01) */
+  int gen;                             /* 1: walls in x and / or y as well (duct, cavity): the general ghost fills below */
+  char cbcvel[2][3][3], cbcpre[2][3], cbcsgs[2][3];   /* [ib][idir][ivel] */
+  double bcvel[2][3][3];
   double *dyn[24];                     /* work arrays of the dynamic model (sgs.f90:156-166): uc,vc,wc, uf,vf,wf, wk(6), sij(6), mij(6) */
 } cpu_t;
 
@@ -81,6 +88,8 @@ static void plan_init(fftplan *pl, int n) {
   pl->tw = (cpx *)malloc(sizeof(cpx) * (size_t)n);
   const double pi = acos(-1.0);
   for (int k = 0; k < n; k++) { pl->tw[k].re = cos(2.0 * pi * k / n); pl->tw[k].im = -sin(2.0 * pi * k / n); }
+  pl->tq = (cpx *)malloc(sizeof(cpx) * (size_t)n);
+  for (int k = 0; k < n; k++) { pl->tq[k].re = cos(pi * k / (2.0 * n)); pl->tq[k].im = -sin(pi * k / (2.0 * n)); }
 }
 
 /* Stockham autosort, decimation in frequency; sign=-1 forward, +1 backward (conjugated twiddles).
@@ -169,6 +178,49 @@ static void hc2r_pair(const fftplan *pl, double *a, double *b, long st, cpx *x, 
   for (int j = 0; j < n; j++) { a[j * st] = z[j].re; if (b) b[j * st] = z[j].im; }
 }
 
+/* FFTW REDFT10 (DCT-II, Y_k = 2 sum_j X_j cos(pi (j + 1/2) k / n)) of two real lines in place, through ONE complex transform
+ * of length n (Makhoul's even/odd re-ordering; the pair is separated as in r2hc_pair).  fft.f90:221-244 plans these kinds
+ * for Neumann-Neumann, cell-centred directions. */
+static void redft10_pair(const fftplan *pl, double *a, double *b, long st, cpx *x, cpx *y) {
+  const int n = pl->n, h = (n + 1) / 2;
+  for (int j = 0; j < h; j++) { x[j].re = a[(long)(2 * j) * st]; x[j].im = b ? b[(long)(2 * j) * st] : 0.0; }
+  for (int j = 0; j < n / 2; j++) { x[n - 1 - j].re = a[(long)(2 * j + 1) * st]; x[n - 1 - j].im = b ? b[(long)(2 * j + 1) * st] : 0.0; }
+  cpx *z = fft_exec(pl, x, y, -1);
+  for (int k = 0; k < n; k++) {
+    const cpx zk = z[k], zc = z[(n - k) % n], t = pl->tq[k];
+    const double are = 0.5 * (zk.re + zc.re), aim = 0.5 * (zk.im - zc.im);
+    const double bre = 0.5 * (zk.im + zc.im), bim = -0.5 * (zk.re - zc.re);
+    a[(long)k * st] = 2. * (are * t.re - aim * t.im);
+    if (b) b[(long)k * st] = 2. * (bre * t.re - bim * t.im);
+  }
+}
+
+/* FFTW REDFT01 (DCT-III, Y_j = X_0 + 2 sum_{k>=1} X_k cos(pi k (j + 1/2) / n)), the unnormalised inverse of REDFT10 (x 2n):
+ * W_k = e^{i pi k / 2n} (X_k - i X_{n-k}), X_n = 0, is Hermitian, so its backward transform is real and two lines ride
+ * one complex transform. */
+static void redft01_pair(const fftplan *pl, double *a, double *b, long st, cpx *x, cpx *y) {
+  const int n = pl->n, h = (n + 1) / 2;
+  for (int k = 0; k < n; k++) {
+    const double xa = a[(long)k * st], xan = k ? a[(long)(n - k) * st] : 0.0;
+    const double xb = b ? b[(long)k * st] : 0.0, xbn = (b && k) ? b[(long)(n - k) * st] : 0.0;
+    const double cr = pl->tq[k].re, ci = -pl->tq[k].im;
+    const double war = cr * xa + ci * xan, wai = ci * xa - cr * xan;
+    const double wbr = cr * xb + ci * xbn, wbi = ci * xb - cr * xbn;
+    x[k].re = war - wbi; x[k].im = wai + wbr;
+  }
+  cpx *z = fft_exec(pl, x, y, +1);
+  for (int j = 0; j < h; j++) { a[(long)(2 * j) * st] = z[j].re; if (b) b[(long)(2 * j) * st] = z[j].im; }
+  for (int j = 0; j < n / 2; j++) { a[(long)(2 * j + 1) * st] = z[n - 1 - j].re; if (b) b[(long)(2 * j + 1) * st] = z[n - 1 - j].im; }
+}
+
+/* forward / backward transform of a pair of lines by the BC pair of the direction: 'P' R2HC / HC2R, 'N' REDFT10 / REDFT01 */
+static void fwd_pair(char kind, const fftplan *pl, double *a, double *b, long st, cpx *x, cpx *y) {
+  if (kind == 'N') redft10_pair(pl, a, b, st, x, y); else r2hc_pair(pl, a, b, st, x, y);
+}
+static void bwd_pair(char kind, const fftplan *pl, double *a, double *b, long st, cpx *x, cpx *y) {
+  if (kind == 'N') redft01_pair(pl, a, b, st, x, y); else hc2r_pair(pl, a, b, st, x, y);
+}
+
 /* ------------------------------------------------------------------------------------------ ghost fill */
 /* bound.f90:175-199 / 42-46 with all-periodic BCs on one rank: direction by direction, full extent. */
 static void bound_periodic(const cpu_t *s, double *p) {
@@ -218,6 +270,72 @@ static void set_bc_z(const cpu_t *s, char ctype, int centered, const double *bc0
         if (do1) p[q + pl * (n + 1)] = dr1 * b1 + sgn * p[q + pl * n];
       }
     }
+}
+
+/* set_bc (bound.f90:202-399) for a face of any direction with a CONSTANT boundary value (all the decks covered here), on
+ * the whole plane, ghost rows of the other directions included */
+static void set_bc_c(const cpu_t *s, char ctype, int ibound, int idir, int centered, double bc, double dr, double *p) {
+  const int nn[3] = {s->n1, s->n2, s->n3};
+  const long st[3] = {1, s->sj, s->sk};
+  const int n = nn[idir], d1 = (idir + 1) % 3, d2 = (idir + 2) % 3;
+  const long sd = st[idir];
+  const double sgn = (ctype == 'D' && centered) ? -1. : 1.;
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b <= nn[d2] + 1; b++)
+    for (int a = 0; a <= nn[d1] + 1; a++) {
+      double *q = p + (long)a * st[d1] + (long)b * st[d2];                       /* q[m * sd] = p(.., m, ..) */
+      if (ctype == 'P') {                                                        /* 232-248 */
+        q[0] = q[(long)n * sd]; q[(long)(n + 1) * sd] = q[sd];
+      } else if (ctype == 'D' && centered) {                                     /* 250-282 */
+        if (ibound == 0) q[0] = 2. * bc + sgn * q[sd];
+        else q[(long)(n + 1) * sd] = 2. * bc + sgn * q[(long)n * sd];
+      } else if (ctype == 'D') {                                                 /* 283-319 */
+        if (ibound == 0) q[0] = bc;
+        else { q[(long)(n + 1) * sd] = q[(long)(n - 1) * sd]; q[(long)n * sd] = bc; }
+      } else if (ctype == 'N' && centered) {                                     /* 320-353 */
+        if (ibound == 0) q[0] = -dr * bc + sgn * q[sd];
+        else q[(long)(n + 1) * sd] = dr * bc + sgn * q[(long)n * sd];
+      } else if (ctype == 'N') {                                                 /* 354-396 */
+        if (ibound == 0) q[0] = -dr * bc + q[sd];
+        else { q[(long)(n + 1) * sd] = q[(long)n * sd]; q[(long)n * sd] = dr * bc + q[(long)(n - 1) * sd]; }
+      }
+    }
+}
+
+/* halo exchange of one rank (bound.f90:619-696): a decomposed direction (y, z) that is periodic is its own neighbour */
+static void halo_self(const cpu_t *s, int idir, double *p) { set_bc_c(s, 'P', 0, idir, 1, 0., 0., p); }
+
+/* bounduvw (bound.f90:18-154) in general: walls in any direction, no wall model (lwm = 0 everywhere) */
+static void bounduvw_gen(cpu_t *s, double *u, double *v, double *w, int is_correc) {
+  double *f[3] = {u, v, w};
+  for (int idir = 1; idir < 3; idir++)                                           /* updthalo, 42-46: x is the pencil direction */
+    if (s->cbcpre[0][idir] == 'P') for (int m = 0; m < 3; m++) halo_self(s, idir, f[m]);
+  const int n3 = s->n3;
+  for (int idir = 0; idir < 3; idir++) {
+    const int is_bound = idir == 0 || s->cbcpre[0][idir] != 'P';                 /* initmpi.f90:169-176 */
+    if (!is_bound) continue;
+    const int pp = s->cbcvel[0][idir][idir] == 'P' && s->cbcvel[1][idir][idir] == 'P';
+    const int impose_norm_bc = !is_correc || pp;
+    for (int ib = 0; ib < 2; ib++) {
+      const double drf = idir == 0 ? s->dl[0] : idir == 1 ? s->dl[1] : (ib == 0 ? s->dzf[0] : s->dzf[n3]);
+      const double drc = idir == 0 ? s->dl[0] : idir == 1 ? s->dl[1] : (ib == 0 ? s->dzc[0] : s->dzc[n3]);
+      if (impose_norm_bc) set_bc_c(s, s->cbcvel[ib][idir][idir], ib, idir, 0, s->bcvel[ib][idir][idir], drf, f[idir]);
+      for (int m = 0; m < 3; m++)                                                /* the two wall-parallel components, in index order */
+        if (m != idir) set_bc_c(s, s->cbcvel[ib][idir][m], ib, idir, 1, s->bcvel[ib][idir][m], drc, f[m]);
+    }
+  }
+}
+
+/* boundp (bound.f90:156-200) in general, boundary values 0 */
+static void boundp_gen(const cpu_t *s, const char cbc[2][3], double *p) {
+  for (int idir = 1; idir < 3; idir++) if (cbc[0][idir] == 'P') halo_self(s, idir, p);
+  const int n3 = s->n3;
+  for (int idir = 0; idir < 3; idir++) {
+    const int is_bound = idir == 0 || s->cbcpre[0][idir] != 'P';
+    if (!is_bound) continue;
+    for (int ib = 0; ib < 2; ib++)
+      set_bc_c(s, cbc[ib][idir], ib, idir, 1, 0., idir == 0 ? s->dl[0] : idir == 1 ? s->dl[1] : (ib == 0 ? s->dzc[0] : s->dzc[n3]), p);
+  }
 }
 
 /* wmodel.f90:288-335, WM_LOG */
@@ -311,11 +429,13 @@ static void boundp_channel(const cpu_t *s, char ctype, double *p) {
 }
 
 static void fill_uvw(cpu_t *s, int is_correc) {
-  if (s->zwall) bounduvw_channel(s, is_correc);
+  if (s->gen) bounduvw_gen(s, s->u, s->v, s->w, is_correc);
+  else if (s->zwall) bounduvw_channel(s, is_correc);
   else { bound_periodic(s, s->u); bound_periodic(s, s->v); bound_periodic(s, s->w); }
 }
 static void fill_p(cpu_t *s, double *p, char ctype) {
-  if (s->zwall) boundp_channel(s, ctype, p); else bound_periodic(s, p);
+  if (s->gen) boundp_gen(s, ctype == 'N' ? s->cbcpre : s->cbcsgs, p);
+  else if (s->zwall) boundp_channel(s, ctype, p); else bound_periodic(s, p);
 }
 
 /* ------------------------------------------------------------------------------------------------ SGS */
@@ -351,7 +471,30 @@ static void cmpt_sgs_smag(cpu_t *s) {
       const double dele = pow(s->dl[0] * s->dl[1] * s->dzf[k], 1. / 3.);
       for (int i = 1; i <= n1; i++) {
         double fd = 1.0;
-        if (s->zwall) {                                                          /* van Driest, sgs.f90:106-147: walls 5 and 6 only */
+        if (s->gen) {                                                            /* van Driest, sgs.f90:106-147, any set of walls */
+          const double big = 1.7976931348623157e308;                             /* huge(1._rp), param.f90:25 */
+          double dw[6] = {s->dl[0] * (i - 0.5), s->dl[0] * (n1 - i + 0.5), s->dl[1] * (j - 0.5), s->dl[1] * (n2 - j + 0.5), s->zc[k], s->l[2] - s->zc[k]};
+          int loc = 0;
+          for (int q = 0; q < 6; q++) {
+            const double isw = (s->cbcvel[q & 1][q >> 1][q >> 1] == 'D' && ((q >> 1) == 0 || s->cbcpre[0][q >> 1] != 'P')) ? 1. : 0.;
+            dw[q] = dw[q] * isw + big * (1. - isw);
+          }
+          for (int q = 1; q < 6; q++) if (dw[q] < dw[loc]) loc = q;              /* minloc: the first minimum */
+          const double dw_min = dw[loc];
+          double t1, t2, tauw_s;
+          const double *ww = s->w;
+#define F(f, a, b, c_) f[IDX(s, a, b, c_)]
+          if (loc == 0) { t1 = F(vo, 1, j, k) - F(vo, 0, j, k) + F(vo, 1, j - 1, k) - F(vo, 0, j - 1, k); t2 = F(ww, 1, j, k) - F(ww, 0, j, k) + F(ww, 1, j, k - 1) - F(ww, 0, j, k - 1); tauw_s = sqrt(t1 * t1 + t2 * t2) * dxi; }
+          else if (loc == 1) { t1 = F(vo, n1, j, k) - F(vo, n1 + 1, j, k) + F(vo, n1, j - 1, k) - F(vo, n1 + 1, j - 1, k); t2 = F(ww, n1, j, k) - F(ww, n1 + 1, j, k) + F(ww, n1, j, k - 1) - F(ww, n1 + 1, j, k - 1); tauw_s = sqrt(t1 * t1 + t2 * t2) * dxi; }
+          else if (loc == 2) { t1 = F(uo, i, 1, k) - F(uo, i, 0, k) + F(uo, i - 1, 1, k) - F(uo, i - 1, 0, k); t2 = F(ww, i, 1, k) - F(ww, i, 0, k) + F(ww, i, 1, k - 1) - F(ww, i, 0, k - 1); tauw_s = sqrt(t1 * t1 + t2 * t2) * dyi; }
+          else if (loc == 3) { t1 = F(uo, i, n2, k) - F(uo, i, n2 + 1, k) + F(uo, i - 1, n2, k) - F(uo, i - 1, n2 + 1, k); t2 = F(ww, i, n2, k) - F(ww, i, n2 + 1, k) + F(ww, i, n2, k - 1) - F(ww, i, n2 + 1, k - 1); tauw_s = sqrt(t1 * t1 + t2 * t2) * dyi; }
+          else if (loc == 4) { t1 = F(uo, i, j, 1) - F(uo, i, j, 0) + F(uo, i - 1, j, 1) - F(uo, i - 1, j, 0); t2 = F(vo, i, j, 1) - F(vo, i, j, 0) + F(vo, i, j - 1, 1) - F(vo, i, j - 1, 0); tauw_s = sqrt(t1 * t1 + t2 * t2) * s->dzci[0]; }
+          else { t1 = F(uo, i, j, n3) - F(uo, i, j, n3 + 1) + F(uo, i - 1, j, n3) - F(uo, i - 1, j, n3 + 1); t2 = F(vo, i, j, n3) - F(vo, i, j, n3 + 1) + F(vo, i, j - 1, n3) - F(vo, i, j - 1, n3 + 1); tauw_s = sqrt(t1 * t1 + t2 * t2) * s->dzci[n3]; }
+#undef F
+          tauw_s = 0.5 * visc * tauw_s;
+          const double dw_plus = dw_min * sqrt(tauw_s) * visci;
+          fd = 1. - exp(-dw_plus / 25.);
+        } else if (s->zwall) {                                                   /* the same for the channel: walls 5 and 6 only */
           const double dw5 = s->zc[k], dw6 = s->l[2] - s->zc[k];
           double dw_min, tauw_s;
           if (dw5 <= dw6) {                                                      /* minloc: the first minimum */
@@ -760,8 +903,8 @@ static void solver(cpu_t *s) { /* solver.f90:20-80, one rank: no transposes */
     for (int k = 0; k < n3; k++) {
       double *pl = wk + (long)n1 * n2 * k;
       for (int j = 0; j < n2; j++) memcpy(pl + (long)n1 * j, s->pp + IDX(s, 1, j + 1, k + 1), sizeof(double) * (size_t)n1);
-      for (int j = 0; j < n2; j += 2) r2hc_pair(&s->px, pl + (long)n1 * j, j + 1 < n2 ? pl + (long)n1 * (j + 1) : NULL, 1, x, y);
-      for (int i = 0; i < n1; i += 2) r2hc_pair(&s->py, pl + i, i + 1 < n1 ? pl + i + 1 : NULL, n1, x, y);
+      for (int j = 0; j < n2; j += 2) fwd_pair(s->kx, &s->px, pl + (long)n1 * j, j + 1 < n2 ? pl + (long)n1 * (j + 1) : NULL, 1, x, y);
+      for (int i = 0; i < n1; i += 2) fwd_pair(s->ky, &s->py, pl + i, i + 1 < n1 ? pl + i + 1 : NULL, n1, x, y);
     }
     free(x); free(y);
   }
@@ -818,8 +961,8 @@ static void solver(cpu_t *s) { /* solver.f90:20-80, one rank: no transposes */
 #pragma omp for schedule(static)
     for (int k = 0; k < n3; k++) {
       double *pl = wk + (long)n1 * n2 * k;
-      for (int i = 0; i < n1; i += 2) hc2r_pair(&s->py, pl + i, i + 1 < n1 ? pl + i + 1 : NULL, n1, x, y);
-      for (int j = 0; j < n2; j += 2) hc2r_pair(&s->px, pl + (long)n1 * j, j + 1 < n2 ? pl + (long)n1 * (j + 1) : NULL, 1, x, y);
+      for (int i = 0; i < n1; i += 2) bwd_pair(s->ky, &s->py, pl + i, i + 1 < n1 ? pl + i + 1 : NULL, n1, x, y);
+      for (int j = 0; j < n2; j += 2) bwd_pair(s->kx, &s->px, pl + (long)n1 * j, j + 1 < n2 ? pl + (long)n1 * (j + 1) : NULL, 1, x, y);
       for (int j = 0; j < n2; j++) {
         double *dst = s->pp + IDX(s, 1, j + 1, k + 1);
         for (int i = 0; i < n1; i++) dst[i] = pl[(long)n1 * j + i] * s->normfft;
@@ -870,6 +1013,7 @@ void *cales_cpu_new(int n1, int n2, int n3, const double *l, double visc, const 
   for (int m = 0; m < 3; m++) { s->rhs[m] = (double *)calloc((size_t)s->nint, 8); s->rhso[m] = (double *)calloc((size_t)s->nint, 8); }
   s->wk = (double *)calloc((size_t)s->nint, 8);
   plan_init(&s->px, n1); plan_init(&s->py, n2);
+  s->kx = 'P'; s->ky = 'P';
   /* initsolver.f90:17-64 with cbcpre = P/P/P, c_or_f = c,c,c: eigenvalues 66-78, tridmatrix 127-169, normfft fft.f90:99,136 */
   const double pi = acos(-1.0);
   double *lx = (double *)malloc(8 * (size_t)n1), *ly = (double *)malloc(8 * (size_t)n2);
@@ -913,6 +1057,48 @@ int cales_cpu_set_channel(void *h, const double *zc, const double *zf, const int
   }
   s->b[0] = s->b[0] + 1. * s->a[0];
   s->b[n3 - 1] = s->b[n3 - 1] + 1. * s->c[n3 - 1];
+  return 0;
+}
+
+/* Walls in x and / or y as well (square duct, lid-driven cavity; no wall model, static Smagorinsky): cbcvel(0:1,3,3),
+ * bcvel(0:1,3,3), cbcpre(0:1,3), cbcsgs(0:1,3) in Fortran order; pressure and eddy-viscosity boundary values are 0.  Call
+ * right after cales_cpu_new.  Transform kinds by find_fft (fft.f90:192-245): P,P -> R2HC/HC2R, N,N cell-centred ->
+ * REDFT10/REDFT01; eigenvalues initsolver.f90:66-103; normfft fft.f90:99,136,142; tridmatrix fold-in initsolver.f90:149-164. */
+int cales_cpu_set_bc(void *h, const char *cbcvel, const double *bcvel, const char *cbcpre, const char *cbcsgs, const double *zc, const double *zf,
+                     const int *is_forced, const double *velf, const double *bforce) {
+  cpu_t *s = (cpu_t *)h;
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  for (int ivel = 0; ivel < 3; ivel++)
+    for (int idir = 0; idir < 3; idir++)
+      for (int ib = 0; ib < 2; ib++) {
+        s->cbcvel[ib][idir][ivel] = cbcvel[ib + 2 * (idir + 3 * ivel)];
+        s->bcvel[ib][idir][ivel] = bcvel[ib + 2 * (idir + 3 * ivel)];
+      }
+  for (int idir = 0; idir < 3; idir++)
+    for (int ib = 0; ib < 2; ib++) { s->cbcpre[ib][idir] = cbcpre[ib + 2 * idir]; s->cbcsgs[ib][idir] = cbcsgs[ib + 2 * idir]; }
+  for (int idir = 0; idir < 3; idir++) {
+    const char a = s->cbcpre[0][idir], b = s->cbcpre[1][idir];
+    if (!((a == 'P' && b == 'P') || (a == 'N' && b == 'N'))) return 1;            /* the kinds restated here */
+  }
+  s->gen = 1;
+  s->zwall = s->cbcpre[0][2] != 'P';
+  size_t nz = (size_t)(n3 + 2);
+  s->zc = (double *)malloc(8 * nz); s->zf = (double *)malloc(8 * nz); s->gvr_c = (double *)malloc(8 * nz); s->gvr_f = (double *)malloc(8 * nz);
+  for (int k = 0; k < n3 + 2; k++) {
+    s->zc[k] = zc[k]; s->zf[k] = zf[k];
+    s->gvr_c[k] = s->dl[0] * s->dl[1] * s->dzc[k] / (s->l[0] * s->l[1] * s->l[2]);
+    s->gvr_f[k] = s->dl[0] * s->dl[1] * s->dzf[k] / (s->l[0] * s->l[1] * s->l[2]);
+  }
+  for (int m = 0; m < 3; m++) { s->is_forced[m] = is_forced[m]; s->velf[m] = velf[m]; s->bforce[m] = bforce[m]; }
+  s->kx = s->cbcpre[0][0]; s->ky = s->cbcpre[0][1];
+  const double pi = acos(-1.0);
+  double *lx = (double *)malloc(8 * (size_t)n1), *ly = (double *)malloc(8 * (size_t)n2);
+  for (int i = 0; i < n1; i++) lx[i] = (s->kx == 'P' ? -2. * (1. - cos((2 * i) * pi / (1. * n1))) : -2. * (1. - cos((i) * pi / (1. * n1)))) * (s->dli[0] * s->dli[0]);
+  for (int j = 0; j < n2; j++) ly[j] = (s->ky == 'P' ? -2. * (1. - cos((2 * j) * pi / (1. * n2))) : -2. * (1. - cos((j) * pi / (1. * n2)))) * (s->dli[1] * s->dli[1]);
+  for (int j = 0; j < n2; j++) for (int i = 0; i < n1; i++) s->lambdaxy[i + (long)n1 * j] = lx[i] + ly[j];
+  free(lx); free(ly);
+  s->normfft = 1. / (((s->kx == 'P' ? 1. : 2.) * (n1 + 0.)) * ((s->ky == 'P' ? 1. : 2.) * (n2 + 0.)));
+  if (s->zwall) { s->b[0] = s->b[0] + 1. * s->a[0]; s->b[n3 - 1] = s->b[n3 - 1] + 1. * s->c[n3 - 1]; }
   return 0;
 }
 
@@ -1029,5 +1215,5 @@ void cales_cpu_free(void *h) {
   for (size_t m = 0; m < sizeof(f) / sizeof(f[0]); m++) free(f[m]);
   for (int m = 0; m < 3; m++) { free(s->rhs[m]); free(s->rhso[m]); }
   for (int m = 0; m < 24; m++) free(s->dyn[m]);
-  free(s->px.tw); free(s->py.tw); free(s);
+  free(s->px.tw); free(s->py.tw); free(s->px.tq); free(s->py.tq); free(s);
 }

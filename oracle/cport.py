@@ -39,6 +39,9 @@ def load():
         ip = C.POINTER(C.c_int)
         lib.cales_cpu_set_channel.restype = C.c_int
         lib.cales_cpu_set_channel.argtypes = [C.c_void_p, dp, dp, ip, C.c_double, ip, dp, dp]
+        cp = C.c_char_p
+        lib.cales_cpu_set_bc.restype = C.c_int
+        lib.cales_cpu_set_bc.argtypes = [C.c_void_p, cp, dp, cp, cp, dp, dp, ip, dp, dp]
         lib.cales_cpu_set_sgs.restype = None
         lib.cales_cpu_set_sgs.argtypes = [C.c_void_p, C.c_int]
         lib.cales_cpu_forcing.restype = C.c_double
@@ -53,7 +56,8 @@ def _dp(a):
 
 
 class CSim:
-    """Mirror of oracle.main.Sim for an all-periodic or plane-channel 'smag' deck on one rank, backed by the C library."""
+    """Mirror of oracle.main.Sim for the decks the C library covers (all-periodic and plane channel with either model; square
+    duct and lid-driven cavity with the static model) on one rank."""
 
     @staticmethod
     def kind(deck):
@@ -67,7 +71,14 @@ class CSim:
             (deck.cbcpre[:, 2] == "N").all() and (deck.cbcsgs[:, 0:2] == "P").all() and (deck.cbcsgs[:, 2] == "D").all() and \
             not deck.bcvel.any() and not deck.bcpre.any() and not deck.bcsgs.any() and not deck.lwm[:, 0:2].any() and \
             all(int(x) in (0, 1) for x in deck.lwm[:, 2])
-        return "channel" if ok else None
+        if ok:
+            return "channel"
+        pairs = [deck.cbcpre[0, q] + deck.cbcpre[1, q] for q in range(3)]
+        ok = deck.sgstype.strip() == "smag" and all(p in ("PP", "NN") for p in pairs) and not deck.lwm.any() and \
+            not deck.bcpre.any() and not deck.bcsgs.any() and \
+            all(((deck.cbcvel[:, q, :] == "P").all() and (deck.cbcsgs[:, q] == "P").all()) if pairs[q] == "PP" else
+                (np.isin(deck.cbcvel[:, q, :], ("D", "N")).all() and np.isin(deck.cbcsgs[:, q], ("D", "N")).all()) for q in range(3))
+        return "walls" if ok else None                            # square duct, lid-driven cavity
 
     def __init__(self, deck, threads=None):
         """threads: OpenMP threads to use (None = the OpenMP default, i.e. OMP_NUM_THREADS or all cores)."""
@@ -89,6 +100,14 @@ class CSim:
             da = lambda a: (C.c_double * len(a))(*[float(x) for x in a])
             rc = self.lib.cales_cpu_set_channel(self.h, _dp(np.ascontiguousarray(zc)), _dp(np.ascontiguousarray(zf)), ia(deck.lwm[:, 2]),
                                                 float(deck.hwm), ia([bool(x) for x in deck.is_forced]), da(deck.velf), da(deck.bforce))
+            assert rc == 0
+        if kind == "walls":
+            ia = lambda a: (C.c_int * len(a))(*[int(x) for x in a])
+            da = lambda a: (C.c_double * len(a))(*[float(x) for x in a])
+            fl = lambda a: "".join(np.asarray(a).ravel(order="F")).encode()
+            rc = self.lib.cales_cpu_set_bc(self.h, fl(deck.cbcvel), da(np.asarray(deck.bcvel, dtype=float).ravel(order="F")), fl(deck.cbcpre),
+                                           fl(deck.cbcsgs), _dp(np.ascontiguousarray(zc)), _dp(np.ascontiguousarray(zf)),
+                                           ia([bool(x) for x in deck.is_forced]), da(deck.velf), da(deck.bforce))
             assert rc == 0
         self.lib.cales_cpu_set_sgs(self.h, 1 if deck.sgstype.strip() == "dsmag" else 0)
         shp = (n[0] + 2, n[1] + 2, n[2] + 2)

@@ -128,10 +128,72 @@ def test_c_port_dynamic_smagorinsky_matches_numpy_oracle(case):
         c.close()
 
 
+WALLS = {"duct_smag": ("deck_duct", dict(ng=(16, 12, 14), sgstype="smag"), None),
+         "duct_smag_3d_field": ("deck_duct", dict(ng=(12, 15, 9), sgstype="smag"), "tgv"),      # odd lengths, non-trivial pressure
+         "cavity_smag": ("deck_cavity", dict(ng=(12, 12, 12), sgstype="smag"), None),
+         "cavity_smag_odd": ("deck_cavity", dict(ng=(16, 10, 15), sgstype="smag"), None)}
+
+
+@pytest.mark.parametrize("case", list(WALLS))
+def test_c_port_duct_and_cavity_match_numpy_oracle(case):
+    """walls in y (duct) or in every direction (cavity, moving lid): general set_bc sequence of bounduvw / boundp, van Driest
+    distance over every wall, REDFT10 / REDFT01 through the port's own complex FFT vs scipy's DCT-II / DCT-III"""
+    name, kw, inivel = WALLS[case]
+    d = getattr(op, name)(**kw)
+    if inivel:
+        d.inivel = inivel
+    assert CSim.kind(d) == "walls"
+    o, c = Sim(d), CSim(d)
+    try:
+        for nm, on in PAIRS[:4]:
+            assert np.array_equal(c.f[nm], getattr(o, on)[0]), nm
+        assert np.abs(c.f["visct"] - o.VISCT[0]).max() <= 4e-16 * np.abs(o.VISCT[0]).max()
+        assert abs(c.dt - o.dt) <= 1e-15 * o.dt
+        for _ in range(3):
+            divo = o.step(icheck=1)
+            divc = c.step(icheck=1)
+        assert divc < 1e-12 and divo[1] < 1e-12
+        vs = max(np.abs(getattr(o, on)[0]).max() for on in ("U", "V", "W"))
+        for nm, on in PAIRS:
+            a = c.f[nm][1:-1, 1:-1, 1:-1]
+            b = getattr(o, on)[0][1:-1, 1:-1, 1:-1]
+            if nm == "p":
+                a = a - a.mean(); b = b - b.mean()
+            scale = vs if nm in ("u", "v", "w") else max(np.abs(b).max(), vs * vs if nm == "p" else 0.)
+            assert np.abs(a - b).max() / scale < 1e-12, nm
+        assert abs(c.dt - o.dt) <= 1e-12 * o.dt
+    finally:
+        c.close()
+
+
+def test_c_port_cosine_transforms_are_fftw_redft10_and_redft01():
+    """the port's cosine-transform pair routines (REDFT10 forward, REDFT01 backward, x and y) through its solver on the
+    all-Neumann cavity problem: the discrete Laplacian of the solution reproduces a compatible (zero-mean) right-hand side"""
+    ng = (12, 10, 9)
+    d = op.deck_cavity(ng=ng, sgstype="smag")
+    c = CSim(d)
+    try:
+        rng = np.random.default_rng(5)
+        rhs = rng.standard_normal(ng); rhs -= rhs.mean()
+        c.f["pp"][1:-1, 1:-1, 1:-1] = rhs
+        c.lib.cales_cpu_solver(c.h)
+        c.lib.cales_cpu_boundp(c.h, 4)
+        p = c.f["pp"]; dli = d.dli
+        lap = ((p[2:, 1:-1, 1:-1] - 2 * p[1:-1, 1:-1, 1:-1] + p[:-2, 1:-1, 1:-1]) * dli[0] ** 2 +
+               (p[1:-1, 2:, 1:-1] - 2 * p[1:-1, 1:-1, 1:-1] + p[1:-1, :-2, 1:-1]) * dli[1] ** 2 +
+               (p[1:-1, 1:-1, 2:] - 2 * p[1:-1, 1:-1, 1:-1] + p[1:-1, 1:-1, :-2]) * dli[2] ** 2)
+        floor = np.finfo(float).eps * np.abs(p).max() * 4. * (dli[0] ** 2 + dli[1] ** 2 + dli[2] ** 2)
+        assert np.abs(lap - rhs).max() < max(1e-11 * np.abs(rhs).max(), 4. * floor)
+    finally:
+        c.close()
+
+
 def test_c_port_refuses_what_it_does_not_cover():
     assert CSim.kind(op.deck_channel(ng=(8, 8, 8), sgstype="dsmag")) == "channel"
     assert CSim.kind(op.deck_channel(ng=(8, 8, 8), sgstype="none")) is None
-    assert CSim.kind(op.deck_duct(ng=(8, 8, 8))) is None and CSim.kind(op.deck_cavity(ng=(8, 8, 8))) is None
+    assert CSim.kind(op.deck_duct(ng=(8, 8, 8))) == "walls" and CSim.kind(op.deck_cavity(ng=(8, 8, 8))) == "walls"
+    assert CSim.kind(op.deck_duct(ng=(8, 8, 8), sgstype="dsmag")) is None          # dynamic model: periodic x and y only
+    assert CSim.kind(op.deck_duct(ng=(8, 8, 8), wall_model=True)) is None          # wall model: z walls only
     assert CSim.kind(op.deck_tgv(ng=(8, 8, 8))) == "periodic"
     with pytest.raises(AssertionError):
-        CSim(op.deck_duct(ng=(8, 8, 8)))
+        CSim(op.deck_duct(ng=(8, 8, 8), wall_model=True))
