@@ -69,7 +69,7 @@ typedef struct {
   double *zc, *zf, *gvr_c, *gvr_f;     /* 0:n3+1 */
   double *bcu_z, *bcv_z;               /* wall-model Neumann planes bcu%z, bcv%z: (0:n1+1, 0:n2+1, 0:1) */
   double *wku, *wkv;                   /* copies of u, v for the extrapolation of cmpt_sgs (sgs.f90:84-90) */
-  int dsmag;                           /* 0: 'smag', 1: 'dsmag' */
+  int dsmag, sgs_done;                 /* 0: 'smag', 1: 'dsmag', 2: 'none' */
   char kx, ky;                         /* transform kind of x and y: 'P' (R2HC/HC2R) or 'N' (REDFT10/REDFT01) */
   int gen;                             /* 1: walls in x and / or y as well (duct, cavity): the general ghost fills below */
   char cbcvel[2][3][3], cbcpre[2][3], cbcsgs[2][3];   /* [ib][idir][ivel] */
@@ -711,7 +711,11 @@ static void cmpt_sgs_dsmag(cpu_t *s) {
       }
 }
 
-static void cmpt_sgs(cpu_t *s) { if (s->dsmag) cmpt_sgs_dsmag(s); else cmpt_sgs_smag(s); }
+/* cmpt_sgs (sgs.f90:21-386): 'none' (58-68: the eddy viscosity is zeroed on the first call and never touched again), 'smag', 'dsmag' */
+static void cmpt_sgs(cpu_t *s) {
+  if (s->dsmag == 2) { if (!s->sgs_done) { s->sgs_done = 1; memset(s->visct, 0, sizeof(double) * (size_t)s->ntot); } return; }
+  if (s->dsmag) cmpt_sgs_dsmag(s); else cmpt_sgs_smag(s);
+}
 
 /* ---------------------------------------------------------------------------------------------- mom + rk */
 /* mom.f90:142-302 (explicit branch) and rk.f90:45-100, then cmpt_bulk_forcing (rk.f90:197-222). */

@@ -62,7 +62,7 @@ class CSim:
     @staticmethod
     def kind(deck):
         """'periodic', 'channel' or None (not covered by the C restatement)"""
-        if deck.sgstype.strip() not in ("smag", "dsmag") or deck.impdiff or tuple(deck.dims) != (1, 1):
+        if deck.sgstype.strip() not in ("none", "smag", "dsmag") or deck.impdiff or tuple(deck.dims) != (1, 1):
             return None
         if (deck.cbcvel == "P").all() and (deck.cbcpre == "P").all() and not any(deck.is_forced) and not any(deck.bforce) \
                 and not deck.lwm.any():
@@ -74,7 +74,7 @@ class CSim:
         if ok:
             return "channel"
         pairs = [deck.cbcpre[0, q] + deck.cbcpre[1, q] for q in range(3)]
-        ok = deck.sgstype.strip() == "smag" and all(p in ("PP", "NN") for p in pairs) and not deck.lwm.any() and \
+        ok = deck.sgstype.strip() in ("none", "smag") and all(p in ("PP", "NN") for p in pairs) and not deck.lwm.any() and \
             not deck.bcpre.any() and not deck.bcsgs.any() and \
             all(((deck.cbcvel[:, q, :] == "P").all() and (deck.cbcsgs[:, q] == "P").all()) if pairs[q] == "PP" else
                 (np.isin(deck.cbcvel[:, q, :], ("D", "N")).all() and np.isin(deck.cbcsgs[:, q], ("D", "N")).all()) for q in range(3))
@@ -109,7 +109,7 @@ class CSim:
                                            fl(deck.cbcsgs), _dp(np.ascontiguousarray(zc)), _dp(np.ascontiguousarray(zf)),
                                            ia([bool(x) for x in deck.is_forced]), da(deck.velf), da(deck.bforce))
             assert rc == 0
-        self.lib.cales_cpu_set_sgs(self.h, 1 if deck.sgstype.strip() == "dsmag" else 0)
+        self.lib.cales_cpu_set_sgs(self.h, {"smag": 0, "dsmag": 1, "none": 2}[deck.sgstype.strip()])
         shp = (n[0] + 2, n[1] + 2, n[2] + 2)
         self.f = {nm: np.ctypeslib.as_array(self.lib.cales_cpu_field(self.h, i), shape=shp[::-1]).T for nm, i in FIELDS.items()}
         u, v, w, p = initflow(deck, (1, 1, 1), n, zc, zf, dzc, dzf)

@@ -197,3 +197,37 @@ def test_c_port_refuses_what_it_does_not_cover():
     assert CSim.kind(op.deck_tgv(ng=(8, 8, 8))) == "periodic"
     with pytest.raises(AssertionError):
         CSim(op.deck_duct(ng=(8, 8, 8), wall_model=True))
+
+
+def test_two_restatements_agree_on_the_reference_example_decks():
+    """every input.nml the reference ships (examples/dns, examples/les), shrunk to 16 x 12 x 14 on one rank: the decks the C
+    restatement covers (all but the inflow/outflow ones, which need DCT-IV, and the wall-modelled duct) run two RK3 steps in both
+    restatements -- moving walls, free-slip lids, body forces, constant-pressure-gradient and bulk-velocity forcing, every
+    initial condition incl. the noisy ones -- and agree to round-off"""
+    import glob
+    files = sorted(glob.glob("/root/reference/examples/**/input.nml", recursive=True))
+    if not files:
+        pytest.skip("reference tree not present")
+    covered = 0
+    for f in files:
+        d = op.read_input(f)
+        d.dims = (1, 1); d.ng = (16, 12, 14)
+        if CSim.kind(d) is None:
+            assert "developing_" in f or "duct_wall_model" in f, f
+            continue
+        covered += 1
+        o, c = Sim(d), CSim(d)
+        try:
+            for _ in range(2):
+                o.step(icheck=1); c.step(icheck=1)
+            vs = max(np.abs(getattr(o, on)[0]).max() for on in ("U", "V", "W")) or 1.
+            for nm, on in PAIRS:
+                a = c.f[nm][1:-1, 1:-1, 1:-1]; b = getattr(o, on)[0][1:-1, 1:-1, 1:-1]
+                if nm == "p":
+                    a = a - a.mean(); b = b - b.mean()
+                scale = vs if nm in ("u", "v", "w") else max(np.abs(b).max(), vs * vs if nm == "p" else 1e-300)
+                assert np.abs(a - b).max() / scale < 1e-11, (f, nm)
+            assert abs(c.dt - o.dt) <= 1e-12 * o.dt, f
+        finally:
+            c.close()
+    assert covered >= 18
