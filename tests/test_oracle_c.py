@@ -190,7 +190,9 @@ def test_c_port_cosine_transforms_are_fftw_redft10_and_redft01():
 
 def test_c_port_refuses_what_it_does_not_cover():
     assert CSim.kind(op.deck_channel(ng=(8, 8, 8), sgstype="dsmag")) == "channel"
-    assert CSim.kind(op.deck_channel(ng=(8, 8, 8), sgstype="none")) is None
+    assert CSim.kind(op.deck_channel(ng=(8, 8, 8), sgstype="none")) == "channel"
+    nd = op.deck_channel(ng=(8, 8, 8)); nd.cbcpre[1, 2] = "D"                      # N,D pressure pair: DCT-IV kinds, not restated in C
+    assert CSim.kind(nd) is None
     assert CSim.kind(op.deck_duct(ng=(8, 8, 8))) == "walls" and CSim.kind(op.deck_cavity(ng=(8, 8, 8))) == "walls"
     assert CSim.kind(op.deck_duct(ng=(8, 8, 8), sgstype="dsmag")) is None          # dynamic model: periodic x and y only
     assert CSim.kind(op.deck_duct(ng=(8, 8, 8), wall_model=True)) is None          # wall model: z walls only
