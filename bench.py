@@ -361,6 +361,7 @@ def run_ours(args):
     # compute of step s on the library's stream, through double-buffered device staging; PCIe is full duplex.
     e2e = None
     if not args.no_e2e:
+        torch.ones(1 << 22).sum().item()      # host thread pool (shared OpenMP runtime) comes up with the process's full CPU mask first
         old_mask, numa_note = bind_near_gpu(local)
         names = ("u", "v", "w", "p")
         hin = {nm: torch.empty(sim.ncell, dtype=torch.float64).pin_memory() for nm in names}
