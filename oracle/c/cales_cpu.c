@@ -7,7 +7,8 @@
  * (sgs.f90:153-380 with filter3d 616-680, extrapolate 682-767, cmpt_alph2 769-822, interpolate 850-870, ave1d_channel
  * 433-538) for both (BASELINE configs 1, 3 and 5); (iii) static Smagorinsky with walls in x and / or y as well -- square
  * duct, lid-driven cavity (BASELINE config 4): the general set_bc sequence of bounduvw / boundp, van Driest distance over all
- * walls, and the cell-centred Neumann-Neumann transforms REDFT10 / REDFT01 (fft.f90:192-245) through the same complex FFT:
+ * walls, the wall model on y and z walls (cmpt_wallmodelbc case(2) and case(3)), and the cell-centred Neumann-Neumann
+ * transforms REDFT10 / REDFT01 (fft.f90:192-245) through the same complex FFT:
  *   src/bound.f90:18-154 (bounduvw), 156-200 (boundp), 202-399 (set_bc: P, D and N, centred and face),
  *   src/wmodel.f90:19-335 (updt_wallmodelbc / cmpt_wallmodelbc case(3) / vel_relative / wallmodel),
  *   src/sgs.f90:69-152 with extrapolate 682-767, src/rk.f90:197-222 + src/utils.f90:16-47 + src/mom.f90:311-335
@@ -74,6 +75,8 @@ typedef struct {
   int gen;                             /* 1: walls in x and / or y as well (duct, cavity): the general ghost fills below */
   char cbcvel[2][3][3], cbcpre[2][3], cbcsgs[2][3];   /* [ib][idir][ivel] */
   double bcvel[2][3][3];
+  int lwm_y[2], index_wm_y[2];         /* wall model on the y walls (lwm(0:1,2)): general mode only */
+  double *bcu_y, *bcw_y, *wkw;         /* bcu%y, bcw%y: (0:n1+1, 0:n3+1, 0:1); copy of w for the extrapolation of cmpt_sgs */
   double *dyn[24];                     /* work arrays of the dynamic model (sgs.f90:156-166): uc,vc,wc, uf,vf,wf, wk(6), sij(6), mij(6) */
 } cpu_t;
 
@@ -305,7 +308,11 @@ static void set_bc_c(const cpu_t *s, char ctype, int ibound, int idir, int cente
 /* halo exchange of one rank (bound.f90:619-696): a decomposed direction (y, z) that is periodic is its own neighbour */
 static void halo_self(const cpu_t *s, int idir, double *p) { set_bc_c(s, 'P', 0, idir, 1, 0., 0., p); }
 
-/* bounduvw (bound.f90:18-154) in general: walls in any direction, no wall model (lwm = 0 everywhere) */
+static void cmpt_wallmodelbc_y(cpu_t *s, int ibound);
+static void cmpt_wallmodelbc_z(cpu_t *s, int ibound);
+static void set_bc_y_plane(const cpu_t *s, int ibound, const double *bc, double dr, double *p);
+
+/* bounduvw (bound.f90:18-154) in general: walls in any direction; wall model on y and / or z walls */
 static void bounduvw_gen(cpu_t *s, double *u, double *v, double *w, int is_correc) {
   double *f[3] = {u, v, w};
   for (int idir = 1; idir < 3; idir++)                                           /* updthalo, 42-46: x is the pencil direction */
@@ -320,10 +327,24 @@ static void bounduvw_gen(cpu_t *s, double *u, double *v, double *w, int is_corre
       const double drf = idir == 0 ? s->dl[0] : idir == 1 ? s->dl[1] : (ib == 0 ? s->dzf[0] : s->dzf[n3]);
       const double drc = idir == 0 ? s->dl[0] : idir == 1 ? s->dl[1] : (ib == 0 ? s->dzc[0] : s->dzc[n3]);
       if (impose_norm_bc) set_bc_c(s, s->cbcvel[ib][idir][idir], ib, idir, 0, s->bcvel[ib][idir][idir], drf, f[idir]);
+      const int wm = idir == 1 ? s->lwm_y[ib] : idir == 2 ? s->lwm[ib] : 0;
+      if (wm != 0) continue;                                                     /* lwm /= 0: after the wall model, below */
       for (int m = 0; m < 3; m++)                                                /* the two wall-parallel components, in index order */
         if (m != idir) set_bc_c(s, s->cbcvel[ib][idir][m], ib, idir, 1, s->bcvel[ib][idir][m], drc, f[m]);
     }
   }
+  if (!(s->lwm_y[0] || s->lwm_y[1] || s->lwm[0] || s->lwm[1])) return;
+  /* updt_wallmodelbc (wmodel.f90:19-62; is_updt_wm = .true. on this path), then the Neumann ghosts of the wall-model faces */
+  for (int ib = 0; ib < 2; ib++) if (s->lwm_y[ib]) cmpt_wallmodelbc_y(s, ib);
+  for (int ib = 0; ib < 2; ib++) if (s->lwm[ib]) cmpt_wallmodelbc_z(s, ib);
+  const long ply = (long)(s->n1 + 2) * (s->n3 + 2), plz = (long)(s->n1 + 2) * (s->n2 + 2);
+  for (int ib = 0; ib < 2; ib++)
+    if (s->lwm_y[ib]) { set_bc_y_plane(s, ib, s->bcu_y + ply * ib, s->dl[1], u); set_bc_y_plane(s, ib, s->bcw_y + ply * ib, s->dl[1], w); }
+  for (int ib = 0; ib < 2; ib++)
+    if (s->lwm[ib]) {
+      set_bc_z(s, 'N', 1, s->bcu_z, s->bcu_z + plz, s->dzc[0], s->dzc[n3], u, ib == 0, ib == 1);
+      set_bc_z(s, 'N', 1, s->bcv_z, s->bcv_z + plz, s->dzc[0], s->dzc[n3], v, ib == 0, ib == 1);
+    }
 }
 
 /* boundp (bound.f90:156-200) in general, boundary values 0 */
@@ -397,6 +418,60 @@ static void cmpt_wallmodelbc_z(cpu_t *s, int ibound) {
     }
 }
 
+/* cmpt_wallmodelbc, case(2) (wmodel.f90:171-214), walls at rest */
+static void cmpt_wallmodelbc_y(cpu_t *s, int ibound) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  const long sk = s->sk;
+  const double h = s->hwm, visc = s->visc, visci = 1. / visc;
+  const double *u = s->u, *w = s->w;
+  int j1, j2; double coef, sgn;
+  if (ibound == 0) { j2 = s->index_wm_y[0]; j1 = j2 - 1; coef = (h - (j1 - 0.5) * s->dl[1]) / s->dl[1]; sgn = 1.; }
+  else { j2 = s->index_wm_y[1]; j1 = j2 + 1; coef = (h - (n2 - j1 + 0.5) * s->dl[1]) / s->dl[1]; sgn = -1.; }
+  const long pl = (long)(n1 + 2) * (n3 + 2);
+  double *bcu = s->bcu_y + pl * ibound, *bcw = s->bcw_y + pl * ibound;
+#pragma omp parallel for schedule(static)
+  for (int k = 1; k <= n3; k++)
+    for (int i = 0; i <= n1; i++) {
+      const long c1 = IDX(s, i, j1, k), c2 = IDX(s, i, j2, k);
+      const double u1 = u[c1], u2 = u[c2];
+      const double w1 = 0.25 * (w[c1] + w[c1 + 1] + w[c1 - sk] + w[c1 + 1 - sk]);
+      const double w2 = 0.25 * (w[c2] + w[c2 + 1] + w[c2 - sk] + w[c2 + 1 - sk]);
+      const double u_mag = 0., w_mag = 0.25 * (0. + 0. + 0. + 0.);
+      double uh = (1. - coef) * u1 + coef * u2; uh = uh - u_mag;
+      double wh = (1. - coef) * w1 + coef * w2; wh = wh - w_mag;
+      double tauw[2];
+      wallmodel_log(uh, wh, h, visc, s->eps, tauw);
+      bcu[(long)i + (long)(n1 + 2) * k] = sgn * visci * tauw[0];
+    }
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k <= n3; k++)
+    for (int i = 1; i <= n1; i++) {
+      const long c1 = IDX(s, i, j1, k), c2 = IDX(s, i, j2, k);
+      const double wei = (s->zf[k] - s->zc[k]) / s->dzc[k];
+      const double u1 = 0.5 * ((1. - wei) * (u[c1 - 1] + u[c1]) + wei * (u[c1 - 1 + sk] + u[c1 + sk]));
+      const double u2 = 0.5 * ((1. - wei) * (u[c2 - 1] + u[c2]) + wei * (u[c2 - 1 + sk] + u[c2 + sk]));
+      const double w1 = w[c1], w2 = w[c2];
+      const double u_mag = 0.5 * ((1. - wei) * (0. + 0.) + wei * (0. + 0.)), w_mag = 0.;
+      double uh = (1. - coef) * u1 + coef * u2; uh = uh - u_mag;
+      double wh = (1. - coef) * w1 + coef * w2; wh = wh - w_mag;
+      double tauw[2];
+      wallmodel_log(uh, wh, h, visc, s->eps, tauw);
+      bcw[(long)i + (long)(n1 + 2) * k] = sgn * visci * tauw[1];
+    }
+}
+
+/* set_bc('N', centred) on a y face with a plane of boundary values (0:n1+1, 0:n3+1) (bound.f90:320-353) */
+static void set_bc_y_plane(const cpu_t *s, int ibound, const double *bc, double dr, double *p) {
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+#pragma omp parallel for schedule(static)
+  for (int k = 0; k <= n3 + 1; k++)
+    for (int i = 0; i <= n1 + 1; i++) {
+      const double b = bc[(long)i + (long)(n1 + 2) * k];
+      if (ibound == 0) p[IDX(s, i, 0, k)] = -dr * b + p[IDX(s, i, 1, k)];
+      else p[IDX(s, i, n2 + 1, k)] = dr * b + p[IDX(s, i, n2, k)];
+    }
+}
+
 /* bounduvw (bound.f90:18-154) for the channel on one rank.  is_updt_wm = 1: the fields are s->u, v, w and the wall-model
  * planes bcu%z, bcv%z are recomputed first (125-128); is_updt_wm = 0 (the filtered velocities of the dynamic model,
  * sgs.f90:256-257, with bcuf = bcvf = the initial planes = 0): the Neumann planes are zero. */
@@ -446,7 +521,7 @@ static void cmpt_sgs_smag(cpu_t *s) {
   const double dxi = s->dli[0], dyi = s->dli[1];
   const double *u = s->u, *v = s->v, *w = s->w;
   const double *uo = s->u, *vo = s->v;                                          /* the un-extrapolated fields: van Driest wall shear */
-  if (s->zwall && (s->lwm[0] || s->lwm[1])) {
+  if (!s->gen && s->zwall && (s->lwm[0] || s->lwm[1])) {
     /* sgs.f90:84-90: copies, then extrapolate(iface = 1, 2, lwm) (682-767): wall-parallel ghosts on the wall-model
      * faces by linear extrapolation; w (iface = 3) is not extrapolated on the z walls */
     memcpy(s->wku, s->u, sizeof(double) * (size_t)s->ntot); memcpy(s->wkv, s->v, sizeof(double) * (size_t)s->ntot);
@@ -462,6 +537,30 @@ static void cmpt_sgs_smag(cpu_t *s) {
         }
     }
     u = s->wku; v = s->wkv;
+  }
+  if (s->gen && (s->lwm_y[0] || s->lwm_y[1] || s->lwm[0] || s->lwm[1])) {
+    /* the same in general (sgs.f90:84-90, extrapolate 682-767 with lwm): per array the y faces first, then the z faces;
+     * u (iface 1): y and z, v (iface 2): z only, w (iface 3): y only */
+    const size_t nb = sizeof(double) * (size_t)s->ntot;
+    memcpy(s->wku, s->u, nb); memcpy(s->wkv, s->v, nb); memcpy(s->wkw, s->w, nb);
+    const double factor0 = s->dzc[0] * s->dzci[1], factor1 = s->dzc[n3] * s->dzci[n3 - 1];
+    double *wk3[3] = {s->wku, s->wkv, s->wkw};
+    for (int m = 0; m < 3; m++) {
+      double *p = wk3[m];
+      if (m != 1)
+        for (int k = 0; k <= n3 + 1; k++)
+          for (int i = 0; i <= n1 + 1; i++) {
+            if (s->lwm_y[0]) p[IDX(s, i, 0, k)] = 2. * p[IDX(s, i, 1, k)] - p[IDX(s, i, 2, k)];
+            if (s->lwm_y[1]) p[IDX(s, i, n2 + 1, k)] = 2. * p[IDX(s, i, n2, k)] - p[IDX(s, i, n2 - 1, k)];
+          }
+      if (m != 2)
+        for (int j = 0; j <= n2 + 1; j++)
+          for (int i = 0; i <= n1 + 1; i++) {
+            if (s->lwm[0]) p[IDX(s, i, j, 0)] = (1. + factor0) * p[IDX(s, i, j, 1)] - factor0 * p[IDX(s, i, j, 2)];
+            if (s->lwm[1]) p[IDX(s, i, j, n3 + 1)] = (1. + factor1) * p[IDX(s, i, j, n3)] - factor1 * p[IDX(s, i, j, n3 - 1)];
+          }
+    }
+    u = s->wku; v = s->wkv; w = s->wkw;
   }
   const double visc = s->visc, visci = 1. / visc;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -1106,6 +1205,29 @@ int cales_cpu_set_bc(void *h, const char *cbcvel, const double *bcvel, const cha
   return 0;
 }
 
+/* Wall model (WM_LOG) on y and / or z walls in the general mode: lwm(0:1,3) in Fortran order, after cales_cpu_set_bc.
+ * initbc (bound.f90:746-758): the wall-parallel components of a wall-model face become 'N', the normal one 'D';
+ * index_wm 830-863. */
+int cales_cpu_set_wm(void *h, const int *lwm, double hwm) {
+  cpu_t *s = (cpu_t *)h;
+  const int n1 = s->n1, n2 = s->n2, n3 = s->n3;
+  if (!s->gen || lwm[0] || lwm[1]) return 1;                                     /* x walls: not restated */
+  for (int q = 2; q < 6; q++) if (lwm[q] != 0 && lwm[q] != 1) return 1;
+  s->hwm = hwm;
+  for (int ib = 0; ib < 2; ib++) { s->lwm_y[ib] = lwm[ib + 2]; s->lwm[ib] = lwm[ib + 4]; }
+  for (int idir = 1; idir < 3; idir++)
+    for (int ib = 0; ib < 2; ib++)
+      if (lwm[ib + 2 * idir]) for (int ivel = 0; ivel < 3; ivel++) s->cbcvel[ib][idir][ivel] = ivel == idir ? 'D' : 'N';
+  s->bcu_y = (double *)calloc(2 * (size_t)(n1 + 2) * (size_t)(n3 + 2), 8); s->bcw_y = (double *)calloc(2 * (size_t)(n1 + 2) * (size_t)(n3 + 2), 8);
+  s->bcu_z = (double *)calloc(2 * (size_t)(n1 + 2) * (size_t)(n2 + 2), 8); s->bcv_z = (double *)calloc(2 * (size_t)(n1 + 2) * (size_t)(n2 + 2), 8);
+  s->wku = (double *)calloc((size_t)s->ntot, 8); s->wkv = (double *)calloc((size_t)s->ntot, 8); s->wkw = (double *)calloc((size_t)s->ntot, 8);
+  if (s->lwm_y[0]) { int j = 1; while ((j - 0.5) * s->dl[1] < hwm) j = j + 1; s->index_wm_y[0] = j; }
+  if (s->lwm_y[1]) { int j = n2; while ((n2 - j + 0.5) * s->dl[1] < hwm) j = j - 1; s->index_wm_y[1] = j; }
+  if (s->lwm[0]) { int k = 1; while (s->zc[k] < hwm) k = k + 1; s->index_wm[0] = k; }
+  if (s->lwm[1]) { int k = n3; while (s->l[2] - s->zc[k] < hwm) k = k - 1; s->index_wm[1] = k; }
+  return 0;
+}
+
 double cales_cpu_forcing(void *h, int m) { return ((cpu_t *)h)->f[m]; }
 
 double *cales_cpu_field(void *h, int which) { /* 0 u, 1 v, 2 w, 3 p, 4 pp, 5 visct, 6 s0 */
@@ -1215,7 +1337,7 @@ void cales_cpu_free(void *h) {
   cpu_t *s = (cpu_t *)h;
   if (!s) return;
   double *f[] = {s->u, s->v, s->w, s->p, s->pp, s->visct, s->s0, s->wk, s->dzc, s->dzf, s->dzci, s->dzfi, s->a, s->b, s->c, s->lambdaxy,
-                 s->zc, s->zf, s->gvr_c, s->gvr_f, s->bcu_z, s->bcv_z, s->wku, s->wkv};
+                 s->zc, s->zf, s->gvr_c, s->gvr_f, s->bcu_z, s->bcv_z, s->wku, s->wkv, s->bcu_y, s->bcw_y, s->wkw};
   for (size_t m = 0; m < sizeof(f) / sizeof(f[0]); m++) free(f[m]);
   for (int m = 0; m < 3; m++) { free(s->rhs[m]); free(s->rhso[m]); }
   for (int m = 0; m < 24; m++) free(s->dyn[m]);

@@ -42,6 +42,8 @@ def load():
         cp = C.c_char_p
         lib.cales_cpu_set_bc.restype = C.c_int
         lib.cales_cpu_set_bc.argtypes = [C.c_void_p, cp, dp, cp, cp, dp, dp, ip, dp, dp]
+        lib.cales_cpu_set_wm.restype = C.c_int
+        lib.cales_cpu_set_wm.argtypes = [C.c_void_p, ip, C.c_double]
         lib.cales_cpu_set_sgs.restype = None
         lib.cales_cpu_set_sgs.argtypes = [C.c_void_p, C.c_int]
         lib.cales_cpu_forcing.restype = C.c_double
@@ -74,7 +76,9 @@ class CSim:
         if ok:
             return "channel"
         pairs = [deck.cbcpre[0, q] + deck.cbcpre[1, q] for q in range(3)]
-        ok = deck.sgstype.strip() in ("none", "smag") and all(p in ("PP", "NN") for p in pairs) and not deck.lwm.any() and \
+        wm_ok = not deck.lwm[:, 0].any() and all(int(x) in (0, 1) for x in deck.lwm.ravel()) and \
+            all(pairs[q] == "NN" and (deck.cbcvel[:, q, :] == "D").all() for q in (1, 2) if deck.lwm[:, q].any())
+        ok = deck.sgstype.strip() in ("none", "smag") and all(p in ("PP", "NN") for p in pairs) and wm_ok and \
             not deck.bcpre.any() and not deck.bcsgs.any() and \
             all(((deck.cbcvel[:, q, :] == "P").all() and (deck.cbcsgs[:, q] == "P").all()) if pairs[q] == "PP" else
                 (np.isin(deck.cbcvel[:, q, :], ("D", "N")).all() and np.isin(deck.cbcsgs[:, q], ("D", "N")).all()) for q in range(3))
@@ -109,6 +113,8 @@ class CSim:
                                            fl(deck.cbcsgs), _dp(np.ascontiguousarray(zc)), _dp(np.ascontiguousarray(zf)),
                                            ia([bool(x) for x in deck.is_forced]), da(deck.velf), da(deck.bforce))
             assert rc == 0
+            if deck.lwm.any():
+                assert self.lib.cales_cpu_set_wm(self.h, ia(np.asarray(deck.lwm).ravel(order="F")), float(deck.hwm)) == 0
         self.lib.cales_cpu_set_sgs(self.h, {"smag": 0, "dsmag": 1, "none": 2}[deck.sgstype.strip()])
         shp = (n[0] + 2, n[1] + 2, n[2] + 2)
         self.f = {nm: np.ctypeslib.as_array(self.lib.cales_cpu_field(self.h, i), shape=shp[::-1]).T for nm, i in FIELDS.items()}

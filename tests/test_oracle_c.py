@@ -131,7 +131,10 @@ def test_c_port_dynamic_smagorinsky_matches_numpy_oracle(case):
 WALLS = {"duct_smag": ("deck_duct", dict(ng=(16, 12, 14), sgstype="smag"), None),
          "duct_smag_3d_field": ("deck_duct", dict(ng=(12, 15, 9), sgstype="smag"), "tgv"),      # odd lengths, non-trivial pressure
          "cavity_smag": ("deck_cavity", dict(ng=(12, 12, 12), sgstype="smag"), None),
-         "cavity_smag_odd": ("deck_cavity", dict(ng=(16, 10, 15), sgstype="smag"), None)}
+         "cavity_smag_odd": ("deck_cavity", dict(ng=(16, 10, 15), sgstype="smag"), None),
+         # log-law wall model on the y AND z walls of the duct (cmpt_wallmodelbc case(2) and case(3), wmodel.f90:171-271)
+         "duct_wm_smag": ("deck_duct", dict(ng=(8, 12, 12), sgstype="smag", wall_model=True), None),
+         "duct_wm_smag_3d_field": ("deck_duct", dict(ng=(12, 20, 24), sgstype="smag", wall_model=True), "tgv")}
 
 
 @pytest.mark.parametrize("case", list(WALLS))
@@ -146,13 +149,16 @@ def test_c_port_duct_and_cavity_match_numpy_oracle(case):
     o, c = Sim(d), CSim(d)
     try:
         for nm, on in PAIRS[:4]:
-            assert np.array_equal(c.f[nm], getattr(o, on)[0]), nm
+            if d.lwm.any():        # the wall-model ghosts go through log / exp: libm vs numpy may differ in the last bit
+                assert np.abs(c.f[nm] - getattr(o, on)[0]).max() <= 4e-16 * max(np.abs(getattr(o, on)[0]).max(), 1.), nm
+            else:
+                assert np.array_equal(c.f[nm], getattr(o, on)[0]), nm
         assert np.abs(c.f["visct"] - o.VISCT[0]).max() <= 4e-16 * np.abs(o.VISCT[0]).max()
         assert abs(c.dt - o.dt) <= 1e-15 * o.dt
         for _ in range(3):
             divo = o.step(icheck=1)
             divc = c.step(icheck=1)
-        assert divc < 1e-12 and divo[1] < 1e-12
+        assert divc < 1e-11 and divo[1] < 1e-11
         vs = max(np.abs(getattr(o, on)[0]).max() for on in ("U", "V", "W"))
         for nm, on in PAIRS:
             a = c.f[nm][1:-1, 1:-1, 1:-1]
@@ -195,15 +201,17 @@ def test_c_port_refuses_what_it_does_not_cover():
     assert CSim.kind(nd) is None
     assert CSim.kind(op.deck_duct(ng=(8, 8, 8))) == "walls" and CSim.kind(op.deck_cavity(ng=(8, 8, 8))) == "walls"
     assert CSim.kind(op.deck_duct(ng=(8, 8, 8), sgstype="dsmag")) is None          # dynamic model: periodic x and y only
-    assert CSim.kind(op.deck_duct(ng=(8, 8, 8), wall_model=True)) is None          # wall model: z walls only
+    assert CSim.kind(op.deck_duct(ng=(8, 8, 8), wall_model=True)) == "walls"       # wall model on y and z walls
+    cv = op.deck_cavity(ng=(8, 8, 8)); cv.lwm[:, 0] = 1                            # wall model on x walls: not restated in C
+    assert CSim.kind(cv) is None
     assert CSim.kind(op.deck_tgv(ng=(8, 8, 8))) == "periodic"
     with pytest.raises(AssertionError):
-        CSim(op.deck_duct(ng=(8, 8, 8), wall_model=True))
+        CSim(cv)
 
 
 def test_two_restatements_agree_on_the_reference_example_decks():
     """every input.nml the reference ships (examples/dns, examples/les), shrunk to 16 x 12 x 14 on one rank: the decks the C
-    restatement covers (all but the inflow/outflow ones, which need DCT-IV, and the wall-modelled duct) run two RK3 steps in both
+    restatement covers (all but the two inflow/outflow ones, which need DCT-IV) run two RK3 steps in both
     restatements -- moving walls, free-slip lids, body forces, constant-pressure-gradient and bulk-velocity forcing, every
     initial condition incl. the noisy ones -- and agree to round-off"""
     import glob
@@ -215,7 +223,7 @@ def test_two_restatements_agree_on_the_reference_example_decks():
         d = op.read_input(f)
         d.dims = (1, 1); d.ng = (16, 12, 14)
         if CSim.kind(d) is None:
-            assert "developing_" in f or "duct_wall_model" in f, f
+            assert "developing_" in f, f
             continue
         covered += 1
         o, c = Sim(d), CSim(d)
@@ -232,4 +240,4 @@ def test_two_restatements_agree_on_the_reference_example_decks():
             assert abs(c.dt - o.dt) <= 1e-12 * o.dt, f
         finally:
             c.close()
-    assert covered >= 18
+    assert covered >= 19
