@@ -241,3 +241,28 @@ def test_two_restatements_agree_on_the_reference_example_decks():
         finally:
             c.close()
     assert covered >= 19
+
+
+def test_every_case_of_the_gpu_parity_table_in_both_restatements():
+    """tests/parity_mgpu.py::CASES is what the CUDA path is compared with (numpy oracle, 1e-10): the C restatement reproduces
+    each of those oracle runs (10 steps, as tests/test_gpu_step.py::test_ten_steps) to round-off"""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from parity_mgpu import CASES
+    for case, (name, kw) in CASES.items():
+        d = getattr(op, name)(**kw)
+        assert CSim.kind(d) is not None, case
+        o, c = Sim(d), CSim(d)
+        try:
+            for _ in range(10):
+                o.step(icheck=1); c.step(icheck=1)
+            vs = max(np.abs(getattr(o, on)[0]).max() for on in ("U", "V", "W"))
+            for nm, on in PAIRS:
+                a = c.f[nm][1:-1, 1:-1, 1:-1]; b = getattr(o, on)[0][1:-1, 1:-1, 1:-1]
+                if nm == "p":
+                    a = a - a.mean(); b = b - b.mean()
+                scale = vs if nm in ("u", "v", "w") else max(np.abs(b).max(), vs * vs if nm == "p" else 1e-300)
+                assert np.abs(a - b).max() / scale < 1e-11, (case, nm)
+        finally:
+            c.close()
